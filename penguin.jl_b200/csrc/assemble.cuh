@@ -1,0 +1,145 @@
+// assemble.cuh -- per-step right-hand sides, known-value elimination and state write-back.
+// Restates b_mono_unstead_diff / b_diph_unstead_diff / b_*_stead_diff (/root/reference/src/solver/diffusion.jl:45-58,
+// 146-161, 243-265, 391-420), the border rows of BC_border_mono!/diph! (src/solver.jl:417-580) and the scatter of
+// solve_system! (src/solver.jl:186-187) on the device, fused into one pass per step.
+#pragma once
+#include "operators.cuh"
+
+struct SrcSpec { const double *arr; double cst; };   // value(l) = arr ? arr[l] : cst
+__device__ __forceinline__ double src_at(const SrcSpec &s, int64_t l) { return s.arr ? s.arr[l] : s.cst; }
+
+struct StepCoef {
+    double cV;     // 1 unsteady / 0 steady
+    double c;      // implicit coefficient on D G'W!(..): dt (BE), dt/2 (CN), 1 (steady)
+    double ce;     // explicit coefficient: dt/2 (CN) else 0
+    double c2;     // mono interface row scale: dt/2 (CN) else 1
+    double wf0, wf1;  // source weights: V * (wf0 f(t_n) + wf1 f(t_n+dt))  -- BE (0,dt) CN (dt/2,dt/2) steady (1,0)
+    double wg0, wg1;  // mono interface data weights: g_eff = wg0 g0 + wg1 g1 -- BE (0,1) CN (1,1) steady (1,0)
+    int cn;        // 1: Crank-Nicolson
+    int sym;       // symmetrised rows (CG path)
+};
+
+// mono, Dirichlet interface: kept T_gamma values. BE/steady: g ; CN: g0 + g1 - T_gamma^n (row 2 of diffusion.jl:227,258)
+__global__ void k_gamma_known(Grid g, StepCoef sc, const unsigned char *__restrict__ m, SrcSpec g0, SrcSpec g1, const double *__restrict__ Tg,
+                              double *__restrict__ gK)
+{
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (m[l] & MB_IKNOWN) {
+            v = sc.wg0 * src_at(g0, l) + sc.wg1 * src_at(g1, l);
+            if (sc.cn) v -= Tg[l];
+        }
+        gK[l] = v;
+    }
+}
+
+template <int N>
+__global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m, const double *__restrict__ Tw,
+                           const double *__restrict__ Tg, const double *__restrict__ ufix, const double *__restrict__ gK, SrcSpec f0, SrcSpec f1,
+                           SrcSpec g0, SrcSpec g1, double *__restrict__ bb, double *__restrict__ bi)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        const unsigned char mb = m[l];
+        const bool wb = mb & MB_FREE, wi = bi && (mb & MB_IFREE);
+        if (!wb && !wi) { bb[l] = 0.0; if (bi) bi[l] = 0.0; continue; }
+        const double D = D_at(p, l), V = p.V[l], Gm = p.Gam[l];
+        double Rbk, Rik, Rbe = 0.0, Rie = 0.0;
+        GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
+        phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
+        if (sc.cn) {
+            GamSpec ge = {Tg, 1.0, nullptr, 0.0, 0.0};
+            phase_rows<N>(p, g, l, c, Tw, ge, Rbe, Rie);
+        }
+        if (wb) {
+            double v = sc.cV * V * Tw[l] + V * (sc.wf0 * src_at(f0, l) + sc.wf1 * src_at(f1, l)) - sc.ce * D * Rbe
+                       - (sc.cV * V * ufix[l] + sc.c * D * Rbk);
+            if (sc.sym) v /= D;
+            bb[l] = v;
+        } else bb[l] = 0.0;
+        if (bi) {
+            if (wi) {
+                const double gKl = gK ? gK[l] : 0.0;
+                double v = sc.c2 * Gm * (sc.wg0 * src_at(g0, l) + sc.wg1 * src_at(g1, l))
+                           - sc.ce * (sp.beta * Rie + sp.alpha * Gm * (sc.cn ? Tg[l] : 0.0))
+                           - sc.c2 * (sp.beta * Rik + sp.alpha * Gm * gKl);
+                if (sc.sym) v *= sc.c / (sc.c2 * sp.beta);
+                bi[l] = v;
+            } else bi[l] = 0.0;
+        }
+    }
+}
+
+// diph: known gamma1 = g / a1 everywhere (row 2), gamma2 known part = 0
+template <int N>
+__global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m1,
+                           const unsigned char *__restrict__ m2, const double *__restrict__ Tw1, const double *__restrict__ Tg1,
+                           const double *__restrict__ Tw2, const double *__restrict__ Tg2, const double *__restrict__ ufix1,
+                           const double *__restrict__ ufix2, SrcSpec f10, SrcSpec f11, SrcSpec f20, SrcSpec f21, SrcSpec gj, SrcSpec hj,
+                           double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        const unsigned char a = m1[l], b = m2[l];
+        const bool w1 = a & MB_FREE, w2 = b & MB_FREE, ww = b & MB_IFREE;
+        if (!w1 && !w2 && !ww) { b1[l] = 0.0; b2[l] = 0.0; bw[l] = 0.0; continue; }
+        GamSpec gk1 = {gj.arr, 1.0 / sp.a1, nullptr, 0.0, gj.arr ? 0.0 : gj.cst / sp.a1};
+        GamSpec gk2 = {nullptr, 0.0, nullptr, 0.0, 0.0};
+        double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0, Rbe1 = 0, Rie1 = 0, Rbe2 = 0, Rie2 = 0;
+        if (w1 || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
+        if (w2 || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
+        if (sc.cn) {
+            GamSpec ge1 = {Tg1, 1.0, nullptr, 0.0, 0.0}, ge2 = {Tg2, 1.0, nullptr, 0.0, 0.0};
+            if (w1) phase_rows<N>(p1, g, l, c, Tw1, ge1, Rbe1, Rie1);
+            if (w2) phase_rows<N>(p2, g, l, c, Tw2, ge2, Rbe2, Rie2);
+        }
+        const double V1 = p1.V[l], V2 = p2.V[l];
+        b1[l] = w1 ? sc.cV * V1 * Tw1[l] + V1 * (sc.wf0 * src_at(f10, l) + sc.wf1 * src_at(f11, l)) - sc.ce * D_at(p1, l) * Rbe1
+                         - (sc.cV * V1 * ufix1[l] + sc.c * D_at(p1, l) * Rbk1)
+                   : 0.0;
+        b2[l] = w2 ? sc.cV * V2 * Tw2[l] + V2 * (sc.wf0 * src_at(f20, l) + sc.wf1 * src_at(f21, l)) - sc.ce * D_at(p2, l) * Rbe2
+                         - (sc.cV * V2 * ufix2[l] + sc.c * D_at(p2, l) * Rbk2)
+                   : 0.0;
+        bw[l] = ww ? p2.Gam[l] * src_at(hj, l) - (sp.b1 * Rik1 + sp.b2 * Rik2) : 0.0;
+    }
+}
+
+// initial guess: previous state restricted to the free sets (warm) or zero
+__global__ void k_guess(Grid g, int warm, const unsigned char *__restrict__ m, unsigned char bit, const double *__restrict__ T, double *__restrict__ x)
+{
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x)
+        x[l] = (warm && (m[l] & bit)) ? T[l] : 0.0;
+}
+
+// state write-back (solve_system!: removed DOFs are exactly 0; border rows hold their value)
+__global__ void k_store_bulk(Grid g, const double *__restrict__ x, const double *__restrict__ ufix, double *__restrict__ T)
+{
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x)
+        T[l] = x[l] + ufix[l];
+}
+// diph: T_gamma2 = w ; T_gamma1 = (g + a2 w) / a1 on every cell
+__global__ void k_store_diph_ifc(Grid g, SysParams sp, SrcSpec gj, const double *__restrict__ w, double *__restrict__ Tg1, double *__restrict__ Tg2)
+{
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
+        const double wv = w[l];
+        Tg2[l] = wv;
+        Tg1[l] = (src_at(gj, l) + sp.a2 * wv) / sp.a1;
+    }
+}
+
+// DOF census: [0] bulk kept (free + fixed, all phases), [1] interface kept
+__global__ void k_count(Grid g, const unsigned char *__restrict__ m1, const unsigned char *__restrict__ m2, double *partials, double *results,
+                        unsigned *counter)
+{
+    double v[2] = {0.0, 0.0};
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char a = m1[l], b = m2 ? m2[l] : 0;
+        v[0] += ((a & (MB_FREE | MB_FIXED)) ? 1.0 : 0.0) + ((b & (MB_FREE | MB_FIXED)) ? 1.0 : 0.0);
+        v[1] += ((a & (MB_IFREE | MB_IKNOWN)) ? 1.0 : 0.0) + ((b & MB_IFREE) ? 1.0 : 0.0);
+    }
+    block_reduce_publish<2>(v, partials, results, counter);
+}

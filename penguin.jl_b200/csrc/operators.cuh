@@ -1,0 +1,335 @@
+// operators.cuh -- matrix-free G / H / W-dagger stencils (the sparse products of /root/reference/src/operators.jl:127-158
+// and the block rows of /root/reference/src/solver/diffusion.jl:30-43, 104-144, 212-241, 334-389 are never assembled).
+//
+// Per phase and direction d, with i-1 the neighbour in direction d (checked against the sparse
+// definition by tests/test_operators.py):
+//     e_i      = 0 on the last padded index of direction d, else 1          (delta_m zeroes D[n,n], operators.jl:9)
+//     q_{d,i}  = W!_{d,i} [ e_i B_i u_i - B_{i-1} u_{i-1} + e_i (A_i - B_i) g_i - (A_i - B_{i-1}) g_{i-1} ]
+//     (G'q)_i  = B_i ( e_i q_{d,i} - q_{d,i+1} )
+//     (H'q)_i  = e_i (A_i - B_i) q_{d,i} - (A_{i+1} - B_i) q_{d,i+1}
+// Faces i = 0 (no i-1 terms) and i = n_d (W! = 1 where W = 0) are included exactly as the reference includes them.
+#pragma once
+#include "common.cuh"
+
+struct PhaseDev {
+    const double *V, *Gam;
+    const double *A[PB_MAXD], *B[PB_MAXD], *Wd[PB_MAXD];
+    const double *Darr;  // per-cell D or nullptr
+    double Dc;           // constant D when Darr == nullptr
+};
+
+// gamma "spec": value(l) = scale * (ptr ? ptr[l] : 0) + (off_ptr ? off_scale * off_ptr[l] : 0) + cst
+struct GamSpec {
+    const double *ptr; double scale;
+    const double *off_ptr; double off_scale;
+    double cst;
+};
+__device__ __forceinline__ double gam_at(const GamSpec &s, int64_t l)
+{
+    double v = s.cst;
+    if (s.ptr) v += s.scale * s.ptr[l];
+    if (s.off_ptr) v += s.off_scale * s.off_ptr[l];
+    return v;
+}
+
+// raw rows of one phase at local index l (global coords c): Rb = [G' W! (G u + H g)]_l,  Ri = [H' W! (G u + H g)]_l
+template <int N>
+__device__ __forceinline__ void phase_rows(const PhaseDev &ph, const Grid &g, int64_t l, const int c[PB_MAXD], const double *__restrict__ u,
+                                           const GamSpec &gs, double &Rb, double &Ri)
+{
+    Rb = 0.0; Ri = 0.0;
+    const double ui = u ? u[l] : 0.0;
+    const double gi = gam_at(gs, l);
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int64_t s = g.stride[d];
+        const int id = c[d], last = g.pd[d] - 1;
+        const double *__restrict__ A = ph.A[d], *__restrict__ B = ph.B[d], *__restrict__ W = ph.Wd[d];
+        const double bi = B[l], ai = A[l];
+        const double ei = id < last ? 1.0 : 0.0;
+        // lower face (d, i)
+        double qL = ei * (bi * ui + (ai - bi) * gi);
+        if (id > 0) {
+            const double bm = B[l - s];
+            qL -= bm * (u ? u[l - s] : 0.0) + (ai - bm) * gam_at(gs, l - s);
+        }
+        qL *= W[l];
+        // upper face (d, i+1)
+        double qU = 0.0, hpU = 0.0;
+        if (id < last) {
+            const double bp = B[l + s], ap = A[l + s];
+            const double ep = id + 1 < last ? 1.0 : 0.0;
+            hpU = ap - bi;
+            qU = W[l + s] * (ep * (bp * (u ? u[l + s] : 0.0) + (ap - bp) * gam_at(gs, l + s)) - bi * ui - hpU * gi);
+        }
+        Rb += bi * (ei * qL - qU);
+        Ri += ei * (ai - bi) * qL - hpU * qU;
+    }
+}
+
+// diagonal entries: GG_ll = sum_d B_l^2 (e_l W!_l + W!_{l+1}),  HH_ll = sum_d e_l (A_l-B_l)^2 W!_l + (A_{l+1}-B_l)^2 W!_{l+1}
+// also the "row of H' is nonzero" predicate used by the reference's zero-row trimming (src/solver.jl:59-78)
+template <int N>
+__device__ __forceinline__ void phase_diag(const PhaseDev &ph, const Grid &g, int64_t l, const int c[PB_MAXD], double &GG, double &HH, bool &rowG,
+                                           bool &hrow)
+{
+    GG = 0.0; HH = 0.0; rowG = false; hrow = false;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int64_t s = g.stride[d];
+        const int id = c[d], last = g.pd[d] - 1;
+        const double bi = ph.B[d][l], ai = ph.A[d][l];
+        const double ei = id < last ? 1.0 : 0.0;
+        const double hm = ei * (ai - bi);
+        double wU = 0.0, hp = 0.0;
+        if (id < last) { wU = ph.Wd[d][l + s]; hp = ph.A[d][l + s] - bi; }
+        const double wL = ph.Wd[d][l];
+        GG += bi * bi * (ei * wL + wU);
+        HH += hm * hm * wL + hp * hp * wU;
+        rowG = rowG || (bi != 0.0);
+        hrow = hrow || (hm != 0.0) || (hp != 0.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// mask bits (one byte per local cell and phase)
+// ------------------------------------------------------------------------------------------------------------
+#define MB_FREE 1   // bulk unknown solved for
+#define MB_FIXED 2  // bulk unknown pinned by a border Dirichlet row
+#define MB_IFREE 4  // interface unknown solved for (mono Robin/Neumann: T_gamma ; diph: T_gamma2)
+#define MB_IKNOWN 8 // mono Dirichlet interface: T_gamma = g kept by the reference's trimming (Gamma != 0)
+
+struct BorderDev {
+    int kind[6];
+    double value[6];
+    const double *values[6];  // device arrays (one entry per real cell of the side) or nullptr
+};
+
+// reference key of a real border cell (src/solver.jl:379-409): dim2 first, then dim1, then dim3; -1 if interior
+__device__ __forceinline__ int border_key(const Grid &g, const int c[PB_MAXD])
+{
+    if (g.N >= 2) {
+        if (c[1] == 0) return PB200_LEFT;
+        if (c[1] == g.nc[1] - 1) return PB200_RIGHT;
+    }
+    if (c[0] == 0) return PB200_BOTTOM;
+    if (c[0] == g.nc[0] - 1) return PB200_TOP;
+    if (g.N >= 3) {
+        if (c[2] == 0) return PB200_BACKWARD;
+        if (c[2] == g.nc[2] - 1) return PB200_FORWARD;
+    }
+    return -1;
+}
+// index of a border cell inside its side array (other dims, x fastest)
+__device__ __forceinline__ int64_t side_index(const Grid &g, int key, const int c[PB_MAXD])
+{
+    const int dim = (key == PB200_LEFT || key == PB200_RIGHT) ? 1 : (key == PB200_BOTTOM || key == PB200_TOP) ? 0 : 2;
+    int64_t idx = 0, str = 1;
+    for (int d = 0; d < g.N; ++d) {
+        if (d == dim) continue;
+        idx += (int64_t)c[d] * str;
+        str *= g.nc[d];
+    }
+    return idx;
+}
+
+struct SysParams {
+    int phase_type, time_type, ifc_kind;
+    double alpha, beta;            // mono
+    double a1, a2, b1, b2;         // diph
+};
+
+// masks + pinned border values.  mono: phase 0 only.  (BC_border_mono!/diph!, remove_zero_rows_cols!)
+template <int N>
+__global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__restrict__ ct1, const double *__restrict__ ct2, SysParams sp,
+                              BorderDev bd, unsigned char *__restrict__ m1, unsigned char *__restrict__ m2, double *__restrict__ ufix1,
+                              double *__restrict__ ufix2)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        bool real = true;
+        for (int d = 0; d < N; ++d) real = real && (c[d] < g.nc[d]);
+        int key = real ? border_key(g, c) : -1;
+        bool dirichlet = key >= 0 && bd.kind[key] == PB200_BC_DIRICHLET;
+        double bval = 0.0;
+        if (dirichlet) bval = bd.values[key] ? bd.values[key][side_index(g, key, c)] : bd.value[key];
+        const bool unsteady = sp.time_type == PB200_UNSTEADY;
+        double GG, HH;
+        bool rowG, hrow1, hrow2 = false;
+        phase_diag<N>(p1, g, l, c, GG, HH, rowG, hrow1);
+        unsigned char b1 = 0, b2 = 0;
+        bool kept1 = (unsteady && p1.V[l] != 0.0) || rowG;
+        if (sp.phase_type == PB200_MONO) {
+            if (dirichlet) { b1 |= MB_FIXED; ufix1[l] = bval; }
+            else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
+            bool keptI = (sp.beta != 0.0 && hrow1) || (sp.alpha != 0.0 && p1.Gam[l] != 0.0);
+            if (keptI) b1 |= (sp.beta != 0.0 ? MB_IFREE : MB_IKNOWN);
+            m1[l] = b1;
+        } else {
+            bool rowG2;
+            phase_diag<N>(p2, g, l, c, GG, HH, rowG2, hrow2);
+            bool kept2 = (unsteady && p2.V[l] != 0.0) || rowG2;
+            bool d1 = dirichlet && ct1[l] != 0.0, d2 = dirichlet && ct2[l] != 0.0;   // src/solver.jl:573-576
+            if (d1) { b1 |= MB_FIXED; ufix1[l] = bval; } else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
+            if (d2) { b2 |= MB_FIXED; ufix2[l] = bval; } else { if (kept2) b2 |= MB_FREE; ufix2[l] = 0.0; }
+            bool keptI = (sp.b1 != 0.0 && hrow1) || (sp.b2 != 0.0 && hrow2);
+            if (keptI) b2 |= MB_IFREE;   // T_gamma2 is the interface unknown; T_gamma1 = (g + a2 T_gamma2) / a1 everywhere
+            m1[l] = b1; m2[l] = b2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// general block-row kernels
+// ------------------------------------------------------------------------------------------------------------
+struct ApplyCoef {
+    double cV;    // coefficient of V (1 unsteady, 0 steady)
+    double c;     // theta * dt (1 for steady): multiplies D G' W! (...)
+    double c2;    // mono interface-row scale (dt/2 for CN, else 1)
+    int sym;      // 1: rows scaled to make the mono system symmetric (bulk rows / D_i, interface rows * c/(c2 beta))
+    int masked;   // 1: outputs restricted to free rows (Krylov operator); 0: all rows (known-part / explicit products)
+};
+
+__device__ __forceinline__ double D_at(const PhaseDev &p, int64_t l) { return p.Darr ? p.Darr[l] : p.Dc; }
+
+// mono: y_b = cV V u + c D Rb ; y_i = c2 (beta Ri + alpha Gamma gam)
+template <int N>
+__global__ void k_apply_mono(Grid g, PhaseDev p, SysParams sp, ApplyCoef ac, const unsigned char *__restrict__ m, const double *__restrict__ u,
+                             GamSpec gs, double *__restrict__ yb, double *__restrict__ yi)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        const unsigned char mb = m[l];
+        const bool wb = !ac.masked || (mb & MB_FREE), wi = yi && (!ac.masked || (mb & MB_IFREE));
+        double Rb = 0.0, Ri = 0.0;
+        if (wb || wi) phase_rows<N>(p, g, l, c, u, gs, Rb, Ri);
+        const double D = D_at(p, l);
+        if (wb) {
+            double v = ac.cV * p.V[l] * (u ? u[l] : 0.0) + ac.c * D * Rb;
+            if (ac.sym) v /= D;
+            yb[l] = v;
+        } else yb[l] = 0.0;
+        if (yi) {
+            if (wi) {
+                double v = ac.c2 * (sp.beta * Ri + sp.alpha * p.Gam[l] * gam_at(gs, l));
+                if (ac.sym) v *= ac.c / (ac.c2 * sp.beta);
+                yi[l] = v;
+            } else yi[l] = 0.0;
+        }
+    }
+}
+
+// diph: y1 = cV V1 u1 + c D1 Rb1(u1, g1) ; y2 = cV V2 u2 + c D2 Rb2(u2, g2) ; yw = b1 Ri1 + b2 Ri2
+template <int N>
+__global__ void k_apply_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, ApplyCoef ac, const unsigned char *__restrict__ m1,
+                             const unsigned char *__restrict__ m2, const double *__restrict__ u1, GamSpec g1, const double *__restrict__ u2, GamSpec g2,
+                             double *__restrict__ y1, double *__restrict__ y2, double *__restrict__ yw)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        const unsigned char a = m1[l], b = m2[l];
+        const bool w1 = !ac.masked || (a & MB_FREE), w2 = !ac.masked || (b & MB_FREE), ww = !ac.masked || (b & MB_IFREE);
+        double Rb1 = 0.0, Ri1 = 0.0, Rb2 = 0.0, Ri2 = 0.0;
+        if (w1 || ww) phase_rows<N>(p1, g, l, c, u1, g1, Rb1, Ri1);
+        if (w2 || ww) phase_rows<N>(p2, g, l, c, u2, g2, Rb2, Ri2);
+        y1[l] = w1 ? ac.cV * p1.V[l] * (u1 ? u1[l] : 0.0) + ac.c * D_at(p1, l) * Rb1 : 0.0;
+        y2[l] = w2 ? ac.cV * p2.V[l] * (u2 ? u2[l] : 0.0) + ac.c * D_at(p2, l) * Rb2 : 0.0;
+        yw[l] = ww ? sp.b1 * Ri1 + sp.b2 * Ri2 : 0.0;
+    }
+}
+
+// Jacobi diagonals of the (masked) Krylov operators; entries of non-free rows are set to 1
+template <int N>
+__global__ void k_diag_mono(Grid g, PhaseDev p, SysParams sp, ApplyCoef ac, const unsigned char *__restrict__ m, double *__restrict__ db,
+                            double *__restrict__ di)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        double GG, HH; bool r, h;
+        phase_diag<N>(p, g, l, c, GG, HH, r, h);
+        const double D = D_at(p, l);
+        double vb = ac.cV * p.V[l] + ac.c * D * GG;
+        if (ac.sym) vb /= D;
+        db[l] = (m[l] & MB_FREE) ? vb : 1.0;
+        if (di) {
+            double vi = ac.c2 * (sp.beta * HH + sp.alpha * p.Gam[l]);
+            if (ac.sym) vi *= ac.c / (ac.c2 * sp.beta);
+            di[l] = (m[l] & MB_IFREE) ? vi : 1.0;
+        }
+    }
+}
+template <int N>
+__global__ void k_diag_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, ApplyCoef ac, const unsigned char *__restrict__ m1,
+                            const unsigned char *__restrict__ m2, double *__restrict__ d1, double *__restrict__ d2, double *__restrict__ dw)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        double GG1, HH1, GG2, HH2; bool r, h;
+        phase_diag<N>(p1, g, l, c, GG1, HH1, r, h);
+        phase_diag<N>(p2, g, l, c, GG2, HH2, r, h);
+        d1[l] = (m1[l] & MB_FREE) ? ac.cV * p1.V[l] + ac.c * D_at(p1, l) * GG1 : 1.0;
+        d2[l] = (m2[l] & MB_FREE) ? ac.cV * p2.V[l] + ac.c * D_at(p2, l) * GG2 : 1.0;
+        dw[l] = (m2[l] & MB_IFREE) ? sp.b1 * (sp.a2 / sp.a1) * HH1 + sp.b2 * HH2 : 1.0;
+    }
+}
+
+// grad = W! (G p_omega + H p_gamma)  -- one direction per blockIdx.y  (src/operators.jl:20-23)
+template <int N>
+__global__ void k_grad(Grid g, PhaseDev p, const double *__restrict__ u, const double *__restrict__ gam, double *__restrict__ out /* N * nloc */)
+{
+    const int d = blockIdx.y;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane, s = g.stride[d];
+        const double bi = p.B[d][l], ai = p.A[d][l];
+        const double ei = c[d] < g.pd[d] - 1 ? 1.0 : 0.0;
+        double q = ei * (bi * u[l] + (ai - bi) * gam[l]);
+        if (c[d] > 0) { const double bm = p.B[d][l - s]; q -= bm * u[l - s] + (ai - bm) * gam[l - s]; }
+        out[(int64_t)d * g.nloc + l] = p.Wd[d][l] * q;
+    }
+}
+// div = -(G'+H') q_omega + H' q_gamma  (src/operators.jl:30-34); q_* are N * nloc face fields
+template <int N>
+__global__ void k_div(Grid g, PhaseDev p, const double *__restrict__ qo, const double *__restrict__ qg, double *__restrict__ out)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        double acc = 0.0;
+        for (int d = 0; d < N; ++d) {
+            const int64_t s = g.stride[d], o = (int64_t)d * g.nloc;
+            const int last = g.pd[d] - 1;
+            const double bi = p.B[d][l], ai = p.A[d][l];
+            const double ei = c[d] < last ? 1.0 : 0.0;
+            const double hm = ei * (ai - bi);
+            double hp = 0.0, qoU = 0.0, qgU = 0.0;
+            if (c[d] < last) { hp = p.A[d][l + s] - bi; qoU = qo[o + l + s]; qgU = qg[o + l + s]; }
+            const double GTo = bi * (ei * qo[o + l] - qoU);
+            const double HTo = hm * qo[o + l] - hp * qoU;
+            const double HTg = hm * qg[o + l] - hp * qgU;
+            acc += -(GTo + HTo) + HTg;
+        }
+        out[l] = acc;
+    }
+}
+
+// W! from W (1/W, 1.0 where W == 0) -- src/operators.jl:145-152
+__global__ void k_wdag(int64_t n, const double *__restrict__ W, double *__restrict__ Wd)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double w = W[i];
+        Wd[i] = w != 0.0 ? 1.0 / w : 1.0;
+    }
+}

@@ -1,0 +1,720 @@
+// penguin_b200.cu -- C ABI of libpenguin_b200.so (see include/penguin_b200.h for the reference citations).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC penguin_b200.cu -o libpenguin_b200.so
+#include "common.cuh"
+#include "operators.cuh"
+#include "krylov.cuh"
+#include "assemble.cuh"
+#include "geometry.cuh"
+
+#define DISPATCH_N(N_, ...)                  \
+    do {                                     \
+        if ((N_) == 1) { constexpr int N = 1; __VA_ARGS__; } \
+        else if ((N_) == 2) { constexpr int N = 2; __VA_ARGS__; } \
+        else { constexpr int N = 3; __VA_ARGS__; } \
+    } while (0)
+
+// =================================================================================================================
+// lifecycle
+// =================================================================================================================
+static int ctx_common_init(pb200_ctx *c, int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, PB200_ENODEV, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                                  " (libpenguin_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(nullptr, PB200_EINVAL, "bad device index");
+    c->device = device;
+    CUDA_TRY(c, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(c, cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaMalloc((void **)&c->d_partials, sizeof(double) * RED_MAXK * RED_MAXBLOCKS));
+    CUDA_TRY(c, cudaMalloc((void **)&c->d_results, sizeof(double) * RED_SLOTS));
+    CUDA_TRY(c, cudaMalloc((void **)&c->d_counter, sizeof(unsigned)));
+    CUDA_TRY(c, cudaMemset(c->d_counter, 0, sizeof(unsigned)));
+    CUDA_TRY(c, cudaMemset(c->d_results, 0, sizeof(double) * RED_SLOTS));
+    CUDA_TRY(c, cudaMallocHost((void **)&c->h_results, sizeof(double) * RED_SLOTS));
+    CUDA_TRY(c, cudaEventCreate(&c->ev0));
+    CUDA_TRY(c, cudaEventCreate(&c->ev1));
+    CUDA_TRY(c, cudaEventCreate(&c->ev2));
+    return PB200_OK;
+}
+
+extern "C" int pb200_init(pb200_ctx **ctx, int device)
+{
+    if (!ctx) return set_err(nullptr, PB200_EINVAL, "ctx is NULL");
+    pb200_ctx *c = new pb200_ctx();
+    int rc = ctx_common_init(c, device);
+    if (rc) { delete c; return rc; }
+    *ctx = c;
+    return PB200_OK;
+}
+
+extern "C" int pb200_nccl_unique_id(char id[128])
+{
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    pb_ncclUniqueId u;
+    NCCL_TRY(nullptr, g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return PB200_OK;
+}
+
+extern "C" int pb200_init_dist(pb200_ctx **ctx, int device, int rank, int nranks, const char nccl_id[128])
+{
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return set_err(nullptr, PB200_EINVAL, "bad rank/nranks");
+    pb200_ctx *c = new pb200_ctx();
+    int rc = ctx_common_init(c, device);
+    if (rc) { delete c; return rc; }
+    c->rank = rank; c->nranks = nranks;
+    if (nranks > 1) {
+        rc = nccl_load(c);
+        if (rc) { delete c; return rc; }
+        pb_ncclUniqueId u;
+        memcpy(u.internal, nccl_id, 128);
+        int r = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
+        if (r != 0) { std::string m = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); delete c; return set_err(nullptr, PB200_ENCCL, m); }
+    }
+    *ctx = c;
+    return PB200_OK;
+}
+
+extern "C" int pb200_finalize(pb200_ctx *c)
+{
+    if (!c) return PB200_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_partials); cudaFree(c->d_results); cudaFree(c->d_counter); cudaFreeHost(c->h_results);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return PB200_OK;
+}
+extern "C" const char *pb200_last_error(pb200_ctx *c) { return c ? c->err.c_str() : g_last_error.c_str(); }
+extern "C" int pb200_sync(pb200_ctx *c) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return PB200_OK; }
+extern "C" int64_t pb200_launch_count(pb200_ctx *c) { return c ? c->launches : 0; }
+extern "C" uint64_t pb200_stream(pb200_ctx *c) { return (uint64_t)(uintptr_t)c->stream; }
+
+// =================================================================================================================
+// Capacity
+// =================================================================================================================
+struct pb200_capacity {
+    pb200_ctx *ctx;
+    Grid g;
+    double *V = nullptr, *Gam = nullptr, *ct = nullptr;
+    double *A[PB_MAXD] = {}, *B[PB_MAXD] = {}, *W[PB_MAXD] = {}, *Co[PB_MAXD] = {}, *Cg[PB_MAXD] = {};
+    bool has_cg = false;
+};
+
+static int cap_alloc(pb200_ctx *ctx, pb200_capacity *c)
+{
+    int rc;
+    const Grid &g = c->g;
+    if ((rc = dev_alloc(ctx, &c->V, g.nloc))) return rc;
+    if ((rc = dev_alloc(ctx, &c->Gam, g.nloc))) return rc;
+    if ((rc = dev_alloc(ctx, &c->ct, g.nloc))) return rc;
+    for (int d = 0; d < g.N; ++d) {
+        if ((rc = dev_alloc(ctx, &c->A[d], g.nloc))) return rc;
+        if ((rc = dev_alloc(ctx, &c->B[d], g.nloc))) return rc;
+        if ((rc = dev_alloc(ctx, &c->W[d], g.nloc))) return rc;
+        if ((rc = dev_alloc(ctx, &c->Co[d], g.nloc))) return rc;
+        if ((rc = dev_alloc(ctx, &c->Cg[d], g.nloc))) return rc;
+    }
+    return PB200_OK;
+}
+static int cap_halo(pb200_capacity *c)
+{
+    std::vector<double *> f = {c->V, c->Gam, c->ct};
+    for (int d = 0; d < c->g.N; ++d) { f.push_back(c->A[d]); f.push_back(c->B[d]); f.push_back(c->W[d]); f.push_back(c->Co[d]); }
+    return halo_exchange(c->ctx, c->g, f.data(), (int)f.size());
+}
+
+extern "C" int pb200_capacity_import(pb200_ctx *ctx, int ndim, const int *n, const double *x0, const double *L, const double *V, const double *Gamma,
+                                     const double *cell_types, const double *A, const double *B, const double *W, const double *C_omega,
+                                     const double *C_gamma, pb200_capacity **out)
+{
+    if (!ctx || !out) return set_err(ctx, PB200_EINVAL, "NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    pb200_capacity *c = new pb200_capacity();
+    c->ctx = ctx;
+    int rc = make_grid(ctx, ndim, n, x0, L, &c->g);
+    if (!rc) rc = cap_alloc(ctx, c);
+    if (rc) { delete c; return rc; }
+    const Grid &g = c->g;
+    if ((rc = upload_owned(ctx, g, c->V, V)) || (rc = upload_owned(ctx, g, c->Gam, Gamma)) || (rc = upload_owned(ctx, g, c->ct, cell_types))) return rc;
+    for (int d = 0; d < g.N; ++d) {
+        if ((rc = upload_owned(ctx, g, c->A[d], A ? A + (int64_t)d * g.nown : nullptr))) return rc;
+        if ((rc = upload_owned(ctx, g, c->B[d], B ? B + (int64_t)d * g.nown : nullptr))) return rc;
+        if ((rc = upload_owned(ctx, g, c->W[d], W ? W + (int64_t)d * g.nown : nullptr))) return rc;
+        if ((rc = upload_owned(ctx, g, c->Co[d], C_omega ? C_omega + (int64_t)d * g.nown : nullptr))) return rc;
+        if ((rc = upload_owned(ctx, g, c->Cg[d], C_gamma ? C_gamma + (int64_t)d * g.nown : nullptr))) return rc;
+    }
+    c->has_cg = C_gamma != nullptr;
+    if ((rc = cap_halo(c))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = c;
+    return PB200_OK;
+}
+
+extern "C" int pb200_capacity_create(pb200_ctx *ctx, int ndim, const int *n, const double *x0, const double *L, const pb200_levelset *ls,
+                                     int compute_centroids, pb200_capacity **out)
+{
+    if (!ctx || !out || !ls) return set_err(ctx, PB200_EINVAL, "NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    pb200_capacity *c = new pb200_capacity();
+    c->ctx = ctx;
+    int rc = make_grid(ctx, ndim, n, x0, L, &c->g);
+    if (!rc) rc = cap_alloc(ctx, c);
+    if (rc) { delete c; return rc; }
+    GeomOut go;
+    go.V = c->V; go.Gam = c->Gam; go.ct = c->ct;
+    for (int d = 0; d < PB_MAXD; ++d) { go.A[d] = c->A[d]; go.B[d] = c->B[d]; go.W[d] = c->W[d]; go.Co[d] = c->Co[d]; go.Cg[d] = c->Cg[d]; }
+    rc = geometry_build(ctx, c->g, ls, compute_centroids, go);
+    if (rc) return rc;
+    c->has_cg = compute_centroids != 0;
+    if ((rc = cap_halo(c))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = c;
+    return PB200_OK;
+}
+
+extern "C" int pb200_capacity_export(pb200_capacity *c, double *V, double *Gamma, double *cell_types, double *A, double *B, double *W, double *C_omega,
+                                     double *C_gamma)
+{
+    if (!c) return set_err(nullptr, PB200_EINVAL, "NULL capacity");
+    pb200_ctx *ctx = c->ctx;
+    const Grid &g = c->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = download_owned(ctx, g, V, c->V)) || (rc = download_owned(ctx, g, Gamma, c->Gam)) || (rc = download_owned(ctx, g, cell_types, c->ct))) return rc;
+    for (int d = 0; d < g.N; ++d) {
+        if ((rc = download_owned(ctx, g, A ? A + (int64_t)d * g.nown : nullptr, c->A[d]))) return rc;
+        if ((rc = download_owned(ctx, g, B ? B + (int64_t)d * g.nown : nullptr, c->B[d]))) return rc;
+        if ((rc = download_owned(ctx, g, W ? W + (int64_t)d * g.nown : nullptr, c->W[d]))) return rc;
+        if ((rc = download_owned(ctx, g, C_omega ? C_omega + (int64_t)d * g.nown : nullptr, c->Co[d]))) return rc;
+        if ((rc = download_owned(ctx, g, C_gamma ? C_gamma + (int64_t)d * g.nown : nullptr, c->Cg[d]))) return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+extern "C" int pb200_capacity_local(pb200_capacity *c, int *k0, int *k1, int64_t *nloc)
+{
+    if (!c) return set_err(nullptr, PB200_EINVAL, "NULL capacity");
+    if (k0) *k0 = c->g.k0;
+    if (k1) *k1 = c->g.k1;
+    if (nloc) *nloc = c->g.nown;
+    return PB200_OK;
+}
+extern "C" int pb200_capacity_destroy(pb200_capacity *c)
+{
+    if (!c) return PB200_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    dev_free(c->V); dev_free(c->Gam); dev_free(c->ct);
+    for (int d = 0; d < PB_MAXD; ++d) { dev_free(c->A[d]); dev_free(c->B[d]); dev_free(c->W[d]); dev_free(c->Co[d]); dev_free(c->Cg[d]); }
+    delete c;
+    return PB200_OK;
+}
+
+// =================================================================================================================
+// DiffusionOps
+// =================================================================================================================
+struct pb200_ops {
+    pb200_capacity *cap;
+    double *Wd[PB_MAXD] = {};
+};
+static PhaseDev phase_dev(const pb200_ops *o, const double *Darr, double Dc)
+{
+    PhaseDev p;
+    p.V = o->cap->V; p.Gam = o->cap->Gam;
+    for (int d = 0; d < PB_MAXD; ++d) { p.A[d] = o->cap->A[d]; p.B[d] = o->cap->B[d]; p.Wd[d] = o->Wd[d]; }
+    p.Darr = Darr; p.Dc = Dc;
+    return p;
+}
+static inline int sgrid(pb200_ctx *ctx, int64_t n) { return red_grid(ctx, n); }
+
+extern "C" int pb200_ops_create(pb200_capacity *cap, pb200_ops **out)
+{
+    if (!cap || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = cap->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    pb200_ops *o = new pb200_ops();
+    o->cap = cap;
+    for (int d = 0; d < cap->g.N; ++d) {
+        int rc = dev_alloc(ctx, &o->Wd[d], cap->g.nloc);
+        if (rc) return rc;
+        k_wdag<<<sgrid(ctx, cap->g.nloc), RED_THREADS, 0, ctx->stream>>>(cap->g.nloc, cap->W[d], o->Wd[d]);
+        LAUNCH_CHECK(ctx);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = o;
+    return PB200_OK;
+}
+extern "C" int pb200_ops_destroy(pb200_ops *o)
+{
+    if (!o) return PB200_OK;
+    cudaSetDevice(o->cap->ctx->device);
+    cudaStreamSynchronize(o->cap->ctx->stream);
+    for (int d = 0; d < PB_MAXD; ++d) dev_free(o->Wd[d]);
+    delete o;
+    return PB200_OK;
+}
+extern "C" int pb200_ops_export_wdag(pb200_ops *o, double *wdag)
+{
+    if (!o || !wdag) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = o->cap->ctx;
+    const Grid &g = o->cap->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int d = 0; d < g.N; ++d) { int rc = download_owned(ctx, g, wdag + (int64_t)d * g.nown, o->Wd[d]); if (rc) return rc; }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+
+extern "C" int pb200_ops_grad(pb200_ops *o, const double *p, double *out)
+{
+    if (!o || !p || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = o->cap->ctx;
+    const Grid &g = o->cap->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    double *u = nullptr, *gm = nullptr, *q = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &u, g.nloc)) || (rc = dev_alloc(ctx, &gm, g.nloc)) || (rc = dev_alloc(ctx, &q, g.nloc * g.N))) return rc;
+    if ((rc = upload_owned(ctx, g, u, p)) || (rc = upload_owned(ctx, g, gm, p + g.nown))) return rc;
+    double *fl[2] = {u, gm};
+    if ((rc = halo_exchange(ctx, g, fl, 2))) return rc;
+    PhaseDev ph = phase_dev(o, nullptr, 1.0);
+    dim3 grid(sgrid(ctx, g.nown), g.N);
+    DISPATCH_N(g.N, (k_grad<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, ph, u, gm, q)));
+    LAUNCH_CHECK(ctx);
+    for (int d = 0; d < g.N; ++d)
+        if ((rc = download_owned(ctx, g, out + (int64_t)d * g.nown, q + (int64_t)d * g.nloc))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(u); dev_free(gm); dev_free(q);
+    return PB200_OK;
+}
+extern "C" int pb200_ops_div(pb200_ops *o, const double *qo, const double *qg, double *out)
+{
+    if (!o || !qo || !qg || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = o->cap->ctx;
+    const Grid &g = o->cap->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    double *a = nullptr, *b = nullptr, *r = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &a, g.nloc * g.N)) || (rc = dev_alloc(ctx, &b, g.nloc * g.N)) || (rc = dev_alloc(ctx, &r, g.nloc))) return rc;
+    std::vector<double *> fl;
+    for (int d = 0; d < g.N; ++d) {
+        if ((rc = upload_owned(ctx, g, a + (int64_t)d * g.nloc, qo + (int64_t)d * g.nown))) return rc;
+        if ((rc = upload_owned(ctx, g, b + (int64_t)d * g.nloc, qg + (int64_t)d * g.nown))) return rc;
+        fl.push_back(a + (int64_t)d * g.nloc); fl.push_back(b + (int64_t)d * g.nloc);
+    }
+    if ((rc = halo_exchange(ctx, g, fl.data(), (int)fl.size()))) return rc;
+    PhaseDev ph = phase_dev(o, nullptr, 1.0);
+    DISPATCH_N(g.N, (k_div<N><<<sgrid(ctx, g.nown), RED_THREADS, 0, ctx->stream>>>(g, ph, a, b, r)));
+    LAUNCH_CHECK(ctx);
+    if ((rc = download_owned(ctx, g, out, r))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(a); dev_free(b); dev_free(r);
+    return PB200_OK;
+}
+
+// =================================================================================================================
+// Solver
+// =================================================================================================================
+struct pb200_solver {
+    pb200_ctx *ctx;
+    Grid g;
+    SysParams sp;
+    pb200_ops *o1 = nullptr, *o2 = nullptr;
+    PhaseDev p1, p2;
+    double *D1arr = nullptr, *D2arr = nullptr;
+    BorderDev bd;
+    double *bvals[6] = {};
+    bool masks_dirty = true;
+    unsigned char *m1 = nullptr, *m2 = nullptr;
+    double *ufix1 = nullptr, *ufix2 = nullptr;
+    double *Tw[2] = {}, *Tg[2] = {};
+    int nf = 1;
+    MVec x, b, r, r0, p, ph, v, s, sh, t, dinv;
+    double *gK = nullptr;
+    double *fS[2][2] = {}, *gS[2] = {};
+    int64_t dof_bulk = 0, dof_ifc = 0;
+    ApplyCoef diag_key = {-1, -1, -1, -1, -1};
+    std::vector<double *> owned;
+};
+
+static int solver_vec(pb200_solver *s, MVec *v)
+{
+    for (int f = 0; f < KV_MAXF; ++f) v->f[f] = nullptr;
+    for (int f = 0; f < s->nf; ++f) {
+        int rc = dev_alloc(s->ctx, &v->f[f], s->g.nloc);
+        if (rc) return rc;
+        s->owned.push_back(v->f[f]);
+    }
+    return PB200_OK;
+}
+
+extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, pb200_solver **out)
+{
+    if (!ctx || !d || !out || !d->ops1) return set_err(ctx, PB200_EINVAL, "NULL argument");
+    if (d->phase_type == PB200_DIPH && !d->ops2) return set_err(ctx, PB200_EINVAL, "diphasic solver needs ops2");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    pb200_solver *s = new pb200_solver();
+    s->ctx = ctx;
+    s->g = d->ops1->cap->g;
+    const Grid &g = s->g;
+    s->o1 = d->ops1; s->o2 = d->ops2;
+    s->sp.phase_type = d->phase_type; s->sp.time_type = d->time_type; s->sp.ifc_kind = d->ifc_kind;
+    s->sp.alpha = d->alpha; s->sp.beta = d->beta;
+    s->sp.a1 = d->alpha1; s->sp.a2 = d->alpha2; s->sp.b1 = d->beta1; s->sp.b2 = d->beta2;
+    if (d->phase_type == PB200_MONO) {
+        if (d->ifc_kind == PB200_BC_DIRICHLET) { s->sp.alpha = 1.0; s->sp.beta = 0.0; }
+        else if (d->ifc_kind == PB200_BC_NEUMANN) { s->sp.alpha = 0.0; s->sp.beta = 1.0; }
+        else if (d->ifc_kind != PB200_BC_ROBIN) return set_err(ctx, PB200_EINVAL, "mono interface condition must be Dirichlet, Neumann or Robin");
+    } else {
+        if (d->alpha1 == 0.0) return set_err(ctx, PB200_EUNSUPPORTED, "ScalarJump with alpha1 == 0 is not supported");
+        const Grid &g2 = d->ops2->cap->g;
+        if (g2.N != g.N || g2.ntot != g.ntot) return set_err(ctx, PB200_EINVAL, "phase capacities must share the same mesh");
+    }
+    int rc;
+    if (d->D1_arr) { if ((rc = dev_alloc(ctx, &s->D1arr, g.nloc)) || (rc = upload_owned(ctx, g, s->D1arr, d->D1_arr))) return rc; }
+    if (d->D2_arr) { if ((rc = dev_alloc(ctx, &s->D2arr, g.nloc)) || (rc = upload_owned(ctx, g, s->D2arr, d->D2_arr))) return rc; }
+    {
+        double *fl[2] = {s->D1arr, s->D2arr};
+        if ((rc = halo_exchange(ctx, g, fl, 2))) return rc;
+    }
+    s->p1 = phase_dev(d->ops1, s->D1arr, d->D1);
+    if (d->ops2) s->p2 = phase_dev(d->ops2, s->D2arr, d->D2); else s->p2 = s->p1;
+    for (int k = 0; k < 6; ++k) { s->bd.kind[k] = PB200_BC_NONE; s->bd.value[k] = 0.0; s->bd.values[k] = nullptr; }
+    const bool diph = d->phase_type == PB200_DIPH;
+    s->nf = diph ? 3 : (s->sp.beta != 0.0 ? 2 : 1);
+    CUDA_TRY(ctx, cudaMalloc((void **)&s->m1, (size_t)g.nloc));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->m1, 0, (size_t)g.nloc, ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc((void **)&s->m2, (size_t)g.nloc));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->m2, 0, (size_t)g.nloc, ctx->stream));
+    if ((rc = dev_alloc(ctx, &s->ufix1, g.nloc)) || (rc = dev_alloc(ctx, &s->ufix2, g.nloc))) return rc;
+    for (int ph = 0; ph < (diph ? 2 : 1); ++ph)
+        if ((rc = dev_alloc(ctx, &s->Tw[ph], g.nloc)) || (rc = dev_alloc(ctx, &s->Tg[ph], g.nloc))) return rc;
+    if ((rc = dev_alloc(ctx, &s->gK, g.nloc))) return rc;
+    MVec *vs[] = {&s->x, &s->b, &s->r, &s->r0, &s->p, &s->ph, &s->v, &s->s, &s->sh, &s->t, &s->dinv};
+    for (MVec *v : vs) if ((rc = solver_vec(s, v))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return PB200_OK;
+}
+
+extern "C" int pb200_solver_destroy(pb200_solver *s)
+{
+    if (!s) return PB200_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (double *p : s->owned) cudaFree(p);
+    dev_free(s->D1arr); dev_free(s->D2arr); dev_free(s->ufix1); dev_free(s->ufix2); dev_free(s->gK);
+    for (int k = 0; k < 6; ++k) dev_free(s->bvals[k]);
+    for (int a = 0; a < 2; ++a) { dev_free(s->Tw[a]); dev_free(s->Tg[a]); dev_free(s->gS[a]); for (int b = 0; b < 2; ++b) dev_free(s->fS[a][b]); }
+    cudaFree(s->m1); cudaFree(s->m2);
+    delete s;
+    return PB200_OK;
+}
+
+static int64_t side_cells(const Grid &g, int side)
+{
+    const int dim = (side == PB200_LEFT || side == PB200_RIGHT) ? 1 : (side == PB200_BOTTOM || side == PB200_TOP) ? 0 : 2;
+    int64_t n = 1;
+    for (int d = 0; d < g.N; ++d) if (d != dim) n *= g.nc[d];
+    return n;
+}
+
+extern "C" int pb200_solver_set_border(pb200_solver *s, int side, int kind, double value, const double *values)
+{
+    if (!s || side < 0 || side > 5) return set_err(nullptr, PB200_EINVAL, "bad side");
+    pb200_ctx *ctx = s->ctx;
+    const int dim = (side == PB200_LEFT || side == PB200_RIGHT) ? 1 : (side == PB200_BOTTOM || side == PB200_TOP) ? 0 : 2;
+    if (dim >= s->g.N) return PB200_OK;   // keys of absent dimensions never match a cell (src/solver.jl:379-409)
+    if (kind == PB200_BC_PERIODIC) return set_err(ctx, PB200_EUNSUPPORTED, "Periodic borders are not supported by libpenguin_b200 yet");
+    if (kind == PB200_BC_NEUMANN && s->g.N == 1) return set_err(ctx, PB200_EUNSUPPORTED, "1-D Neumann border rows are not supported by libpenguin_b200 yet");
+    // Neumann (>= 2-D) and Robin borders are no-ops in the reference (src/solver.jl:471-498): record as NONE
+    if (kind != PB200_BC_DIRICHLET) kind = PB200_BC_NONE;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    s->bd.kind[side] = kind;
+    s->bd.value[side] = value;
+    if (values && kind == PB200_BC_DIRICHLET) {
+        int64_t n = side_cells(s->g, side);
+        if (!s->bvals[side]) CUDA_TRY(ctx, cudaMalloc((void **)&s->bvals[side], sizeof(double) * (size_t)n));
+        CUDA_TRY(ctx, cudaMemcpyAsync(s->bvals[side], values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        s->bd.values[side] = s->bvals[side];
+    } else s->bd.values[side] = nullptr;
+    s->masks_dirty = true;
+    return PB200_OK;
+}
+
+extern "C" int pb200_solver_set_state(pb200_solver *s, const double *x)
+{
+    if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const int np = s->sp.phase_type == PB200_DIPH ? 2 : 1;
+    for (int ph = 0; ph < np; ++ph) {
+        if ((rc = upload_owned(ctx, g, s->Tw[ph], x + (int64_t)(2 * ph) * g.nown))) return rc;
+        if ((rc = upload_owned(ctx, g, s->Tg[ph], x + (int64_t)(2 * ph + 1) * g.nown))) return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+extern "C" int pb200_solver_get_state(pb200_solver *s, double *x)
+{
+    if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const int np = s->sp.phase_type == PB200_DIPH ? 2 : 1;
+    for (int ph = 0; ph < np; ++ph) {
+        if ((rc = download_owned(ctx, g, x + (int64_t)(2 * ph) * g.nown, s->Tw[ph]))) return rc;
+        if ((rc = download_owned(ctx, g, x + (int64_t)(2 * ph + 1) * g.nown, s->Tg[ph]))) return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+
+// ---- operator application on Krylov vectors ------------------------------------------------------------------------
+static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const MVec &out)
+{
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    int rc;
+    if ((rc = halo_exchange(ctx, g, in.f, s->nf))) return rc;
+    const int grid = sgrid(ctx, g.nown);
+    if (s->sp.phase_type == PB200_MONO) {
+        GamSpec gs = {s->nf == 2 ? in.f[1] : nullptr, 1.0, nullptr, 0.0, 0.0};
+        DISPATCH_N(g.N, (k_apply_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, ac, s->m1, in.f[0], gs, out.f[0],
+                                                                                 s->nf == 2 ? out.f[1] : nullptr)));
+    } else {
+        GamSpec g1 = {in.f[2], s->sp.a2 / s->sp.a1, nullptr, 0.0, 0.0};
+        GamSpec g2 = {in.f[2], 1.0, nullptr, 0.0, 0.0};
+        DISPATCH_N(g.N, (k_apply_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, ac, s->m1, s->m2, in.f[0], g1, in.f[1], g2,
+                                                                                 out.f[0], out.f[1], out.f[2])));
+    }
+    LAUNCH_CHECK(ctx);
+    return PB200_OK;
+}
+
+static int build_masks(pb200_solver *s)
+{
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    const int grid = sgrid(ctx, g.nown);
+    const double *ct1 = s->o1->cap->ct, *ct2 = s->o2 ? s->o2->cap->ct : s->o1->cap->ct;
+    DISPATCH_N(g.N, (k_build_masks<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, ct1, ct2, s->sp, s->bd, s->m1, s->m2, s->ufix1, s->ufix2)));
+    LAUNCH_CHECK(ctx);
+    double *fl[2] = {s->ufix1, s->ufix2};
+    int rc;
+    if ((rc = halo_exchange(ctx, g, fl, 2))) return rc;
+    k_count<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m1, s->sp.phase_type == PB200_DIPH ? s->m2 : nullptr, ctx->d_partials, ctx->d_results + SL_TMP,
+                                                   ctx->d_counter);
+    LAUNCH_CHECK(ctx);
+    if ((rc = allreduce_results(ctx, SL_TMP, 2))) return rc;
+    double cnt[2];
+    if ((rc = fetch_results(ctx, SL_TMP, 2, cnt))) return rc;
+    s->dof_bulk = (int64_t)(cnt[0] + 0.5);
+    s->dof_ifc = (int64_t)(cnt[1] + 0.5);
+    s->masks_dirty = false;
+    s->diag_key.cV = -1;
+    return PB200_OK;
+}
+
+static int stage_src(pb200_solver *s, double **slot, const double *host, double cst, SrcSpec *out)
+{
+    out->cst = cst; out->arr = nullptr;
+    if (!host) return PB200_OK;
+    int rc;
+    if (!*slot && (rc = dev_alloc(s->ctx, slot, s->g.nloc))) return rc;
+    if ((rc = upload_owned(s->ctx, s->g, *slot, host))) return rc;
+    out->arr = *slot;
+    return PB200_OK;
+}
+
+extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const pb200_krylov_opts *opts_in, pb200_step_stats *stats)
+{
+    if (!s || !in) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t launches0 = ctx->launches;
+    pb200_krylov_opts o = {PB200_KRYLOV_AUTO, 1e-10, 0.0, 10000, 1, 1};
+    if (opts_in) o = *opts_in;
+    if (o.maxit <= 0) o.maxit = 10000;
+    if (o.check_every <= 0) o.check_every = 1;
+    const bool diph = s->sp.phase_type == PB200_DIPH;
+    const bool unsteady = s->sp.time_type == PB200_UNSTEADY;
+    const bool cn = unsteady && in->scheme == PB200_CN;
+    int method = o.method;
+    const bool nonconstD = s->D1arr != nullptr;
+    if (method == PB200_KRYLOV_AUTO) method = diph ? PB200_KRYLOV_BICGSTAB : PB200_KRYLOV_CG;
+    if (method == PB200_KRYLOV_CG && diph) return set_err(ctx, PB200_EUNSUPPORTED, "CG on the diphasic system is not available; use BiCGSTAB");
+    (void)nonconstD;
+    int rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (s->masks_dirty && (rc = build_masks(s))) return rc;
+
+    StepCoef sc;
+    if (unsteady) {
+        if (!(in->dt > 0.0)) return set_err(ctx, PB200_EINVAL, "dt must be positive");
+        sc.cV = 1.0; sc.cn = cn ? 1 : 0;
+        sc.c = cn ? 0.5 * in->dt : in->dt; sc.ce = cn ? 0.5 * in->dt : 0.0; sc.c2 = cn ? 0.5 * in->dt : 1.0;
+        sc.wf0 = cn ? 0.5 * in->dt : 0.0; sc.wf1 = cn ? 0.5 * in->dt : in->dt;
+        sc.wg0 = cn ? 1.0 : 0.0; sc.wg1 = 1.0;
+    } else {
+        sc.cV = 0.0; sc.cn = 0; sc.c = 1.0; sc.ce = 0.0; sc.c2 = 1.0; sc.wf0 = 1.0; sc.wf1 = 0.0; sc.wg0 = 1.0; sc.wg1 = 0.0;
+    }
+    sc.sym = (method == PB200_KRYLOV_CG) ? 1 : 0;
+    ApplyCoef ac = {sc.cV, sc.c, sc.c2, sc.sym, 1};
+
+    // sources
+    SrcSpec f[2][2], gsp[2];
+    for (int ph = 0; ph < 2; ++ph)
+        for (int w = 0; w < 2; ++w)
+            if ((rc = stage_src(s, &s->fS[ph][w], in->f_arr[ph][w], in->f_const[ph][w], &f[ph][w]))) return rc;
+    for (int w = 0; w < 2; ++w)
+        if ((rc = stage_src(s, &s->gS[w], in->g_arr[w], in->g_const[w], &gsp[w]))) return rc;
+
+    const int grid = sgrid(ctx, g.nown);
+    // ghost planes of the state (stencil inputs of the explicit part)
+    {
+        double *fl[4] = {s->Tw[0], s->Tg[0], s->Tw[1], s->Tg[1]};
+        if (cn && (rc = halo_exchange(ctx, g, fl, diph ? 4 : 2))) return rc;
+    }
+    if (!diph) {
+        k_gamma_known<<<grid, RED_THREADS, 0, ctx->stream>>>(g, sc, s->m1, gsp[0], gsp[1], s->Tg[0], s->gK);
+        LAUNCH_CHECK(ctx);
+        double *fl[1] = {s->gK};
+        if ((rc = halo_exchange(ctx, g, fl, 1))) return rc;
+        DISPATCH_N(g.N, (k_rhs_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Tw[0], s->Tg[0], s->ufix1, s->gK, f[0][0],
+                                                                               f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr)));
+        LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m1, MB_FREE, s->Tw[0], s->x.f[0]);
+        LAUNCH_CHECK(ctx);
+        if (s->nf == 2) { k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m1, MB_IFREE, s->Tg[0], s->x.f[1]); LAUNCH_CHECK(ctx); }
+    } else {
+        if (gsp[0].arr) { double *fl[1] = {s->gS[0]}; if ((rc = halo_exchange(ctx, g, fl, 1))) return rc; }
+        DISPATCH_N(g.N, (k_rhs_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
+                                                                               s->Tg[1], s->ufix1, s->ufix2, f[0][0], f[0][1], f[1][0], f[1][1], gsp[0],
+                                                                               gsp[1], s->b.f[0], s->b.f[1], s->b.f[2])));
+        LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m1, MB_FREE, s->Tw[0], s->x.f[0]); LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m2, MB_FREE, s->Tw[1], s->x.f[1]); LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m2, MB_IFREE, s->Tg[1], s->x.f[2]); LAUNCH_CHECK(ctx);
+    }
+    // Jacobi diagonal (cached per coefficient set)
+    if (memcmp(&ac, &s->diag_key, sizeof(ac)) != 0) {
+        if (!diph) {
+            DISPATCH_N(g.N, (k_diag_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, ac, s->m1, s->dinv.f[0], s->nf == 2 ? s->dinv.f[1] : nullptr)));
+        } else {
+            DISPATCH_N(g.N, (k_diag_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, ac, s->m1, s->m2, s->dinv.f[0], s->dinv.f[1], s->dinv.f[2])));
+        }
+        LAUNCH_CHECK(ctx);
+        k_recip<<<dim3(grid, s->nf), RED_THREADS, 0, ctx->stream>>>(g, s->dinv);
+        LAUNCH_CHECK(ctx);
+        s->diag_key = ac;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+
+    // ---- Krylov ----------------------------------------------------------------------------------------------------------
+    double *res = ctx->d_results;
+    const dim3 vgrid(grid, s->nf);
+    MVec z = s->x;  // alias
+    // bnorm
+    k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->b, s->b, s->b, s->b, ctx->d_partials, res + SL_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
+    if ((rc = allreduce_results(ctx, SL_BB, 1))) return rc;
+    // r = b - A x
+    if ((rc = apply_op(s, ac, z, s->t))) return rc;
+    int cur = 0;  // pair index holding (rho, rr)
+    k_resid<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->b, s->t, s->r, ctx->d_partials, res + SL_TMP, ctx->d_counter); LAUNCH_CHECK(ctx);
+    if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
+    double h[2];
+    if ((rc = fetch_results(ctx, SL_BB, 2, h))) return rc;   // SL_BB, SL_TMP adjacent
+    const double bnorm = sqrt(h[0]);
+    double rnorm = sqrt(h[1]);
+    const double tol = fmax(o.rtol * bnorm, o.atol);
+    int it = 0, converged = rnorm <= tol ? 1 : 0;
+    if (!converged) {
+        if (method == PB200_KRYLOV_CG) {
+            // p = dinv r ; rho = (r, dinv r)
+            k_scale<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, s->dinv, s->r, s->p); LAUNCH_CHECK(ctx);
+            k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->r, s->p, s->r, s->p, ctx->d_partials, res + 2 * cur, ctx->d_counter); LAUNCH_CHECK(ctx);
+            if ((rc = allreduce_results(ctx, 2 * cur, 1))) return rc;
+            while (it < o.maxit) {
+                if ((rc = apply_op(s, ac, s->p, s->v))) return rc;
+                k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->p, s->v, s->p, s->v, ctx->d_partials, res + SL_SIGMA, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, SL_SIGMA, 1))) return rc;
+                const int nxt = cur ^ 1;
+                k_cg_update<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, res, 2 * cur, 2 * nxt, s->dinv, s->p, s->v, z, s->r, ctx->d_partials, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                k_cg_p<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, res, 2 * cur, 2 * nxt, s->dinv, s->r, s->p); LAUNCH_CHECK(ctx);
+                cur = nxt;
+                ++it;
+                if (it % o.check_every == 0 || it == o.maxit) {
+                    if ((rc = fetch_results(ctx, 2 * cur + 1, 1, h))) return rc;
+                    rnorm = sqrt(h[0]);
+                    if (rnorm <= tol) { converged = 1; break; }
+                    if (!(rnorm == rnorm)) break;
+                }
+            }
+        } else {
+            // r0 = r ; p = r ; ph = dinv p ; rho = (r0, r) = rr
+            k_copy<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, s->r, s->r0); LAUNCH_CHECK(ctx);
+            k_copy<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, s->r, s->p); LAUNCH_CHECK(ctx);
+            k_scale<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, s->dinv, s->p, s->ph); LAUNCH_CHECK(ctx);
+            k_dots<2><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->r0, s->r, s->r, s->r, ctx->d_partials, res + 2 * cur, ctx->d_counter); LAUNCH_CHECK(ctx);
+            if ((rc = allreduce_results(ctx, 2 * cur, 2))) return rc;
+            while (it < o.maxit) {
+                if ((rc = apply_op(s, ac, s->ph, s->v))) return rc;
+                k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->r0, s->v, s->r0, s->v, ctx->d_partials, res + SL_SIGMA, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, SL_SIGMA, 1))) return rc;
+                k_bicg_s<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, res, 2 * cur, s->dinv, s->r, s->v, s->s, s->sh); LAUNCH_CHECK(ctx);
+                if ((rc = apply_op(s, ac, s->sh, s->t))) return rc;
+                k_dots<2><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->t, s->s, s->t, s->t, ctx->d_partials, res + SL_TS, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, SL_TS, 2))) return rc;
+                const int nxt = cur ^ 1;
+                k_bicg_xr<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, res, 2 * cur, 2 * nxt, s->ph, s->sh, s->s, s->t, s->r0, z, s->r, ctx->d_partials, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                k_bicg_p<<<vgrid, RED_THREADS, 0, ctx->stream>>>(g, res, 2 * cur, 2 * nxt, s->dinv, s->r, s->v, s->p, s->ph); LAUNCH_CHECK(ctx);
+                cur = nxt;
+                ++it;
+                if (it % o.check_every == 0 || it == o.maxit) {
+                    if ((rc = fetch_results(ctx, 2 * cur + 1, 1, h))) return rc;
+                    rnorm = sqrt(h[0]);
+                    if (rnorm <= tol) { converged = 1; break; }
+                    if (!(rnorm == rnorm)) break;
+                }
+            }
+        }
+    }
+    // ---- write the new state ----------------------------------------------------------------------------------------------
+    k_store_bulk<<<grid, RED_THREADS, 0, ctx->stream>>>(g, z.f[0], s->ufix1, s->Tw[0]); LAUNCH_CHECK(ctx);
+    if (!diph) {
+        const double *src = s->nf == 2 ? z.f[1] : s->gK;
+        CUDA_TRY(ctx, cudaMemcpyAsync(s->Tg[0] + g.plane, src + g.plane, sizeof(double) * (size_t)g.nown, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        k_store_bulk<<<grid, RED_THREADS, 0, ctx->stream>>>(g, z.f[1], s->ufix2, s->Tw[1]); LAUNCH_CHECK(ctx);
+        k_store_diph_ifc<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->sp, gsp[0], z.f[2], s->Tg[0], s->Tg[1]); LAUNCH_CHECK(ctx);
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev2));
+    if (stats) {
+        float ms_setup = 0, ms_solve = 0;
+        cudaEventElapsedTime(&ms_setup, ctx->ev0, ctx->ev1);
+        cudaEventElapsedTime(&ms_solve, ctx->ev1, ctx->ev2);
+        stats->iters = it; stats->converged = converged; stats->rnorm = rnorm; stats->bnorm = bnorm;
+        stats->solve_ms = ms_solve; stats->setup_ms = ms_setup;
+        stats->dof_bulk = s->dof_bulk; stats->dof_ifc = s->dof_ifc;
+        stats->launches = ctx->launches - launches0;
+    }
+    if (!converged) return set_err(ctx, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
+    return PB200_OK;
+}

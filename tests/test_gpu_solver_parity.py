@@ -1,0 +1,221 @@
+"""GPU parity of the operator / solver stages against the CPU oracle on identical (imported) capacities.
+
+Bar (BASELINE.json north_star): per-step solutions agree with the reference solve at the same dt to relative
+L2 <= 1e-9 in fp64.  Every call goes through the C ABI (penguin_b200 -> ctypes -> libpenguin_b200.so).
+"""
+import numpy as np
+import pytest
+
+from oracle import geom
+from oracle import penguin_oracle as po
+from helpers import import_capacity, rel_l2, to_oracle_bc, to_oracle_borders
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+KW = dict(reltol=1e-13, maxiter=50000)
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import penguin_b200
+    penguin_b200.init()
+    return penguin_b200
+
+
+def _phases(pb, mesh_o, mesh_g, ls, f, D):
+    cap_o = geom.capacity(mesh_o, ls)
+    op_o = po.DiffusionOps(cap_o)
+    cap_g = import_capacity(pb, mesh_g, cap_o)
+    op_g = pb.DiffusionOps(cap_g)
+    return po.Phase(cap_o, op_o, f, D), pb.Phase(cap_g, op_g, f, D)
+
+
+def _meshes(pb, n, L, x0=None):
+    return po.Mesh(n, L, x0), pb.Mesh(n, L, x0)
+
+
+@pytest.mark.parametrize("n,L,c,r", [((12,), (4.0,), (2.1,), 1.0), ((16, 12), (4.0, 3.0), (2.05, 1.45), 0.9),
+                                     ((9, 8, 7), (4.0, 4.0, 4.0), (2.0, 2.1, 1.9), 1.2)])
+def test_grad_div(pb, n, L, c, r):
+    mo, mg = _meshes(pb, n, L)
+    f = lambda *a: 0.0
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball(c, r), f, 1.0)
+    rng = np.random.default_rng(0)
+    nn = mo.n
+    p = rng.standard_normal(2 * nn)
+    assert rel_l2(pb.grad(phg.operator, p), po.grad(pho.operator, p)) < 1e-13
+    N = len(n)
+    qo, qg = rng.standard_normal(N * nn), rng.standard_normal(N * nn)
+    assert rel_l2(pb.div(phg.operator, qo, qg), po.div(pho.operator, qo, qg)) < 1e-13
+    assert np.array_equal(phg.operator.Wdag, pho.operator.Wdag_diag)
+
+
+def test_steady_mono_2d(pb):
+    # test/solver/diffusion_test.jl:5-26 on both sides
+    mo, mg = _meshes(pb, (20, 20), (2.0, 2.0))
+    f, D = (lambda x, y, z: 0.0 * x), (lambda x, y, z: 1.0 + 0 * x)
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((0.5, 0.5), 0.5), f, D)
+    bcb = pb.BorderConditions({k: pb.Dirichlet(1.0) for k in ("left", "right", "top", "bottom")})
+    so = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(pho, to_oracle_borders(pb, bcb), po.Dirichlet(1.0)))
+    sg = pb.solve_DiffusionSteadyMono_(pb.DiffusionSteadyMono(phg, bcb, pb.Dirichlet(1.0)), **KW)
+    assert rel_l2(sg.x, so.x) < TOL
+    assert abs(sg.x[:mo.n].max() - 1.0) < 1e-2
+
+
+@pytest.mark.parametrize("ifc", ["dirichlet", "robin", "neumann"])
+def test_steady_mono_manufactured(pb, ifc):
+    # test/convergence_test.jl:30-49 geometry; f = 4, Dirichlet / Robin / Neumann interface rows
+    mo, mg = _meshes(pb, (24, 24), (4.0, 4.0))
+    f, D = (lambda x, y, z: 4.0 + 0 * x), 1.0
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((2.0, 2.0), 1.0), f, D)
+    bcb = pb.BorderConditions({k: pb.Dirichlet(1.0) for k in ("left", "right", "top", "bottom")})
+    bci = {"dirichlet": pb.Dirichlet(0.0), "robin": pb.Robin(1.0, 0.5, 0.25), "neumann": pb.Robin(1e-3, 1.0, 0.1)}[ifc]
+    so = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(pho, to_oracle_borders(pb, bcb), to_oracle_bc(pb, bci)))
+    sg = pb.solve_DiffusionSteadyMono_(pb.DiffusionSteadyMono(phg, bcb, bci), **KW)
+    assert rel_l2(sg.x, so.x) < TOL
+
+
+def test_steady_diph_2d(pb):
+    # test/solver/diffusion_test.jl:28-55 (40^2 here): max u1 pinned on the oracle at 80^2
+    mo, mg = _meshes(pb, (40, 40), (4.0, 4.0))
+    f, D = (lambda x, y, z: 1.0 + 0 * x), 1.0
+    ls = geom.LevelSet.ball((2.0, 2.0), 1.0)
+    p1o, p1g = _phases(pb, mo, mg, ls, f, D)
+    p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, D)
+    bcb = pb.BorderConditions({k: pb.Dirichlet(0.0) for k in ("left", "right", "top", "bottom")})
+    so = po.solve_DiffusionSteadyDiph(po.DiffusionSteadyDiph(p1o, p2o, to_oracle_borders(pb, bcb),
+                                                             po.InterfaceConditions(po.ScalarJump(1.0, 1.0, 0.0), po.FluxJump(1.0, 1.0, 0.0))))
+    ic = pb.InterfaceConditions(pb.ScalarJump(1.0, 1.0, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+    sg = pb.solve_DiffusionSteadyDiph_(pb.DiffusionSteadyDiph(p1g, p2g, bcb, ic), **KW)
+    assert rel_l2(sg.x, so.x) < TOL
+
+
+@pytest.mark.parametrize("scheme", ["BE", "CN"])
+@pytest.mark.parametrize("ifc", ["dirichlet_fn", "robin"])
+def test_unsteady_mono_2d(pb, scheme, ifc):
+    # README quick start (README.md:43-79) at 32^2: interface Dirichlet sin(pi x) sin(pi y), borders Dirichlet 0
+    nx = 32
+    mo, mg = _meshes(pb, (nx, nx), (4.0, 4.0))
+    f = lambda x, y, z, t: 0.3 * np.sin(x) * (1 + t)
+    D = lambda x, y, z: 1.0 + 0 * x
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((2.01, 2.01), 1.0), f, D)
+    bcb = pb.BorderConditions({k: pb.Dirichlet(0.0) for k in ("left", "right", "top", "bottom")})
+    if ifc == "dirichlet_fn":
+        bci = pb.Dirichlet(lambda x, y, z, t: np.sin(np.pi * x) * np.sin(np.pi * y) * (1 + 10 * t))
+    else:
+        bci = pb.Robin(2.0, 1.0, 0.5)
+    n = mo.n
+    u0 = np.concatenate([np.zeros(n), np.ones(n)])
+    dt = 0.25 * (4.0 / nx) ** 2
+    Tend = 4.5 * dt
+    so = po.DiffusionUnsteadyMono(pho, to_oracle_borders(pb, bcb), to_oracle_bc(pb, bci), dt, u0, "BE")
+    po.solve_DiffusionUnsteadyMono(so, pho, dt, Tend, to_oracle_borders(pb, bcb), to_oracle_bc(pb, bci), scheme)
+    sg = pb.DiffusionUnsteadyMono(phg, bcb, bci, dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyMono_(sg, phg, dt, Tend, bcb, bci, scheme, **KW)
+    assert len(sg.states) == len(so.states) == 6
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
+
+
+@pytest.mark.parametrize("scheme", ["BE", "CN"])
+def test_unsteady_diph_2d(pb, scheme):
+    # benchmark/Heat_2ph_2D.jl:64-111 at 32^2: empty BorderConditions, ScalarJump(1, He, 0), FluxJump(1, 1, 0)
+    nx = 32
+    mo, mg = _meshes(pb, (nx, nx), (8.0, 8.0))
+    f = lambda x, y, z, t: 0.0 * x
+    ls = geom.LevelSet.ball((4.0, 4.0), 2.0)
+    p1o, p1g = _phases(pb, mo, mg, ls, f, lambda x, y, z: 1.0 + 0 * x)
+    p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, lambda x, y, z: 2.0 + 0 * x)
+    n = mo.n
+    u0 = np.concatenate([np.ones(n), np.ones(n), np.zeros(n), np.zeros(n)])
+    dt = 0.5 * (8.0 / nx) ** 2
+    Tend = 3.5 * dt
+    ico = po.InterfaceConditions(po.ScalarJump(1.0, 0.5, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+    icg = pb.InterfaceConditions(pb.ScalarJump(1.0, 0.5, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+    so = po.DiffusionUnsteadyDiph(p1o, p2o, po.BorderConditions(), ico, dt, u0, "BE")
+    po.solve_DiffusionUnsteadyDiph(so, p1o, p2o, dt, Tend, po.BorderConditions(), ico, scheme)
+    sg = pb.DiffusionUnsteadyDiph(p1g, p2g, pb.BorderConditions(), icg, dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, Tend, pb.BorderConditions(), icg, scheme, **KW)
+    assert len(sg.states) == len(so.states) == 5
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
+
+
+def test_unsteady_diph_borders_jump_values(pb):
+    # Dirichlet borders on a diphasic problem + non-zero jump data g, h
+    nx = 24
+    mo, mg = _meshes(pb, (nx, nx), (4.0, 4.0))
+    f = lambda x, y, z, t: 1.0 + 0 * x
+    ls = geom.LevelSet.ball((2.0, 2.0), 1.0)
+    p1o, p1g = _phases(pb, mo, mg, ls, f, 1.0)
+    p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, 3.0)
+    n = mo.n
+    u0 = np.zeros(4 * n)
+    dt = 0.5 * (4.0 / nx) ** 2
+    Tend = 2.5 * dt
+    keys = ("left", "right", "top", "bottom")
+    bco = po.BorderConditions({k: po.Dirichlet(0.5) for k in keys})
+    bcg = pb.BorderConditions({k: pb.Dirichlet(0.5) for k in keys})
+    ico = po.InterfaceConditions(po.ScalarJump(1.0, 2.0, 0.3), po.FluxJump(1.0, 1.5, 0.2))
+    icg = pb.InterfaceConditions(pb.ScalarJump(1.0, 2.0, 0.3), pb.FluxJump(1.0, 1.5, 0.2))
+    so = po.DiffusionUnsteadyDiph(p1o, p2o, bco, ico, dt, u0, "BE")
+    po.solve_DiffusionUnsteadyDiph(so, p1o, p2o, dt, Tend, bco, ico, "BE")
+    sg = pb.DiffusionUnsteadyDiph(p1g, p2g, bcg, icg, dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, Tend, bcg, icg, "BE", **KW)
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
+
+
+def test_unsteady_mono_3d_cn(pb):
+    # benchmark/Heat3D.jl:53-74 at 14^3: sphere, interface Dirichlet 1, borders Dirichlet 1 (incl. forward/backward), BE then CN
+    nx = 14
+    mo, mg = _meshes(pb, (nx, nx, nx), (4.0, 4.0, 4.0))
+    f = lambda x, y, z, t: 0.0 * x
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((2.01, 2.01, 2.01), 1.0, False), f, 1.0)
+    keys = ("left", "right", "top", "bottom", "forward", "backward")
+    bco = po.BorderConditions({k: po.Dirichlet(1.0) for k in keys})
+    bcg = pb.BorderConditions({k: pb.Dirichlet(1.0) for k in keys})
+    n = mo.n
+    u0 = np.zeros(2 * n)
+    dt = 0.75 * (4.0 / nx) ** 2
+    Tend = 2.5 * dt
+    so = po.DiffusionUnsteadyMono(pho, bco, po.Dirichlet(1.0), dt, u0, "BE")
+    po.solve_DiffusionUnsteadyMono(so, pho, dt, Tend, bco, po.Dirichlet(1.0), "CN")
+    sg = pb.DiffusionUnsteadyMono(phg, bcg, pb.Dirichlet(1.0), dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyMono_(sg, phg, dt, Tend, bcg, pb.Dirichlet(1.0), "CN", **KW)
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
+
+
+def test_unsteady_diph_1d_halfspace(pb):
+    # test/convergence_test.jl:100-192 (first steps)
+    nx, lx, xint = 100, 8.0, 4.0
+    mo, mg = _meshes(pb, (nx,), (lx,))
+    f = lambda x, y, z, t: 0.0 * x
+    ls = geom.LevelSet.halfspace(0, xint, True)
+    p1o, p1g = _phases(pb, mo, mg, ls, f, 1.0)
+    p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, 1.0)
+    n = mo.n
+    u0 = np.concatenate([np.zeros(n), np.zeros(n), np.ones(n), np.ones(n)])
+    dt = 0.5 * (lx / nx) ** 2
+    Tend = 5.5 * dt
+    bco = po.BorderConditions({"top": po.Dirichlet(1.0), "bottom": po.Dirichlet(0.0)})
+    bcg = pb.BorderConditions({"top": pb.Dirichlet(1.0), "bottom": pb.Dirichlet(0.0)})
+    ico = po.InterfaceConditions(po.ScalarJump(1.0, 0.5, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+    icg = pb.InterfaceConditions(pb.ScalarJump(1.0, 0.5, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+    so = po.DiffusionUnsteadyDiph(p1o, p2o, bco, ico, dt, u0, "BE")
+    po.solve_DiffusionUnsteadyDiph(so, p1o, p2o, dt, Tend, bco, ico, "BE")
+    sg = pb.DiffusionUnsteadyDiph(p1g, p2g, bcg, icg, dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, Tend, bcg, icg, "BE", **KW)
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
+
+
+def test_removed_dofs_are_exact_zero(pb):
+    # solve_system! scatters into zeros(n): removed DOFs are exactly 0.0 (src/solver.jl:186-187)
+    mo, mg = _meshes(pb, (16, 16), (4.0, 4.0))
+    f = lambda x, y, z: 1.0 + 0 * x
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((2.0, 2.0), 1.0), f, 1.0)
+    so = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(pho, po.BorderConditions(), po.Dirichlet(0.0)))
+    sg = pb.solve_DiffusionSteadyMono_(pb.DiffusionSteadyMono(phg, pb.BorderConditions(), pb.Dirichlet(0.0)), **KW)
+    assert np.array_equal(sg.x == 0.0, so.x == 0.0)
