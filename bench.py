@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- BE step throughput of the diphasic cut-cell heat problem (BASELINE.json configs[1], Heat_2ph_2D).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libpenguin_b200.so through its C ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port), rank 0 only
+
+Workload (benchmark/Heat_2ph_2D.jl:64-111): 2048 x 2048 cells per GPU on [0,8] x [0,8N], one circular
+interface (r = 2) per GPU slab, phase 1 inside / phase 2 outside, D1 = D2 = 1, ScalarJump(1,1,0), FluxJump(1,1,0),
+empty BorderConditions, u0 = [1,1,0,0], backward Euler with dt = 0.5 h^2, Krylov to ||r|| <= 1e-10 ||b||.
+A "step" is one BE step: RHS assembly + the linear solve + state update.  metric = DOF*steps/s, DOF = active bulk
+unknowns of both phases (the rows the reference keeps after remove_zero_rows_cols!).
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "BE step throughput, 2D diphasic cut-cell heat (Heat_2ph_2D)"
+UNIT = "DOF*steps/s"
+L2_MB = 126
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md, clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the CPU arm: the reference's algorithm (sparse assembly + direct solve per step) restated in oracle/
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_sample(nx, steps, warmup=0):
+    """DOF*steps/s of the oracle port on an nx^2 sample of the same workload (1 core: SciPy SuperLU is serial)."""
+    from oracle import geom, penguin_oracle as po
+    mesh = po.Mesh((nx, nx), (8.0, 8.0))
+    ls = geom.LevelSet.ball((4.0, 4.0), 2.0)
+    c1, c2 = geom.capacity(mesh, ls), geom.capacity(mesh, ls.flipped())
+    f = lambda x, y, z, t: 0.0 * x
+    p1, p2 = po.Phase(c1, po.DiffusionOps(c1), f, 1.0), po.Phase(c2, po.DiffusionOps(c2), f, 1.0)
+    n = mesh.n
+    u0 = np.concatenate([np.ones(2 * n), np.zeros(2 * n)])
+    dt = 0.5 * (8.0 / nx) ** 2
+    ic = po.InterfaceConditions(po.ScalarJump(1.0, 1.0, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+    bc = po.BorderConditions()
+    s = po.DiffusionUnsteadyDiph(p1, p2, bc, ic, dt, u0, "BE")
+    s.x = po.solve_system(s.A, s.b)                       # the constructor's step (solve_DiffusionUnsteadyDiph!, diffusion.jl:429)
+    Ti = s.x
+    s.A = po.A_diph_unstead_diff(p1.operator, p2.operator, c1, c2, p1.D, p2.D, ic, dt, "BE")
+    dof = int(np.count_nonzero((c1.V != 0) | np.any(np.stack(c1.B) != 0, axis=0)) +
+              np.count_nonzero((c2.V != 0) | np.any(np.stack(c2.B) != 0, axis=0)))
+    t, t0 = 0.0, None
+    for k in range(warmup + steps):
+        if k == warmup:
+            t0 = time.perf_counter()
+        t += dt
+        s.b = po.b_diph_unstead_diff(p1.operator, p2.operator, p1.source, p2.source, c1, c2, p1.D, p2.D, ic, Ti, dt, t, "BE")
+        s.A, s.b = po.BC_border_diph(s.A, s.b, bc, c1, c2)
+        s.x = po.solve_system(s.A, s.b)                   # remove_zero_rows_cols! + sparse LU, every step (solver.jl:158-188)
+        Ti = s.x
+    el = time.perf_counter() - t0
+    return dof * steps / el, dof, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx = 256 if args.steps <= 30 else 128
+    v, dof, el = cpu_sample(nx, args.steps, args.warmup)
+    sample = f"{nx}x{nx} sample of the workload, {args.steps} BE steps, sparse LU per step (SciPy SuperLU), {dof} DOF"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": "Heat_2ph_2D diphasic BE step (BASELINE.json configs[1])", "sample": sample},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import penguin_b200 as pb
+    from penguin_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+        def bcast(ident):
+            obj = [ident]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        ctx = pb.init_distributed(rank, world, local, bcast)
+    else:
+        ctx = pb.init(local)
+    lib = L.lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nx = args.nx
+    N = world
+    mesh = pb.Mesh((nx, nx * N), (8.0, 8.0 * N))
+    body = pb.Balls([[4.0, 4.0 + 8.0 * k] for k in range(N)], [2.0] * N)
+    t0 = time.perf_counter()
+    c1, c2 = pb.Capacity(body, mesh, compute_centroids=False), pb.Capacity(-body, mesh, compute_centroids=False)
+    ctx.sync()
+    cap_s = time.perf_counter() - t0
+    f = 0.0
+    p1, p2 = pb.Phase(c1, pb.DiffusionOps(c1), f, 1.0), pb.Phase(c2, pb.DiffusionOps(c2), f, 1.0)
+    nloc = c1.nloc
+    h = 8.0 / nx
+    dt = 0.5 * h * h
+    ic = pb.InterfaceConditions(pb.ScalarJump(1.0, 1.0, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+    u0 = np.concatenate([np.ones(2 * nloc), np.zeros(2 * nloc)])
+    s = pb.DiffusionUnsteadyDiph(p1, p2, pb.BorderConditions(), ic, dt, u0, "BE")
+
+    opts = L.KrylovOpts()
+    opts.method, opts.rtol, opts.atol, opts.maxit, opts.warm_start, opts.check_every = args.method, 1e-10, 0.0, 5000, 1, args.check_every
+    si = L.StepIn()
+    si.scheme, si.dt = 0, dt
+    st = L.StepStats()
+
+    def step():
+        rc = lib.pb200_solver_step(s._h, C.byref(si), C.byref(opts), C.byref(st))
+        L.check(rc, ctx.h)
+
+    ext = torch.cuda.ExternalStream(ctx.stream)     # the library's launching stream, for torch.cuda.Event timing
+    lib.pb200_set_profiling(ctx.h, 0 if args.no_profile else 1)
+    for _ in range(args.warmup):
+        step()
+    iters, apply_ms, apply_n = [], 0.0, 0
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+        iters.append(st.iters)
+        apply_ms += st.apply_ms
+        apply_n += st.apply_launches
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = allmax(e0.elapsed_time(e1))
+    launches = int(allsum(ctx.launches - launches0))
+    dof = int(st.dof_bulk)                          # all ranks (allreduced inside the library)
+    value = dof * args.steps / (ms * 1e-3)
+    rnorm_rel = st.rnorm / st.bnorm if st.bnorm > 0 else 0.0
+
+    # ---- end to end through the public API with HOST buffers: per step the jump data g, h go host -> device from pinned
+    # memory and the new state comes back device -> host (the reference pushes every state to solver.states) ---------------
+    lib.pb200_set_profiling(ctx.h, 0)
+    pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    g_host, h_host, x_host = pin(nloc), pin(nloc), pin(4 * nloc)
+    g_host[:] = 0.0
+    h_host[:] = 0.0
+    dp = L.dp
+    si.g_arr[0] = g_host.ctypes.data_as(dp)
+    si.g_arr[1] = h_host.ctypes.data_as(dp)
+    e2e_steps = max(1, min(args.steps, 20))
+    for _ in range(2):
+        step()
+        L.check(lib.pb200_solver_get_state(s._h, x_host.ctypes.data_as(dp)), ctx.h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step()
+        L.check(lib.pb200_solver_get_state(s._h, x_host.ctypes.data_as(dp)), ctx.h)
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e = {"value": dof * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(allsum(2 * 8 * nloc)),
+           "d2h_bytes_per_step": int(allsum(4 * 8 * nloc)), "steps": e2e_steps, "timing": "host wall clock between device syncs, max over ranks"}
+
+    # ---- roofline of the dominant kernel (the operator apply inside the Krylov loop) ---------------------------------------------
+    peak, peak_src = peaks()
+    roof = None
+    if apply_n and apply_ms > 0:
+        # x, y and N off-diagonal coefficients per active unknown: SURVEY 8(d)'s 8 (N + 3) minus the diagonal array, which the
+        # block-Jacobi scaling turns into the identity (DESIGN.md "Kernels and rooflines")
+        bytes_per_dof = 8 * (mesh.N + 2)
+        local_dof = dof / world
+        achieved = local_dof * bytes_per_dof / (apply_ms / apply_n * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("nx") == nx:
+                traffic = tj.get("dram_bytes_per_launch")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "operator apply, dense part (kf_apply_dense)", "algorithmic_bytes_per_dof": bytes_per_dof, "launches_timed": int(apply_n),
+                "avg_launch_us": 1e3 * apply_ms / apply_n, "peak_source": peak_src}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            v, cdof, el = cpu_sample(256, 12)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"256x256 sample of the workload, 12 BE steps in {el:.1f} s, sparse LU per step (SciPy SuperLU, serial), {cdof} DOF"}
+        fields_mb = 8 * nloc / 1e6
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": "Heat_2ph_2D diphasic BE step (BASELINE.json configs[1])", "grid": [nx, nx * N], "cells_per_gpu": [nx, nx],
+                          "dof": dof, "vector_length_4n": int(allsum(4 * nloc)), "scheme": "BE", "dt": dt, "krylov": "BiCGSTAB" if args.method != 1 else "CG",
+                          "rtol": 1e-10, "iters_per_step": float(np.mean(iters)), "final_rel_residual": rnorm_rel,
+                          "parallelism": f"y-slab x{world}" if world > 1 else "single GPU",
+                          "l2": f"inputs larger than L2: {fields_mb:.0f} MB per field, > 30 fields streamed per step vs {L2_MB} MB L2",
+                          "capacity_build_s": cap_s},
+               "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    pb.finalize()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=2048)
+    ap.add_argument("--method", type=int, default=0, help="0 auto (BiCGSTAB for the diphasic system), 1 CG, 2 BiCGSTAB")
+    ap.add_argument("--check-every", type=int, default=1)
+    ap.add_argument("--no-profile", action="store_true", help="do not bracket the apply launches with CUDA events")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,9 @@ int pb200_sync(pb200_ctx *ctx);
 int64_t pb200_launch_count(pb200_ctx *ctx);
 /* the CUDA stream every kernel of ctx is launched on (cudaStream_t as an integer), for event timing by the host */
 uint64_t pb200_stream(pb200_ctx *ctx);
+/* enable != 0: bracket every operator-apply launch of pb200_solver_step with CUDA events on the launching stream and
+ * report their summed device time in pb200_step_stats.apply_ms (the roofline measurement of bench.py) */
+int pb200_set_profiling(pb200_ctx *ctx, int enable);
 
 /* ---- level-set descriptors (GPU-evaluable bodies; a Julia closure cannot run on the device) ---------------- */
 #define PB200_LS_BALLS 0     /* phi = min_k |x - c_k| - r_k, disjoint balls (interval / circle / sphere) */
@@ -149,6 +152,12 @@ typedef struct {
 #define PB200_KRYLOV_AUTO 0 /* CG for mono, BiCGSTAB for diph */
 #define PB200_KRYLOV_CG 1
 #define PB200_KRYLOV_BICGSTAB 2
+/* PB200_PATH_FOLDED: symmetrised, per-cell block-Jacobi-scaled stencil with unit diagonal (csrc/fold.cuh) -- the fast path, used
+ * whenever the jump / Robin coefficients allow it.  PB200_PATH_GENERIC: the reference's rows applied matrix-free with point-Jacobi
+ * preconditioning (csrc/operators.cuh) -- any coefficients, and the cross-check of the folded path in the tests.          */
+#define PB200_PATH_AUTO 0
+#define PB200_PATH_GENERIC 1
+#define PB200_PATH_FOLDED 2
 typedef struct {
     int method;
     double rtol; /* stop when ||r|| <= max(rtol ||b||, atol)  (IterativeSolvers convention) */
@@ -156,6 +165,7 @@ typedef struct {
     int maxit;
     int warm_start; /* 1: start from the previous state, 0: zero initial guess like the reference */
     int check_every; /* convergence is tested on the host every this many iterations (>= 1) */
+    int path;        /* PB200_PATH_*: which implementation of the solve runs */
 } pb200_krylov_opts;
 
 typedef struct {
@@ -168,6 +178,8 @@ typedef struct {
     int64_t dof_bulk; /* active bulk unknowns (all ranks) -- SURVEY 8(d) definition of DOF */
     int64_t dof_ifc;  /* active interface unknowns (all ranks) */
     int64_t launches; /* kernels launched by this call */
+    double apply_ms;        /* summed device time of the operator-apply launches (0 unless profiling is enabled) */
+    int64_t apply_launches; /* number of operator-apply launches of this call */
 } pb200_step_stats;
 
 /* one solve: builds b from the device-resident state (b_*_unstead_diff / b_*_stead_diff), applies the border

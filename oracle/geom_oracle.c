@@ -216,7 +216,7 @@ static void circle_rect_arcs(const double *c, double rho, const double *lo, cons
         double a0 = ang[i], a1 = ang[i + 1];
         if (!(a1 > a0)) continue;
         double am = 0.5 * (a0 + a1), py = c[0] + rho * cos(am), pz = c[1] + rho * sin(am);
-        if (py > lo[0] && py < hi[0] && pz > lo[1] && pz < hi[1]) {
+        if (py >= lo[0] && py <= hi[0] && pz >= lo[1] && pz <= hi[1]) {   /* closed: an arc tangent to a face at its mid-point is inside */
             double dphi = a1 - a0;
             out[0] += rho * dphi;
             out[1] += rho * ((c[0] - mid[0]) * dphi + rho * (sin(a1) - sin(a0)));

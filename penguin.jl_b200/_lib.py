@@ -29,13 +29,13 @@ class StepIn(C.Structure):
 
 class KrylovOpts(C.Structure):
     _fields_ = [("method", C.c_int), ("rtol", C.c_double), ("atol", C.c_double), ("maxit", C.c_int),
-                ("warm_start", C.c_int), ("check_every", C.c_int)]
+                ("warm_start", C.c_int), ("check_every", C.c_int), ("path", C.c_int)]
 
 
 class StepStats(C.Structure):
     _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("rnorm", C.c_double), ("bnorm", C.c_double),
                 ("solve_ms", C.c_double), ("setup_ms", C.c_double), ("dof_bulk", C.c_int64), ("dof_ifc", C.c_int64),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("apply_ms", C.c_double), ("apply_launches", C.c_int64)]
 
 
 # every symbol include/penguin_b200.h declares (tests/test_abi.py checks the .so exports them all)
@@ -48,6 +48,7 @@ SYMBOLS = {
     "pb200_sync": ([C.c_void_p], C.c_int),
     "pb200_launch_count": ([C.c_void_p], C.c_int64),
     "pb200_stream": ([C.c_void_p], C.c_uint64),
+    "pb200_set_profiling": ([C.c_void_p, C.c_int], C.c_int),
     "pb200_capacity_create": ([C.c_void_p, C.c_int, ip, dp, dp, C.POINTER(LevelSetC), C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "pb200_capacity_import": ([C.c_void_p, C.c_int, ip, dp, dp] + [dp] * 8 + [C.POINTER(C.c_void_p)], C.c_int),
     "pb200_capacity_export": ([C.c_void_p] + [dp] * 8, C.c_int),

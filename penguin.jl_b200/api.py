@@ -470,7 +470,8 @@ def _make_solver(s, phase1, phase2, bc_i, ic):
     for k, ph in ((1, phase1), (2, phase2)):
         if ph is None:
             continue
-        cst, arr = _eval(ph.Diffusion_coeff, _coords3(ph.capacity.C_ω), None, ph.capacity.nloc)
+        Dc = ph.Diffusion_coeff
+        cst, arr = _eval(Dc, _coords3(ph.capacity.C_ω) if callable(Dc) else None, None, ph.capacity.nloc)
         setattr(d, f"D{k}", cst)
         if arr is not None:
             keep.append(arr)
@@ -517,6 +518,7 @@ def _krylov_opts(method, kw):
     o.maxit = int(kw.get("maxiter", 20000))
     o.warm_start = int(kw.get("warm_start", 1))
     o.check_every = int(kw.get("check_every", 1))
+    o.path = {"auto": 0, "generic": 1, "folded": 2}[kw.get("path", "auto")]
     return o
 
 
@@ -531,7 +533,7 @@ def _step(s, scheme, dt, t, bc_i, ic, opts, mono_border_t=True):
     for k, ph in enumerate((ph1, ph2)):
         if ph is None:
             continue
-        cols = _coords3(ph.capacity.C_ω)
+        cols = _coords3(ph.capacity.C_ω) if callable(ph.source) else None
         times = (t, t + dt) if unsteady else (None,)
         for w, tt in enumerate(times):
             cst, arr = _eval(ph.source, cols, tt, ph.capacity.nloc)

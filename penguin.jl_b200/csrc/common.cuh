@@ -35,7 +35,36 @@ struct pb200_ctx {
     unsigned *d_counter = nullptr;
     double *h_results = nullptr;   // pinned mirror
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // optional per-launch timing of the operator apply (pb200_set_profiling)
+    bool profile = false;
+    std::vector<cudaEvent_t> pev;   // event pairs
+    size_t pev_used = 0;
+    int64_t apply_launches = 0;
 };
+
+// event bracket around one launch (no-op unless profiling): PROF_BEGIN(ctx); kernel<<<>>>; PROF_END(ctx);
+static inline void prof_mark(pb200_ctx *ctx)
+{
+    if (!ctx->profile) return;
+    if (ctx->pev_used == ctx->pev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->pev.push_back(e);
+    }
+    cudaEventRecord(ctx->pev[ctx->pev_used++], ctx->stream);
+}
+// summed elapsed time of the recorded pairs (stream must be synchronised); resets the pool
+static inline double prof_collect(pb200_ctx *ctx)
+{
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < ctx->pev_used; i += 2) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->pev[i], ctx->pev[i + 1]);
+        ms += t;
+    }
+    ctx->pev_used = 0;
+    return ms;
+}
 
 static int set_err(pb200_ctx *ctx, int code, const std::string &msg)
 {

@@ -1,0 +1,624 @@
+// fold.cuh -- the fast path of the linear solve: the reduced system of /root/reference/src/solver/diffusion.jl:30-43,
+// 104-144, 212-241, 334-389 (after remove_zero_rows_cols!, src/solver.jl:59-78, and after the elimination of the known
+// unknowns) FOLDED into a symmetric, block-Jacobi-scaled stencil with unit diagonal, and the Krylov kernels that run on it.
+//
+// Algebra (DESIGN.md "Folded system").  Per phase p the reference operator [G H]' W! [G H] is a sum over faces of rank-1
+// terms W!_f g_f g_f' on the four unknowns touching face f = (d, i):
+//     g_f = ( a = e_i B_i  on u_i,   b = -B_{i-1}  on u_{i-1},   c = e_i (A_i - B_i)  on gamma_i,   d = -(A_i - B_{i-1})  on gamma_{i-1} )
+// (operators.cuh derives the same numbers row-wise).  With the interface unknown w (mono: T_gamma; diph: T_gamma2 and
+// T_gamma1 = (g + a2 w) / a1, i.e. gamma_1 = kappa w + known, kappa = a2/a1) and the positive row scalings
+//     bulk rows of phase p:  s_p / (c D_p),   s = 1 (mono),  s_1 = b1 / kappa, s_2 = b2 (diph);   interface row: 1 (diph), 1 / (c2 beta) (mono)
+// the system matrix is  M = diag(s_p cV V_p / (c D_p)) (+ (alpha/beta) Gamma on w, mono Robin)  +  sum_p s_p sum_f W!_f g'_f g'_f^T,
+// symmetric positive definite.  Cut cells couple u_1, u_2 and w of the same cell strongly (small-cell stiffness), so M is scaled
+// by the Cholesky factors L_i of its per-cell 3x3 diagonal blocks:  M^ = L^-1 M L^-T  has identity diagonal blocks; outside the
+// interface band L_i is diagonal and M^ is a plain (2N+1)-point stencil with unit diagonal and N coefficient arrays per phase.
+// Everything that involves a band cell (w active) is kept in compact per-cell 3x3 blocks over the band and its face neighbours.
+//
+// Data layout: bulk fields are the dense padded arrays of common.cuh (only ACTIVE 256-cell chunks are ever touched: the two
+// phases of a diphasic problem are complementary, so streaming both dense would double the traffic); w lives in a compact
+// array over the band cells, sorted by cell index (ghost-plane entries form a prefix / suffix, so its halo is two contiguous ranges).
+#pragma once
+#include <thrust/execution_policy.h>
+#include <thrust/sort.h>
+
+#include "assemble.cuh"
+#include "krylov.cuh"
+#include "operators.cuh"
+
+#define FCH 256   // cells per chunk == threads per block
+
+struct FoldDev {
+    int N, nbulk, has_w;
+    double s[2], kap[2];
+    double mwc;    // (alpha / beta) Gamma on the w diagonal (mono Robin), else 0
+    double wrow;   // row factor of the interface row
+    double cVc;    // cV / c
+    double c;      // theta dt (1 steady)
+    const unsigned char *m[2];   // bulk masks per phase
+    const unsigned char *mw;     // mask carrying MB_IFREE
+    PhaseDev ph[2];
+    double *sc[2];
+    double *off[2][PB_MAXD];
+    int nB, nBlo, nBown, nE;
+    const long long *Bcell, *Ecell;
+    const int *bord;
+    double *Linv;    // [5][nB]: i00 i11 i20 i21 i22
+    int *EB;         // [nE]
+    int *EnbrB;      // [2N][nE]
+    double *Eblk;    // [(1+2N)*9][nE]
+};
+
+struct FVec { double *f[3]; };   // f[0], f[1]: dense bulk fields; f[2]: compact w
+
+struct Items { const int *it; int n; long long lo, hi; int wlo, whi; };
+__device__ __forceinline__ bool item_index(const Items &I, int item, int &f, long long &idx)
+{
+    const unsigned v = (unsigned)I.it[item];
+    f = (int)(v >> 30);
+    const long long ch = (long long)(v & 0x3fffffffu);
+    if (f < 2) { idx = ch * FCH + threadIdx.x; return idx >= I.lo && idx < I.hi; }
+    idx = (long long)I.wlo + ch * FCH + threadIdx.x;
+    return idx < (long long)I.whi;
+}
+
+// result slots of the folded Krylov loops (dense-part and band-part partial sums are adjacent: one allreduce covers both)
+enum { FS_PAIR0 = 0, FS_PAIR1 = 2, FS_SIG_D = 4, FS_SIG_B = 5, FS_TS_D = 6, FS_TT_D = 7, FS_TS_B = 8, FS_TT_B = 9, FS_BB = 10, FS_RR0 = 11, FS_TMP = 12 };
+
+// ---- face coefficients ---------------------------------------------------------------------------------------------------
+// lower face of cell l in direction d (id = coordinate of l along d): W!, (a, cw) on (u_l, w_l), (b, dw) on (u_{l-s}, w_{l-s})
+__device__ __forceinline__ void face_coef(const PhaseDev &ph, const Grid &g, long long l, int d, int id, double kap, double &W, double &a, double &cw,
+                                          double &b, double &dw)
+{
+    const int last = g.pd[d] - 1;
+    const double ei = id < last ? 1.0 : 0.0;
+    const double Al = ph.A[d][l], Bl = ph.B[d][l];
+    W = ph.Wd[d][l];
+    a = ei * Bl;
+    cw = kap * ei * (Al - Bl);
+    if (id > 0) { const double Bm = ph.B[d][l - g.stride[d]]; b = -Bm; dw = -kap * (Al - Bm); }
+    else { b = 0.0; dw = 0.0; }
+}
+
+// per-cell diagonal block of M restricted to the active unknowns: D[0]=D00 D[1]=D11 D[2]=D02 D[3]=D12 D[4]=D22
+template <int N>
+__device__ __forceinline__ void cell_block(const FoldDev &fd, const Grid &g, long long l, const int c[PB_MAXD], bool act0, bool act1, bool actw, double D[5])
+{
+    D[0] = D[1] = D[2] = D[3] = D[4] = 0.0;
+    for (int p = 0; p < fd.nbulk; ++p) {
+        const PhaseDev &ph = fd.ph[p];
+        const double sp = fd.s[p];
+        double Dpp = sp * fd.cVc * ph.V[l] / D_at(ph, l), Dpw = 0.0, Dww = 0.0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            double W, a, cw, b, dw;
+            face_coef(ph, g, l, d, c[d], fd.kap[p], W, a, cw, b, dw);
+            Dpp += sp * W * a * a; Dpw += sp * W * a * cw; Dww += sp * W * cw * cw;
+            if (c[d] < g.pd[d] - 1) {
+                face_coef(ph, g, l + g.stride[d], d, c[d] + 1, fd.kap[p], W, a, cw, b, dw);
+                Dpp += sp * W * b * b; Dpw += sp * W * b * dw; Dww += sp * W * dw * dw;
+            }
+        }
+        D[p] = Dpp; D[2 + p] = Dpw; D[4] += Dww;
+    }
+    D[4] += fd.mwc * fd.ph[0].Gam[l];
+    if (!act0) { D[0] = 1.0; D[2] = 0.0; }
+    if (!act1) { D[1] = 1.0; D[3] = 0.0; }
+    if (!actw) { D[4] = 1.0; D[2] = 0.0; D[3] = 0.0; }
+}
+
+// L^-1 of a cell: (i00, i11, i20, i21, i22); diagonal (sc0, sc1, 0) outside the band
+__device__ __forceinline__ void cell_linv(const FoldDev &fd, long long l, double I[5])
+{
+    const int bo = fd.bord ? fd.bord[l] : -1;
+    if (bo >= 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) I[k] = fd.Linv[(size_t)k * fd.nB + bo];
+    } else {
+        I[0] = fd.sc[0][l]; I[1] = fd.nbulk > 1 ? fd.sc[1][l] : 0.0; I[2] = I[3] = I[4] = 0.0;
+    }
+}
+// R = Li * O * Lj^T for lower-triangular Li, Lj given as (i00,i11,i20,i21,i22)
+__device__ __forceinline__ void tri_sandwich(const double Li[5], const double O[9], const double Lj[5], double R[9])
+{
+    double T[9];   // T = Li * O
+#pragma unroll
+    for (int cidx = 0; cidx < 3; ++cidx) {
+        T[0 * 3 + cidx] = Li[0] * O[0 * 3 + cidx];
+        T[1 * 3 + cidx] = Li[1] * O[1 * 3 + cidx];
+        T[2 * 3 + cidx] = Li[2] * O[0 * 3 + cidx] + Li[3] * O[1 * 3 + cidx] + Li[4] * O[2 * 3 + cidx];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {   // R = T * Lj^T : R[r][0] = T[r][0] Lj00 ; R[r][1] = T[r][1] Lj11 ; R[r][2] = T[r][0] Lj20 + T[r][1] Lj21 + T[r][2] Lj22
+        R[r * 3 + 0] = T[r * 3 + 0] * Lj[0];
+        R[r * 3 + 1] = T[r * 3 + 1] * Lj[1];
+        R[r * 3 + 2] = T[r * 3 + 0] * Lj[2] + T[r * 3 + 1] * Lj[3] + T[r * 3 + 2] * Lj[4];
+    }
+}
+
+// ---- set-up kernels -------------------------------------------------------------------------------------------------------
+__global__ void kf_mark_band(long long nloc, const unsigned char *__restrict__ mw, long long *list, int *count, int cap)
+{
+    for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < nloc; l += (long long)gridDim.x * blockDim.x)
+        if (mw[l] & MB_IFREE) { const int k = atomicAdd(count, 1); if (k < cap) list[k] = l; }
+}
+__global__ void kf_bord_fill(int nB, const long long *__restrict__ Bcell, int *__restrict__ bord)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nB; k += gridDim.x * blockDim.x) bord[Bcell[k]] = k;
+}
+
+template <int N>
+__global__ void kf_diag(Grid g, FoldDev fd)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nown; t += (long long)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const long long l = t + g.plane;
+        const bool act0 = fd.m[0][l] & MB_FREE, act1 = fd.nbulk > 1 && (fd.m[1][l] & MB_FREE), actw = fd.has_w && (fd.mw[l] & MB_IFREE);
+        if (!act0 && !act1 && !actw) { fd.sc[0][l] = 0.0; if (fd.nbulk > 1) fd.sc[1][l] = 0.0; continue; }
+        double D[5];
+        cell_block<N>(fd, g, l, c, act0, act1, actw, D);
+        if (!actw) {
+            fd.sc[0][l] = (act0 && D[0] > 0.0) ? 1.0 / sqrt(D[0]) : 0.0;
+            if (fd.nbulk > 1) fd.sc[1][l] = (act1 && D[1] > 0.0) ? 1.0 / sqrt(D[1]) : 0.0;
+        } else {
+            fd.sc[0][l] = 0.0;
+            if (fd.nbulk > 1) fd.sc[1][l] = 0.0;
+            const int bo = fd.bord[l];
+            const double l00 = sqrt(D[0]), l11 = sqrt(D[1]);
+            const double l20 = D[2] / l00, l21 = D[3] / l11;
+            double S = D[4] - l20 * l20 - l21 * l21;
+            if (!(S > 1e-14 * D[4])) S = 1e-14 * D[4];
+            const double l22 = sqrt(S);
+            const double i00 = act0 ? 1.0 / l00 : 0.0, i11 = act1 ? 1.0 / l11 : 0.0, i22 = 1.0 / l22;
+            fd.Linv[(size_t)0 * fd.nB + bo] = i00;
+            fd.Linv[(size_t)1 * fd.nB + bo] = i11;
+            fd.Linv[(size_t)2 * fd.nB + bo] = -l20 * i00 * i22;
+            fd.Linv[(size_t)3 * fd.nB + bo] = -l21 * i11 * i22;
+            fd.Linv[(size_t)4 * fd.nB + bo] = i22;
+        }
+    }
+}
+
+template <int N>
+__global__ void kf_off(Grid g, FoldDev fd)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nown; t += (long long)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const long long l = t + g.plane;
+        const bool band = fd.bord && fd.bord[l] >= 0;
+        for (int p = 0; p < fd.nbulk; ++p) {
+            const double sl = fd.sc[p][l];
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                double v = 0.0;
+                if (sl != 0.0 && c[d] > 0 && !band) {
+                    const long long ln = l - g.stride[d];
+                    const double sn = fd.sc[p][ln];
+                    if (sn != 0.0 && !(fd.bord && fd.bord[ln] >= 0)) {
+                        double W, a, cw, b, dw;
+                        face_coef(fd.ph[p], g, l, d, c[d], fd.kap[p], W, a, cw, b, dw);
+                        v = fd.s[p] * W * a * b * sl * sn;
+                    }
+                }
+                fd.off[p][d][l] = v;
+            }
+        }
+    }
+}
+
+template <int N>
+__global__ void kf_mark_E(Grid g, const int *__restrict__ bord, long long *list, int *count, int cap)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nown; t += (long long)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const long long l = t + g.plane;
+        bool in = bord[l] >= 0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            if (c[d] > 0) in = in || bord[l - g.stride[d]] >= 0;
+            if (c[d] < g.pd[d] - 1) in = in || bord[l + g.stride[d]] >= 0;
+        }
+        if (in) { const int k = atomicAdd(count, 1); if (k < cap) list[k] = l; }
+    }
+}
+
+// coupling block between cell l (rows) and its neighbour across the lower face of `lf` (lf = l: neighbour l-s; lf = l+s: neighbour l+s)
+template <int N>
+__device__ __forceinline__ void face_block(const FoldDev &fd, const Grid &g, long long lf, int d, int idf, bool rows_are_upper, double O[9])
+{
+#pragma unroll
+    for (int k = 0; k < 9; ++k) O[k] = 0.0;
+    for (int p = 0; p < fd.nbulk; ++p) {
+        double W, a, cw, b, dw;
+        face_coef(fd.ph[p], g, lf, d, idf, fd.kap[p], W, a, cw, b, dw);
+        const double sw = fd.s[p] * W;
+        // upper cell (lf) vector: (a on comp p, cw on comp 2); lower cell (lf - s) vector: (b on comp p, dw on comp 2)
+        const double ru[2] = {a, cw}, rl[2] = {b, dw};
+        const double *rr = rows_are_upper ? ru : rl, *cc = rows_are_upper ? rl : ru;
+        O[p * 3 + p] += sw * rr[0] * cc[0];
+        O[p * 3 + 2] += sw * rr[0] * cc[1];
+        O[2 * 3 + p] += sw * rr[1] * cc[0];
+        O[2 * 3 + 2] += sw * rr[1] * cc[1];
+    }
+}
+
+template <int N>
+__global__ void kf_blocks(Grid g, FoldDev fd)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < fd.nE; e += gridDim.x * blockDim.x) {
+        const long long l = fd.Ecell[e];
+        int c[PB_MAXD];
+        cell_coords(g, l - g.plane, c);
+        const int bo = fd.bord[l];
+        fd.EB[e] = bo;
+        double Li[5], O[9], R[9];
+        cell_linv(fd, l, Li);
+        // self block: L^-1 D L^-T - I (exactly what the scaled operator carries on the diagonal block, no cancellation assumed)
+        if (bo >= 0) {
+            const bool act0 = fd.m[0][l] & MB_FREE, act1 = fd.nbulk > 1 && (fd.m[1][l] & MB_FREE);
+            double D[5];
+            cell_block<N>(fd, g, l, c, act0, act1, true, D);
+            O[0] = act0 ? D[0] : 0.0; O[1] = 0.0; O[2] = D[2];
+            O[3] = 0.0; O[4] = act1 ? D[1] : 0.0; O[5] = D[3];
+            O[6] = D[2]; O[7] = D[3]; O[8] = D[4];
+            tri_sandwich(Li, O, Li, R);
+            if (act0) R[0] -= 1.0;
+            if (act1) R[4] -= 1.0;
+            R[8] -= 1.0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) fd.Eblk[(size_t)k * fd.nE + e] = R[k];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            const long long s = g.stride[d];
+            int nbL = -1, nbU = -1;
+            double RL[9], RU[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { RL[k] = 0.0; RU[k] = 0.0; }
+            if (c[d] > 0) {
+                nbL = fd.bord[l - s];
+                if (bo >= 0 || nbL >= 0) {
+                    double Lj[5];
+                    cell_linv(fd, l - s, Lj);
+                    face_block<N>(fd, g, l, d, c[d], true, O);
+                    tri_sandwich(Li, O, Lj, RL);
+                }
+            }
+            if (c[d] < g.pd[d] - 1) {
+                nbU = fd.bord[l + s];
+                if (bo >= 0 || nbU >= 0) {
+                    double Lj[5];
+                    cell_linv(fd, l + s, Lj);
+                    face_block<N>(fd, g, l + s, d, c[d] + 1, false, O);
+                    tri_sandwich(Li, O, Lj, RU);
+                }
+            }
+            fd.EnbrB[(size_t)(2 * d) * fd.nE + e] = nbL;
+            fd.EnbrB[(size_t)(2 * d + 1) * fd.nE + e] = nbU;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                fd.Eblk[(size_t)((1 + 2 * d) * 9 + k) * fd.nE + e] = RL[k];
+                fd.Eblk[(size_t)((2 + 2 * d) * 9 + k) * fd.nE + e] = RU[k];
+            }
+        }
+    }
+}
+
+// active chunk census: flag[f * nchunk + ch] = 1 if any cell of the chunk carries a free unknown of bulk field f
+__global__ void kf_chunk_flags(Grid g, int nbulk, const unsigned char *__restrict__ m0, const unsigned char *__restrict__ m1, long long nchunk, int *flags)
+{
+    for (long long l = g.plane + blockIdx.x * (long long)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (long long)gridDim.x * blockDim.x) {
+        if (m0[l] & MB_FREE) flags[l / FCH] = 1;
+        if (nbulk > 1 && (m1[l] & MB_FREE)) flags[nchunk + l / FCH] = 1;
+    }
+}
+__global__ void kf_chunk_list(int nbulk, long long nchunk, const int *__restrict__ flags, int wchunks, int *items, int *count)
+{
+    const long long tot = (long long)nbulk * nchunk + wchunks;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        int v = -1;
+        if (i < (long long)nbulk * nchunk) { if (flags[i]) v = (int)(((unsigned)(i / nchunk) << 30) | (unsigned)(i % nchunk)); }
+        else v = (int)((2u << 30) | (unsigned)(i - (long long)nbulk * nchunk));
+        if (v != -1) items[atomicAdd(count, 1)] = v;
+    }
+}
+
+// ---- operator ---------------------------------------------------------------------------------------------------------------
+// dense part: y = x + sum_d off_d[l] x[l-s] + off_d[l+s] x[l+s] on the active chunks of each bulk field.
+// MODE 0: no dot; 1: publish (x, y); 2: publish (aux, y); 3: publish (y, x), (y, y)
+template <int N, int MODE>
+__global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items I, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter)
+{
+    double v[2] = {0.0, 0.0};
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        int f; long long l;
+        if (!item_index(I, it, f, l) || f >= 2) continue;
+        const double *__restrict__ xf = f == 0 ? x.f[0] : x.f[1];
+        const double xl = xf[l];
+        double acc = xl;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            const long long s = g.stride[d];
+            const double *__restrict__ of = f == 0 ? fd.off[0][d] : fd.off[1][d];
+            acc += of[l] * xf[l - s] + of[l + s] * xf[l + s];
+        }
+        (f == 0 ? y.f[0] : y.f[1])[l] = acc;
+        if (MODE == 1) v[0] += xl * acc;
+        if (MODE == 2) v[0] += (f == 0 ? aux.f[0] : aux.f[1])[l] * acc;
+        if (MODE == 3) { v[0] += acc * xl; v[1] += acc * acc; }
+    }
+    if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
+    if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
+}
+
+// band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here
+template <int N, int MODE>
+__global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter)
+{
+    double v[2] = {0.0, 0.0};
+    const int nE = fd.nE;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const long long l = fd.Ecell[e];
+        const int bo = fd.EB[e];
+        const bool two = fd.nbulk > 1;
+        const double x0 = x.f[0][l], x1 = two ? x.f[1][l] : 0.0, xw = bo >= 0 ? x.f[2][bo] : 0.0;
+        const double *__restrict__ blk = fd.Eblk + e;
+        double a0, a1, a2;
+        a0 = blk[0 * (size_t)nE] * x0 + blk[1 * (size_t)nE] * x1 + blk[2 * (size_t)nE] * xw;
+        a1 = blk[3 * (size_t)nE] * x0 + blk[4 * (size_t)nE] * x1 + blk[5 * (size_t)nE] * xw;
+        a2 = blk[6 * (size_t)nE] * x0 + blk[7 * (size_t)nE] * x1 + blk[8 * (size_t)nE] * xw;
+#pragma unroll
+        for (int k = 0; k < 2 * N; ++k) {
+            const int d = k >> 1;
+            const long long ln = (k & 1) ? l + g.stride[d] : l - g.stride[d];
+            const int nb = fd.EnbrB[(size_t)k * nE + e];
+            const double *__restrict__ bk = blk + (size_t)((1 + k) * 9) * nE;
+            const double n0 = x.f[0][ln], n1 = two ? x.f[1][ln] : 0.0, nw = nb >= 0 ? x.f[2][nb] : 0.0;
+            a0 += bk[0 * (size_t)nE] * n0 + bk[1 * (size_t)nE] * n1 + bk[2 * (size_t)nE] * nw;
+            a1 += bk[3 * (size_t)nE] * n0 + bk[4 * (size_t)nE] * n1 + bk[5 * (size_t)nE] * nw;
+            a2 += bk[6 * (size_t)nE] * n0 + bk[7 * (size_t)nE] * n1 + bk[8 * (size_t)nE] * nw;
+        }
+        const double y0p = y.f[0][l], y1p = two ? y.f[1][l] : 0.0;
+        y.f[0][l] = y0p + a0;
+        if (two) y.f[1][l] = y1p + a1;
+        double yw = 0.0;
+        if (bo >= 0) { yw = xw + a2; y.f[2][bo] = yw; }
+        if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
+        if (MODE == 2) v[0] += aux.f[0][l] * a0 + (two ? aux.f[1][l] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
+        if (MODE == 3) {
+            v[0] += x0 * a0 + x1 * a1 + xw * yw;
+            v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
+        }
+    }
+    if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
+    if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
+}
+
+// ---- vector kernels over the item list (dense active chunks + compact w) ------------------------------------------------------
+#define FV_LOOP(I)                                                  \
+    for (int it__ = blockIdx.x; it__ < (I).n; it__ += gridDim.x)    \
+        if (int f = 0; true)                                        \
+            if (long long i = 0; item_index((I), it__, f, i))
+
+__global__ void __launch_bounds__(FCH) kf_zero(Items I, FVec a) { FV_LOOP(I) a.f[f][i] = 0.0; }
+__global__ void __launch_bounds__(FCH) kf_copy2(Items I, FVec a, FVec b, FVec c) { FV_LOOP(I) { const double v = a.f[f][i]; b.f[f][i] = v; c.f[f][i] = v; } }
+// r = b - q ; publishes (r, r)
+__global__ void __launch_bounds__(FCH) kf_resid(Items I, FVec b, FVec q, FVec r, double *partials, double *results, unsigned *counter)
+{
+    double v[1] = {0.0};
+    FV_LOOP(I) { const double x = b.f[f][i] - q.f[f][i]; r.f[f][i] = x; v[0] += x * x; }
+    block_reduce_publish<1>(v, partials, results, counter);
+}
+__global__ void __launch_bounds__(FCH) kf_dot(Items I, FVec a, FVec b, double *partials, double *results, unsigned *counter)
+{
+    double v[1] = {0.0};
+    FV_LOOP(I) v[0] += a.f[f][i] * b.f[f][i];
+    block_reduce_publish<1>(v, partials, results, counter);
+}
+// CG: x += alpha p ; r -= alpha q ; publishes (rho_new, rr) = ((r, r), (r, r))
+__global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec q, FVec x, FVec r, double *partials, unsigned *counter)
+{
+    const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
+    double v[2] = {0.0, 0.0};
+    FV_LOOP(I) {
+        x.f[f][i] += alpha * p.f[f][i];
+        const double rn = r.f[f][i] - alpha * q.f[f][i];
+        r.f[f][i] = rn;
+        v[0] += rn * rn;
+    }
+    v[1] = v[0];
+    block_reduce_publish<2>(v, partials, res + sl_new, counter);
+}
+__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec p)
+{
+    const double beta = safe_div(res[sl_new], res[sl_rho]);
+    FV_LOOP(I) p.f[f][i] = r.f[f][i] + beta * p.f[f][i];
+}
+// BiCGSTAB
+__global__ void __launch_bounds__(FCH) kf_bicg_s(Items I, const double *res, int sl_rho, FVec r, FVec v, FVec s)
+{
+    const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
+    FV_LOOP(I) s.f[f][i] = r.f[f][i] - alpha * v.f[f][i];
+}
+__global__ void __launch_bounds__(FCH) kf_bicg_xr(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec s, FVec t, FVec r0, FVec x, FVec r, double *partials,
+                                                  unsigned *counter)
+{
+    const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
+    const double omega = safe_div(res[FS_TS_D] + res[FS_TS_B], res[FS_TT_D] + res[FS_TT_B]);
+    double v[2] = {0.0, 0.0};
+    FV_LOOP(I) {
+        const double sv = s.f[f][i];
+        x.f[f][i] += alpha * p.f[f][i] + omega * sv;
+        const double rn = sv - omega * t.f[f][i];
+        r.f[f][i] = rn;
+        v[0] += r0.f[f][i] * rn;
+        v[1] += rn * rn;
+    }
+    block_reduce_publish<2>(v, partials, res + sl_new, counter);
+}
+__global__ void __launch_bounds__(FCH) kf_bicg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec v, FVec p)
+{
+    const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
+    const double omega = safe_div(res[FS_TS_D] + res[FS_TS_B], res[FS_TT_D] + res[FS_TT_B]);
+    const double beta = safe_div(res[sl_new], res[sl_rho]) * safe_div(alpha, omega);
+    FV_LOOP(I) p.f[f][i] = r.f[f][i] + beta * (p.f[f][i] - omega * v.f[f][i]);
+}
+
+// ---- transforms between the reference's unknowns / rows and the scaled ones ----------------------------------------------------
+__device__ __forceinline__ double fold_rowscale(const FoldDev &fd, int p, long long l) { return fd.s[p] / (fd.c * D_at(fd.ph[p], l)); }
+
+// b^ = L^-1 (rowscale . b): dense part (band cells get 0 here, the band kernel overwrites them)
+__global__ void __launch_bounds__(FCH) kf_to_scaled_dense(FoldDev fd, Items I, MVec b, FVec bh)
+{
+    FV_LOOP(I) { if (f < 2) bh.f[f][i] = fd.sc[f][i] * fold_rowscale(fd, f, i) * b.f[f][i]; }
+}
+__global__ void kf_to_scaled_band(FoldDev fd, MVec b, FVec bh)
+{
+    for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
+        const long long l = fd.Bcell[k];
+        double I5[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) I5[q] = fd.Linv[(size_t)q * fd.nB + k];
+        const double v0 = I5[0] != 0.0 ? fold_rowscale(fd, 0, l) * b.f[0][l] : 0.0;
+        const double v1 = (fd.nbulk > 1 && I5[1] != 0.0) ? fold_rowscale(fd, 1, l) * b.f[1][l] : 0.0;
+        const double vw = fd.wrow * b.f[fd.nbulk][l];
+        bh.f[0][l] = I5[0] * v0;
+        if (fd.nbulk > 1) bh.f[1][l] = I5[1] * v1;
+        bh.f[2][k] = I5[2] * v0 + I5[3] * v1 + I5[4] * vw;
+    }
+}
+// x^ = L^T x (initial guess)
+__global__ void __launch_bounds__(FCH) kf_guess_dense(FoldDev fd, Items I, MVec x, FVec xh)
+{
+    FV_LOOP(I) { if (f < 2) { const double s = fd.sc[f][i]; xh.f[f][i] = s != 0.0 ? x.f[f][i] / s : 0.0; } }
+}
+__global__ void kf_guess_band(FoldDev fd, MVec x, FVec xh)
+{
+    for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
+        const long long l = fd.Bcell[k];
+        double I5[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) I5[q] = fd.Linv[(size_t)q * fd.nB + k];
+        const double l00 = I5[0] != 0.0 ? 1.0 / I5[0] : 0.0, l11 = I5[1] != 0.0 ? 1.0 / I5[1] : 0.0, l22 = 1.0 / I5[4];
+        const double l20 = -I5[2] * l00 * l22, l21 = -I5[3] * l11 * l22;
+        const double x0 = x.f[0][l], x1 = fd.nbulk > 1 ? x.f[1][l] : 0.0, xw = x.f[fd.nbulk][l];
+        xh.f[0][l] = l00 * x0 + l20 * xw;
+        if (fd.nbulk > 1) xh.f[1][l] = l11 * x1 + l21 * xw;
+        xh.f[2][k] = l22 * xw;
+    }
+}
+// x = L^-T x^
+__global__ void __launch_bounds__(FCH) kf_from_scaled_dense(FoldDev fd, Items I, FVec xh, MVec x)
+{
+    FV_LOOP(I) { if (f < 2) x.f[f][i] = fd.sc[f][i] * xh.f[f][i]; }
+}
+__global__ void kf_from_scaled_band(FoldDev fd, FVec xh, MVec x)
+{
+    for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
+        const long long l = fd.Bcell[k];
+        double I5[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) I5[q] = fd.Linv[(size_t)q * fd.nB + k];
+        const double hw = xh.f[2][k];
+        x.f[0][l] = I5[0] * xh.f[0][l] + I5[2] * hw;
+        if (fd.nbulk > 1) x.f[1][l] = I5[1] * xh.f[1][l] + I5[3] * hw;
+        x.f[fd.nbulk][l] = I5[4] * hw;
+    }
+}
+
+// =================================================================================================================================
+// host side
+// =================================================================================================================================
+struct FoldSys {
+    bool built = false;
+    FoldDev d;
+    // owned device memory
+    double *sc[2] = {}, *off[2][PB_MAXD] = {};
+    long long *Bcell = nullptr, *Ecell = nullptr;
+    int *bord = nullptr, *EB = nullptr, *EnbrB = nullptr, *items = nullptr;
+    double *Linv = nullptr, *Eblk = nullptr;
+    int nitems = 0;
+    Items I;
+    FVec x, b, r, p, v, r0, s, t;
+    bool have_bicg = false;
+    long long wcap = 0;
+    double key[8] = {};   // coefficient set the system was built for
+};
+
+static void fold_free_vec(FVec &a) { for (int f = 0; f < 3; ++f) { if (a.f[f]) cudaFree(a.f[f]); a.f[f] = nullptr; } }
+static void fold_free(FoldSys &F)
+{
+    for (int p = 0; p < 2; ++p) { dev_free(F.sc[p]); for (int d = 0; d < PB_MAXD; ++d) dev_free(F.off[p][d]); }
+    if (F.Bcell) cudaFree(F.Bcell); if (F.Ecell) cudaFree(F.Ecell); if (F.bord) cudaFree(F.bord); if (F.EB) cudaFree(F.EB);
+    if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
+    F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
+    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t};
+    for (FVec *a : vs) fold_free_vec(*a);
+    F.built = false; F.have_bicg = false;
+}
+
+static const int PB_NCCL_UINT8 = 1;
+// ghost planes of byte fields (masks)
+static int halo_exchange_bytes(pb200_ctx *ctx, const Grid &g, unsigned char *const *fields, int nf)
+{
+    if (ctx->nranks == 1) return PB200_OK;
+    NCCL_TRY(ctx, g_nccl.GroupStart());
+    for (int f = 0; f < nf; ++f) {
+        unsigned char *p = fields[f];
+        if (!p) continue;
+        size_t cnt = (size_t)g.plane;
+        if (ctx->rank > 0) {
+            NCCL_TRY(ctx, g_nccl.Send(p + g.plane, cnt, PB_NCCL_UINT8, ctx->rank - 1, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx, g_nccl.Recv(p, cnt, PB_NCCL_UINT8, ctx->rank - 1, ctx->comm, ctx->stream));
+        }
+        if (ctx->rank < ctx->nranks - 1) {
+            NCCL_TRY(ctx, g_nccl.Send(p + (long long)(g.lz - 2) * g.plane, cnt, PB_NCCL_UINT8, ctx->rank + 1, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx, g_nccl.Recv(p + (long long)(g.lz - 1) * g.plane, cnt, PB_NCCL_UINT8, ctx->rank + 1, ctx->comm, ctx->stream));
+        }
+    }
+    NCCL_TRY(ctx, g_nccl.GroupEnd());
+    return PB200_OK;
+}
+
+// halo of compact band arrays: `na` arrays of nB doubles (array a at base + a * nB).  The entries of the first / last OWNED plane
+// are contiguous ranges (the list is sorted by cell index) and match the neighbour's ghost prefix / suffix entry for entry.
+struct BandHalo { int lo_send0 = 0, lo_sendn = 0, hi_send0 = 0, hi_sendn = 0; };
+static int fold_band_ranges(pb200_ctx *ctx, const Grid &g, const std::vector<long long> &hB, int nBlo, int nBown, BandHalo *bh)
+{
+    // first owned plane: cells [plane, 2 plane); last owned plane: [(lz-2) plane, (lz-1) plane)
+    const long long p = g.plane;
+    int i = nBlo;
+    bh->lo_send0 = i;
+    while (i < nBlo + nBown && hB[i] < 2 * p) ++i;
+    bh->lo_sendn = i - bh->lo_send0;
+    int j = nBlo + nBown;
+    while (j > nBlo && hB[j - 1] >= (long long)(g.lz - 2) * p) --j;
+    bh->hi_send0 = j;
+    bh->hi_sendn = nBlo + nBown - j;
+    (void)ctx;
+    return PB200_OK;
+}
+static int fold_band_halo(pb200_ctx *ctx, const FoldSys &F, const BandHalo &bh, double *base, int na)
+{
+    if (ctx->nranks == 1 || F.d.nB == 0) return PB200_OK;
+    const int nB = F.d.nB, nBlo = F.d.nBlo, nBown = F.d.nBown, nBhi = nB - nBlo - nBown;
+    NCCL_TRY(ctx, g_nccl.GroupStart());
+    for (int a = 0; a < na; ++a) {
+        double *p = base + (size_t)a * nB;
+        if (ctx->rank > 0) {
+            if (bh.lo_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.lo_send0, (size_t)bh.lo_sendn, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+            if (nBlo) NCCL_TRY(ctx, g_nccl.Recv(p, (size_t)nBlo, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+        }
+        if (ctx->rank < ctx->nranks - 1) {
+            if (bh.hi_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.hi_send0, (size_t)bh.hi_sendn, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+            if (nBhi) NCCL_TRY(ctx, g_nccl.Recv(p + nBlo + nBown, (size_t)nBhi, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+        }
+    }
+    NCCL_TRY(ctx, g_nccl.GroupEnd());
+    return PB200_OK;
+}

@@ -5,6 +5,7 @@
 #include "krylov.cuh"
 #include "assemble.cuh"
 #include "geometry.cuh"
+#include "fold.cuh"
 
 #define DISPATCH_N(N_, ...)                  \
     do {                                     \
@@ -89,6 +90,7 @@ extern "C" int pb200_finalize(pb200_ctx *c)
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_partials); cudaFree(c->d_results); cudaFree(c->d_counter); cudaFreeHost(c->h_results);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return PB200_OK;
@@ -97,6 +99,13 @@ extern "C" const char *pb200_last_error(pb200_ctx *c) { return c ? c->err.c_str(
 extern "C" int pb200_sync(pb200_ctx *c) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return PB200_OK; }
 extern "C" int64_t pb200_launch_count(pb200_ctx *c) { return c ? c->launches : 0; }
 extern "C" uint64_t pb200_stream(pb200_ctx *c) { return (uint64_t)(uintptr_t)c->stream; }
+extern "C" int pb200_set_profiling(pb200_ctx *c, int enable)
+{
+    if (!c) return set_err(nullptr, PB200_EINVAL, "NULL ctx");
+    c->profile = enable != 0;
+    c->pev_used = 0;
+    return PB200_OK;
+}
 
 // =================================================================================================================
 // Capacity
@@ -343,6 +352,8 @@ struct pb200_solver {
     int64_t dof_bulk = 0, dof_ifc = 0;
     ApplyCoef diag_key = {-1, -1, -1, -1, -1};
     std::vector<double *> owned;
+    FoldSys F;
+    BandHalo bh;
 };
 
 static int solver_vec(pb200_solver *s, MVec *v)
@@ -411,6 +422,7 @@ extern "C" int pb200_solver_destroy(pb200_solver *s)
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (double *p : s->owned) cudaFree(p);
+    fold_free(s->F);
     dev_free(s->D1arr); dev_free(s->D2arr); dev_free(s->ufix1); dev_free(s->ufix2); dev_free(s->gK);
     for (int k = 0; k < 6; ++k) dev_free(s->bvals[k]);
     for (int a = 0; a < 2; ++a) { dev_free(s->Tw[a]); dev_free(s->Tg[a]); dev_free(s->gS[a]); for (int b = 0; b < 2; ++b) dev_free(s->fS[a][b]); }
@@ -490,6 +502,8 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
     int rc;
     if ((rc = halo_exchange(ctx, g, in.f, s->nf))) return rc;
     const int grid = sgrid(ctx, g.nown);
+    prof_mark(ctx);
+    ctx->apply_launches++;
     if (s->sp.phase_type == PB200_MONO) {
         GamSpec gs = {s->nf == 2 ? in.f[1] : nullptr, 1.0, nullptr, 0.0, 0.0};
         DISPATCH_N(g.N, (k_apply_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, ac, s->m1, in.f[0], gs, out.f[0],
@@ -501,6 +515,302 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
                                                                                  out.f[0], out.f[1], out.f[2])));
     }
     LAUNCH_CHECK(ctx);
+    prof_mark(ctx);
+    return PB200_OK;
+}
+
+
+// =================================================================================================================
+// folded fast path (fold.cuh): build + Krylov
+// =================================================================================================================
+static bool fold_eligible(const pb200_solver *s)
+{
+    const SysParams &sp = s->sp;
+    if (sp.phase_type == PB200_MONO) {
+        if (sp.beta == 0.0) return true;                       // Dirichlet interface: T_gamma known, SPD bulk system
+        return sp.beta > 0.0 && sp.alpha >= 0.0;               // Robin / Neumann rows symmetrise with positive factors
+    }
+    return sp.a1 != 0.0 && sp.a2 / sp.a1 > 0.0 && sp.b1 > 0.0 && sp.b2 > 0.0;
+}
+
+static int fold_alloc_vec(pb200_solver *s, FVec *v)
+{
+    FoldSys &F = s->F;
+    int rc;
+    for (int f = 0; f < 3; ++f) v->f[f] = nullptr;
+    for (int f = 0; f < F.d.nbulk; ++f) if ((rc = dev_alloc(s->ctx, &v->f[f], s->g.nloc))) return rc;
+    if (F.d.has_w && (rc = dev_alloc(s->ctx, &v->f[2], F.d.nB > 0 ? F.d.nB : 1))) return rc;
+    return PB200_OK;
+}
+
+// two-pass compaction + sort of a marked cell list
+template <typename Launch>
+static int fold_compact(pb200_ctx *ctx, Launch launch, long long **list, int *n)
+{
+    int *d_cnt = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&d_cnt, sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
+    launch((long long *)nullptr, d_cnt, 0);
+    LAUNCH_CHECK(ctx);
+    int cnt = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n = cnt;
+    *list = nullptr;
+    if (cnt > 0) {
+        CUDA_TRY(ctx, cudaMalloc((void **)list, sizeof(long long) * (size_t)cnt));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
+        launch(*list, d_cnt, cnt);
+        LAUNCH_CHECK(ctx);
+        thrust::sort(thrust::cuda::par.on(ctx->stream), *list, *list + cnt);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_cnt);
+    return PB200_OK;
+}
+
+static int fold_build(pb200_solver *s, const ApplyCoef &ac)
+{
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    FoldSys &F = s->F;
+    fold_free(F);
+    FoldDev &d = F.d;
+    memset(&d, 0, sizeof(d));
+    const SysParams &sp = s->sp;
+    const bool diph = sp.phase_type == PB200_DIPH;
+    d.N = g.N; d.nbulk = diph ? 2 : 1; d.has_w = diph || sp.beta != 0.0;
+    d.c = ac.c; d.cVc = ac.cV / ac.c;
+    if (diph) {
+        const double kap = sp.a2 / sp.a1;
+        d.kap[0] = kap; d.kap[1] = 1.0; d.s[0] = sp.b1 / kap; d.s[1] = sp.b2; d.mwc = 0.0; d.wrow = 1.0;
+        d.m[0] = s->m1; d.m[1] = s->m2; d.mw = s->m2;
+    } else {
+        d.kap[0] = d.kap[1] = 1.0; d.s[0] = d.s[1] = 1.0;
+        d.mwc = d.has_w ? sp.alpha / sp.beta : 0.0;
+        d.wrow = d.has_w ? 1.0 / (ac.c2 * sp.beta) : 1.0;
+        d.m[0] = s->m1; d.m[1] = s->m1; d.mw = s->m1;
+    }
+    d.ph[0] = s->p1; d.ph[1] = s->p2;
+    int rc;
+    {
+        unsigned char *ml[2] = {s->m1, s->m2};
+        if ((rc = halo_exchange_bytes(ctx, g, ml, 2))) return rc;
+    }
+    for (int p = 0; p < d.nbulk; ++p) {
+        if ((rc = dev_alloc(ctx, &F.sc[p], g.nloc))) return rc;
+        d.sc[p] = F.sc[p];
+        for (int dd = 0; dd < g.N; ++dd) { if ((rc = dev_alloc(ctx, &F.off[p][dd], g.nloc))) return rc; d.off[p][dd] = F.off[p][dd]; }
+    }
+    const int grid = red_grid(ctx, g.nloc);
+    std::vector<long long> hB;
+    if (d.has_w) {
+        const unsigned char *mw = d.mw;
+        const long long nloc = g.nloc;
+        cudaStream_t st = ctx->stream;
+        if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { kf_mark_band<<<grid, RED_THREADS, 0, st>>>(nloc, mw, list, cnt, cap); }, &F.Bcell, &d.nB))) return rc;
+        d.Bcell = F.Bcell;
+        hB.resize(d.nB);
+        if (d.nB) CUDA_TRY(ctx, cudaMemcpy(hB.data(), F.Bcell, sizeof(long long) * (size_t)d.nB, cudaMemcpyDeviceToHost));
+        int lo = 0, hi = 0;
+        for (long long l : hB) { if (l < g.plane) ++lo; else if (l >= g.plane + g.nown) ++hi; }
+        d.nBlo = lo; d.nBown = d.nB - lo - hi;
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.bord, sizeof(int) * (size_t)g.nloc));
+        CUDA_TRY(ctx, cudaMemsetAsync(F.bord, 0xFF, sizeof(int) * (size_t)g.nloc, ctx->stream));
+        if (d.nB) { kf_bord_fill<<<(d.nB + 255) / 256, 256, 0, ctx->stream>>>(d.nB, F.Bcell, F.bord); LAUNCH_CHECK(ctx); }
+        d.bord = F.bord;
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.Linv, sizeof(double) * 5 * (size_t)(d.nB > 0 ? d.nB : 1)));
+        CUDA_TRY(ctx, cudaMemsetAsync(F.Linv, 0, sizeof(double) * 5 * (size_t)(d.nB > 0 ? d.nB : 1), ctx->stream));
+        d.Linv = F.Linv;
+        fold_band_ranges(ctx, g, hB, d.nBlo, d.nBown, &s->bh);
+    }
+    const int gown = red_grid(ctx, g.nown);
+    DISPATCH_N(g.N, (kf_diag<N><<<gown, RED_THREADS, 0, ctx->stream>>>(g, d)));
+    LAUNCH_CHECK(ctx);
+    if ((rc = halo_exchange(ctx, g, F.sc, d.nbulk))) return rc;
+    if (d.has_w && (rc = fold_band_halo(ctx, F, s->bh, F.Linv, 5))) return rc;
+    if (d.has_w) {
+        const int *bord = F.bord;
+        cudaStream_t st = ctx->stream;
+        Grid gg = g;
+        if (g.N == 1) { if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { kf_mark_E<1><<<gown, RED_THREADS, 0, st>>>(gg, bord, list, cnt, cap); }, &F.Ecell, &d.nE))) return rc; }
+        else if (g.N == 2) { if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { kf_mark_E<2><<<gown, RED_THREADS, 0, st>>>(gg, bord, list, cnt, cap); }, &F.Ecell, &d.nE))) return rc; }
+        else { if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { kf_mark_E<3><<<gown, RED_THREADS, 0, st>>>(gg, bord, list, cnt, cap); }, &F.Ecell, &d.nE))) return rc; }
+        d.Ecell = F.Ecell;
+        const size_t nE = d.nE > 0 ? d.nE : 1;
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.EB, sizeof(int) * nE));
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.EnbrB, sizeof(int) * 2 * g.N * nE));
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.Eblk, sizeof(double) * (1 + 2 * g.N) * 9 * nE));
+        d.EB = F.EB; d.EnbrB = F.EnbrB; d.Eblk = F.Eblk;
+    }
+    DISPATCH_N(g.N, (kf_off<N><<<gown, RED_THREADS, 0, ctx->stream>>>(g, d)));
+    LAUNCH_CHECK(ctx);
+    {
+        double *fl[2 * PB_MAXD];
+        int nf = 0;
+        for (int p = 0; p < d.nbulk; ++p) for (int dd = 0; dd < g.N; ++dd) fl[nf++] = F.off[p][dd];
+        if ((rc = halo_exchange(ctx, g, fl, nf))) return rc;
+    }
+    if (d.has_w && d.nE > 0) {
+        DISPATCH_N(g.N, (kf_blocks<N><<<(d.nE + 127) / 128, 128, 0, ctx->stream>>>(g, d)));
+        LAUNCH_CHECK(ctx);
+    }
+    // active chunk list
+    {
+        const long long nchunk = (g.nloc + FCH - 1) / FCH;
+        const int wchunks = d.has_w ? (d.nBown + FCH - 1) / FCH : 0;
+        const long long tot = (long long)d.nbulk * nchunk + wchunks;
+        int *flags = nullptr, *d_cnt = nullptr;
+        CUDA_TRY(ctx, cudaMalloc((void **)&flags, sizeof(int) * (size_t)(d.nbulk * nchunk)));
+        CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(d.nbulk * nchunk), ctx->stream));
+        CUDA_TRY(ctx, cudaMalloc((void **)&d_cnt, sizeof(int)));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.items, sizeof(int) * (size_t)(tot > 0 ? tot : 1)));
+        kf_chunk_flags<<<gown, RED_THREADS, 0, ctx->stream>>>(g, d.nbulk, d.m[0], d.m[1], nchunk, flags);
+        LAUNCH_CHECK(ctx);
+        kf_chunk_list<<<red_grid(ctx, tot), RED_THREADS, 0, ctx->stream>>>(d.nbulk, nchunk, flags, wchunks, F.items, d_cnt);
+        LAUNCH_CHECK(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(&F.nitems, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (F.nitems > 0) {
+            unsigned *it = (unsigned *)F.items;
+            thrust::sort(thrust::cuda::par.on(ctx->stream), it, it + F.nitems);
+            ctx->launches++;
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(flags); cudaFree(d_cnt);
+        F.I.it = F.items; F.I.n = F.nitems; F.I.lo = g.plane; F.I.hi = g.plane + g.nown; F.I.wlo = d.nBlo; F.I.whi = d.nBlo + d.nBown;
+    }
+    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v};
+    for (FVec *v : vs) if ((rc = fold_alloc_vec(s, v))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    F.key[0] = ac.cV; F.key[1] = ac.c; F.key[2] = ac.c2;
+    F.built = true;
+    return PB200_OK;
+}
+
+static inline int fold_grid(pb200_solver *s) { int b = s->F.nitems; int cap = s->ctx->sm_count * 8; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
+static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
+
+// y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
+static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode)
+{
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    FoldSys &F = s->F;
+    int rc;
+    if (ctx->nranks > 1) {
+        double *fl[2] = {x.f[0], x.f[1]};
+        if ((rc = halo_exchange(ctx, g, fl, F.d.nbulk))) return rc;
+        if (F.d.has_w && (rc = fold_band_halo(ctx, F, s->bh, x.f[2], 1))) return rc;
+    }
+    double *res = ctx->d_results;
+    const int grid = fold_grid(s);
+    double *slotD = res + (mode == 3 ? FS_TS_D : FS_SIG_D), *slotB = res + (mode == 3 ? FS_TS_B : FS_SIG_B);
+    prof_mark(ctx);
+    ctx->apply_launches++;
+#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<grid, FCH, 0, ctx->stream>>>(g, F.d, F.I, x, y, aux, ctx->d_partials, slotD, ctx->d_counter)))
+    if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else FOLD_DENSE(3);
+#undef FOLD_DENSE
+    LAUNCH_CHECK(ctx);
+    prof_mark(ctx);
+    if (F.d.has_w && F.d.nE > 0) {
+        const int gb = band_grid(F.d.nE);
+#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 128, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter)))
+        if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else FOLD_BAND(3);
+#undef FOLD_BAND
+        LAUNCH_CHECK(ctx);
+    }
+    if (mode != 0 && (rc = allreduce_results(ctx, mode == 3 ? FS_TS_D : FS_SIG_D, mode == 3 ? 4 : 2))) return rc;
+    return PB200_OK;
+}
+
+// Krylov solve of the folded system.  In: s->b (reference rows, known parts eliminated), s->x (initial guess on the free sets).
+// Out: s->x.  The stopping test ||r^|| <= max(rtol ||b^||, atol) is on the block-Jacobi-scaled residual.
+static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, bool warm, int *iters, int *conv, double *rnorm_out, double *bnorm_out)
+{
+    pb200_ctx *ctx = s->ctx;
+    FoldSys &F = s->F;
+    const Items &I = F.I;
+    int rc;
+    if (method == PB200_KRYLOV_BICGSTAB && !F.have_bicg) {
+        FVec *vs[] = {&F.r0, &F.s, &F.t};
+        for (FVec *v : vs) if ((rc = fold_alloc_vec(s, v))) return rc;
+        F.have_bicg = true;
+    }
+    double *res = ctx->d_results;
+    CUDA_TRY(ctx, cudaMemsetAsync(res, 0, sizeof(double) * RED_SLOTS, ctx->stream));
+    const int grid = fold_grid(s);
+    const int gb = band_grid(F.d.nBown);
+    const bool band = F.d.has_w && F.d.nBown > 0;
+    // b^ and x^0
+    kf_to_scaled_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, s->b, F.b); LAUNCH_CHECK(ctx);
+    if (band) { kf_to_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->b, F.b); LAUNCH_CHECK(ctx); }
+    kf_dot<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.b, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
+    if (warm) {
+        kf_guess_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, s->x, F.x); LAUNCH_CHECK(ctx);
+        if (band) { kf_guess_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->x, F.x); LAUNCH_CHECK(ctx); }
+        if ((rc = fold_apply(s, F.x, F.v, F.v, 0))) return rc;
+        kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, F.r, ctx->d_partials, res + FS_RR0, ctx->d_counter); LAUNCH_CHECK(ctx);
+    } else {
+        kf_zero<<<grid, FCH, 0, ctx->stream>>>(I, F.x); LAUNCH_CHECK(ctx);
+        kf_zero<<<grid, FCH, 0, ctx->stream>>>(I, F.v); LAUNCH_CHECK(ctx);
+        kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, F.r, ctx->d_partials, res + FS_RR0, ctx->d_counter); LAUNCH_CHECK(ctx);
+    }
+    if ((rc = allreduce_results(ctx, FS_BB, 2))) return rc;
+    double h[2];
+    if ((rc = fetch_results(ctx, FS_BB, 2, h))) return rc;
+    const double bnorm = sqrt(h[0]);
+    double rnorm = sqrt(h[1]);
+    const double tol = fmax(o.rtol * bnorm, o.atol);
+    int it = 0, converged = rnorm <= tol ? 1 : 0;
+    int cur = 0;
+    if (!converged) {
+        // (rho, rr) pair 0 = (rr0, rr0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (method == PB200_KRYLOV_CG) {
+            kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
+            while (it < o.maxit) {
+                if ((rc = fold_apply(s, F.p, F.v, F.v, 1))) return rc;
+                const int nxt = cur ^ 1;
+                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.p); LAUNCH_CHECK(ctx);
+                cur = nxt;
+                ++it;
+                if (it % o.check_every == 0 || it == o.maxit) {
+                    if ((rc = fetch_results(ctx, 2 * cur + 1, 1, h))) return rc;
+                    rnorm = sqrt(h[0]);
+                    if (rnorm <= tol) { converged = 1; break; }
+                    if (!(rnorm == rnorm)) break;
+                }
+            }
+        } else {
+            kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.r0, F.p); LAUNCH_CHECK(ctx);
+            while (it < o.maxit) {
+                if ((rc = fold_apply(s, F.p, F.v, F.r0, 2))) return rc;
+                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, F.r, F.v, F.s); LAUNCH_CHECK(ctx);
+                if ((rc = fold_apply(s, F.s, F.t, F.t, 3))) return rc;
+                const int nxt = cur ^ 1;
+                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.v, F.p); LAUNCH_CHECK(ctx);
+                cur = nxt;
+                ++it;
+                if (it % o.check_every == 0 || it == o.maxit) {
+                    if ((rc = fetch_results(ctx, 2 * cur + 1, 1, h))) return rc;
+                    rnorm = sqrt(h[0]);
+                    if (rnorm <= tol) { converged = 1; break; }
+                    if (!(rnorm == rnorm)) break;
+                }
+            }
+        }
+    }
+    kf_from_scaled_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, F.x, s->x); LAUNCH_CHECK(ctx);
+    if (band) { kf_from_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, F.x, s->x); LAUNCH_CHECK(ctx); }
+    *iters = it; *conv = converged; *rnorm_out = rnorm; *bnorm_out = bnorm;
     return PB200_OK;
 }
 
@@ -525,6 +835,7 @@ static int build_masks(pb200_solver *s)
     s->dof_ifc = (int64_t)(cnt[1] + 0.5);
     s->masks_dirty = false;
     s->diag_key.cV = -1;
+    s->F.built = false;
     return PB200_OK;
 }
 
@@ -545,8 +856,9 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const int64_t launches0 = ctx->launches;
-    pb200_krylov_opts o = {PB200_KRYLOV_AUTO, 1e-10, 0.0, 10000, 1, 1};
+    const int64_t launches0 = ctx->launches, applies0 = ctx->apply_launches;
+    ctx->pev_used = 0;
+    pb200_krylov_opts o = {PB200_KRYLOV_AUTO, 1e-10, 0.0, 10000, 1, 1, PB200_PATH_AUTO};
     if (opts_in) o = *opts_in;
     if (o.maxit <= 0) o.maxit = 10000;
     if (o.check_every <= 0) o.check_every = 1;
@@ -556,7 +868,11 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     int method = o.method;
     const bool nonconstD = s->D1arr != nullptr;
     if (method == PB200_KRYLOV_AUTO) method = diph ? PB200_KRYLOV_BICGSTAB : PB200_KRYLOV_CG;
-    if (method == PB200_KRYLOV_CG && diph) return set_err(ctx, PB200_EUNSUPPORTED, "CG on the diphasic system is not available; use BiCGSTAB");
+    if (o.path == PB200_PATH_FOLDED && !fold_eligible(s))
+        return set_err(ctx, PB200_EUNSUPPORTED, "the folded path needs jump / Robin coefficients of one sign (alpha2/alpha1, beta1, beta2 > 0; beta > 0, alpha >= 0)");
+    const bool use_fold = o.path != PB200_PATH_GENERIC && fold_eligible(s);
+    if (method == PB200_KRYLOV_CG && diph && !use_fold)
+        return set_err(ctx, PB200_EUNSUPPORTED, "CG on the diphasic system needs the folded (symmetrised) path; use BiCGSTAB");
     (void)nonconstD;
     int rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -572,7 +888,7 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     } else {
         sc.cV = 0.0; sc.cn = 0; sc.c = 1.0; sc.ce = 0.0; sc.c2 = 1.0; sc.wf0 = 1.0; sc.wf1 = 0.0; sc.wg0 = 1.0; sc.wg1 = 0.0;
     }
-    sc.sym = (method == PB200_KRYLOV_CG) ? 1 : 0;
+    sc.sym = (!use_fold && method == PB200_KRYLOV_CG) ? 1 : 0;
     ApplyCoef ac = {sc.cV, sc.c, sc.c2, sc.sym, 1};
 
     // sources
@@ -610,8 +926,10 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m2, MB_FREE, s->Tw[1], s->x.f[1]); LAUNCH_CHECK(ctx);
         k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m2, MB_IFREE, s->Tg[1], s->x.f[2]); LAUNCH_CHECK(ctx);
     }
-    // Jacobi diagonal (cached per coefficient set)
-    if (memcmp(&ac, &s->diag_key, sizeof(ac)) != 0) {
+    if (use_fold) {
+        // folded system (cached per coefficient set and mask set)
+        if (!s->F.built || s->F.key[0] != ac.cV || s->F.key[1] != ac.c || s->F.key[2] != ac.c2) { if ((rc = fold_build(s, ac))) return rc; }
+    } else if (memcmp(&ac, &s->diag_key, sizeof(ac)) != 0) {   // Jacobi diagonal (cached per coefficient set)
         if (!diph) {
             DISPATCH_N(g.N, (k_diag_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, ac, s->m1, s->dinv.f[0], s->nf == 2 ? s->dinv.f[1] : nullptr)));
         } else {
@@ -628,6 +946,11 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     double *res = ctx->d_results;
     const dim3 vgrid(grid, s->nf);
     MVec z = s->x;  // alias
+    int it = 0, converged = 0;
+    double rnorm = 0.0, bnorm = 0.0;
+    if (use_fold) {
+        if ((rc = fold_solve(s, method, o, o.warm_start && unsteady, &it, &converged, &rnorm, &bnorm))) return rc;
+    } else {
     // bnorm
     k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->b, s->b, s->b, s->b, ctx->d_partials, res + SL_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
     if ((rc = allreduce_results(ctx, SL_BB, 1))) return rc;
@@ -638,10 +961,10 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
     double h[2];
     if ((rc = fetch_results(ctx, SL_BB, 2, h))) return rc;   // SL_BB, SL_TMP adjacent
-    const double bnorm = sqrt(h[0]);
-    double rnorm = sqrt(h[1]);
+    bnorm = sqrt(h[0]);
+    rnorm = sqrt(h[1]);
     const double tol = fmax(o.rtol * bnorm, o.atol);
-    int it = 0, converged = rnorm <= tol ? 1 : 0;
+    converged = rnorm <= tol ? 1 : 0;
     if (!converged) {
         if (method == PB200_KRYLOV_CG) {
             // p = dinv r ; rho = (r, dinv r)
@@ -695,6 +1018,7 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
             }
         }
     }
+    }   // generic path
     // ---- write the new state ----------------------------------------------------------------------------------------------
     k_store_bulk<<<grid, RED_THREADS, 0, ctx->stream>>>(g, z.f[0], s->ufix1, s->Tw[0]); LAUNCH_CHECK(ctx);
     if (!diph) {
@@ -714,6 +1038,8 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         stats->solve_ms = ms_solve; stats->setup_ms = ms_setup;
         stats->dof_bulk = s->dof_bulk; stats->dof_ifc = s->dof_ifc;
         stats->launches = ctx->launches - launches0;
+        stats->apply_ms = prof_collect(ctx);
+        stats->apply_launches = ctx->apply_launches - applies0;
     }
     if (!converged) return set_err(ctx, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
     return PB200_OK;
