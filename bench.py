@@ -263,11 +263,12 @@ def run_gpu(args):
     peak, peak_src = peaks()
     roof = None
     if apply_n and apply_ms > 0:
-        # x, y and N off-diagonal coefficients per active unknown: SURVEY 8(d)'s 8 (N + 3) minus the diagonal array, which the
-        # block-Jacobi scaling turns into the identity (DESIGN.md "Kernels and rooflines")
-        bytes_per_dof = 8 * (mesh.N + 2)
-        local_dof = dof / world
-        achieved = local_dof * bytes_per_dof / (apply_ms / apply_n * 1e-3) / 1e9
+        # algorithmic bytes of one apply launch on this rank: x and y for every cell of an active tile, plus the N
+        # coefficient arrays for the cells of tiles whose coefficients are not constants (interface band, domain border ring)
+        cu, cg = int(st.apply_cells_uniform), int(st.apply_cells_general)
+        launch_bytes = 8 * (2 * (cu + cg) + mesh.N * cg)
+        bytes_per_dof = launch_bytes / (dof / world)
+        achieved = launch_bytes / (apply_ms / apply_n * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -275,7 +276,8 @@ def run_gpu(args):
             if tj.get("nx") == nx:
                 traffic = tj.get("dram_bytes_per_launch")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "operator apply, dense part (kf_apply_dense)", "algorithmic_bytes_per_dof": bytes_per_dof, "launches_timed": int(apply_n),
+                "kernel": "operator apply, dense part (kf_apply_dense)", "algorithmic_bytes_per_dof": bytes_per_dof, "algorithmic_bytes_per_launch": launch_bytes,
+                "cells_constant_coef_tiles": cu, "cells_streamed_coef_tiles": cg, "launches_timed": int(apply_n),
                 "avg_launch_us": 1e3 * apply_ms / apply_n, "peak_source": peak_src}
 
     if rank == 0:
@@ -289,7 +291,7 @@ def run_gpu(args):
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": "Heat_2ph_2D diphasic BE step (BASELINE.json configs[1])", "grid": [nx, nx * N], "cells_per_gpu": [nx, nx],
-                          "dof": dof, "vector_length_4n": int(allsum(4 * nloc)), "scheme": "BE", "dt": dt, "krylov": "BiCGSTAB" if args.method != 1 else "CG",
+                          "dof": dof, "vector_length_4n": int(allsum(4 * nloc)), "scheme": "BE", "dt": dt, "krylov": "BiCGSTAB" if args.method == 2 else "CG (symmetrised, block-Jacobi-scaled system)",
                           "rtol": 1e-10, "iters_per_step": float(np.mean(iters)), "final_rel_residual": rnorm_rel,
                           "parallelism": f"y-slab x{world}" if world > 1 else "single GPU",
                           "l2": f"inputs larger than L2: {fields_mb:.0f} MB per field, > 30 fields streamed per step vs {L2_MB} MB L2",
@@ -309,8 +311,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=2048)
-    ap.add_argument("--method", type=int, default=0, help="0 auto (BiCGSTAB for the diphasic system), 1 CG, 2 BiCGSTAB")
-    ap.add_argument("--check-every", type=int, default=1)
+    ap.add_argument("--method", type=int, default=0, help="0 auto (CG on the folded system), 1 CG, 2 BiCGSTAB")
+    ap.add_argument("--check-every", type=int, default=8)
     ap.add_argument("--no-profile", action="store_true", help="do not bracket the apply launches with CUDA events")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -149,7 +149,7 @@ typedef struct {
     const double *g_arr[2];
 } pb200_step_in;
 
-#define PB200_KRYLOV_AUTO 0 /* CG for mono, BiCGSTAB for diph */
+#define PB200_KRYLOV_AUTO 0 /* CG on the folded (symmetrised) path and for mono; BiCGSTAB for diph on the generic path */
 #define PB200_KRYLOV_CG 1
 #define PB200_KRYLOV_BICGSTAB 2
 /* PB200_PATH_FOLDED: symmetrised, per-cell block-Jacobi-scaled stencil with unit diagonal (csrc/fold.cuh) -- the fast path, used
@@ -180,6 +180,9 @@ typedef struct {
     int64_t launches; /* kernels launched by this call */
     double apply_ms;        /* summed device time of the operator-apply launches (0 unless profiling is enabled) */
     int64_t apply_launches; /* number of operator-apply launches of this call */
+    /* folded path, this rank: cells of the tiles the apply kernel processes with per-tile constant coefficients (no coefficient
+     * arrays read) and with streamed coefficient arrays -- the census behind bench.py's algorithmic-byte count */
+    int64_t apply_cells_uniform, apply_cells_general;
 } pb200_step_stats;
 
 /* one solve: builds b from the device-resident state (b_*_unstead_diff / b_*_stead_diff), applies the border

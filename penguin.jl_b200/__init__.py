@@ -5,6 +5,6 @@ host-side mirror of the reference's Julia API.  The directory name contains a do
 (the loader module at the repo root).
 """
 from .api import *  # noqa: F401,F403
-from . import api, _lib, build as _build  # noqa: F401
+from . import api, _lib, slab, build as _build  # noqa: F401
 
 build = _build.build

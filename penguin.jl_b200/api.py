@@ -517,7 +517,7 @@ def _krylov_opts(method, kw):
     o.atol = float(kw.get("abstol", kw.get("atol", 0.0)))
     o.maxit = int(kw.get("maxiter", 20000))
     o.warm_start = int(kw.get("warm_start", 1))
-    o.check_every = int(kw.get("check_every", 1))
+    o.check_every = int(kw.get("check_every", 4))
     o.path = {"auto": 0, "generic": 1, "folded": 2}[kw.get("path", "auto")]
     return o
 
@@ -607,7 +607,7 @@ def DiffusionSteadyDiph(phase1, phase2, bc_b, ic):
     return s
 
 
-def solve_DiffusionSteadyDiph_(s, method="bicgstab", algorithm=None, **kw):
+def solve_DiffusionSteadyDiph_(s, method="auto", algorithm=None, **kw):
     """src/solver/diffusion.jl:163-175"""
     if s._h is None:
         raise RuntimeError("Solver is not initialized. Call a solver constructor first.")
@@ -656,7 +656,7 @@ def DiffusionUnsteadyDiph(phase1, phase2, bc_b, ic, Δt, Tᵢ, scheme):
     return s
 
 
-def solve_DiffusionUnsteadyDiph_(s, phase1, phase2, Δt, Tₑ, bc_b, ic, scheme, method="bicgstab", algorithm=None, states_stride=1, **kw):
+def solve_DiffusionUnsteadyDiph_(s, phase1, phase2, Δt, Tₑ, bc_b, ic, scheme, method="auto", algorithm=None, states_stride=1, **kw):
     """src/solver/diffusion.jl:422-454"""
     if s._h is None:
         raise RuntimeError("Solver is not initialized. Call a solver constructor first.")

@@ -50,19 +50,101 @@ struct FoldDev {
 
 struct FVec { double *f[3]; };   // f[0], f[1]: dense bulk fields; f[2]: compact w
 
-struct Items { const int *it; int n; long long lo, hi; int wlo, whi; };
-__device__ __forceinline__ bool item_index(const Items &I, int item, int &f, long long &idx)
+// Work items.  A bulk item is one TILE of 1024 cells of one bulk field, processed by a 256-thread block, FU = 4 cells per thread:
+// 1024 x 1 (1-D: thread t takes x = t + 256 k), 32 x 32 (2-D: row ty + 8 k), 32 x 8 x 4 (3-D: plane k) in the local array (ghost planes
+// included).  A warp reads 256 contiguous bytes per row, a thread has four independent cells in flight, and only the outermost ring of
+// tiles touches the domain border.  A w item is 1024 consecutive entries of the compact interface array.  Only tiles that hold a free
+// unknown are listed; each carries a precomputed record so that no index arithmetic beyond shifts happens in the kernels.
+#define FU 4
+#define FTILE (FCH * FU)
+struct __align__(16) TileRec {
+    long long base;        // local linear index of the tile origin (w items: first entry)
+    short nx;              // valid extent along x (w items: valid entries)
+    signed char f;         // field: 0, 1 bulk, 2 w
+    signed char ylo, yhi;  // valid range of the tile-relative y coordinate
+    signed char zlo, zhi;  // valid range of the tile-relative z coordinate
+    signed char pad;
+};
+struct Items {
+    const int *it; int n;
+    const TileRec *rec;            // [n]
+    int shx;                       // log2 of the thread extent in x: 8 (1-D, w items use this layout too) or 5
+    int kx, ky, kz;                // tile-relative coordinate advance per k: (256,0,0) 1-D, (0,8,0) 2-D, (0,0,1) 3-D
+    long long ustride;             // linear index advance per k
+    long long ld0, ld1, ld2;       // local array extents
+    int T0, T1, T2, nt0, nt1;      // tile extents and tiles per direction (build-time only)
+    int sd, lz;                    // slab dimension and its local extent (first / last plane of it are ghosts)
+    int wlo, whi;
+    const unsigned char *uni;      // [n] 1: the tile's coefficients are constants (ucoef) -- filled by kf_tile_meta
+    const double *ucoef;           // [n][PB_MAXD]
+};
+// cell k (0..FU-1) of this thread inside tile R: linear index and validity
+__device__ __forceinline__ bool tile_cell(const Items &I, const TileRec &R, int k, long long &idx)
 {
-    const unsigned v = (unsigned)I.it[item];
-    f = (int)(v >> 30);
-    const long long ch = (long long)(v & 0x3fffffffu);
-    if (f < 2) { idx = ch * FCH + threadIdx.x; return idx >= I.lo && idx < I.hi; }
-    idx = (long long)I.wlo + ch * FCH + threadIdx.x;
-    return idx < (long long)I.whi;
+    if (R.f >= 2) {   // compact w: 1-D layout
+        const int xr = (int)threadIdx.x + FCH * k;
+        idx = R.base + xr;
+        return xr < R.nx;
+    }
+    const int tx = (int)threadIdx.x & ((1 << I.shx) - 1), ty = (int)threadIdx.x >> I.shx;
+    const int xr = tx + I.kx * k, yr = ty + I.ky * k, zr = I.kz * k;
+    idx = R.base + tx + (long long)ty * I.ld0 + (long long)k * I.ustride;
+    return xr < R.nx && yr >= R.ylo && yr < R.yhi && zr >= R.zlo && zr < R.zhi;
+}
+__device__ __forceinline__ long long tile_of_cell(const Items &I, long long l)
+{
+    const long long c0 = l % I.ld0, q = l / I.ld0, c1 = q % I.ld1, c2 = q / I.ld1;
+    return (c0 / I.T0) + (long long)I.nt0 * ((c1 / I.T1) + (long long)I.nt1 * (c2 / I.T2));
+}
+// record of every listed item (one thread per item, build time)
+__global__ void kf_tile_records(Items I, TileRec *rec)
+{
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < I.n; it += gridDim.x * blockDim.x) {
+        const unsigned v = (unsigned)I.it[it];
+        const int f = (int)(v >> 30);
+        const long long ord = (long long)(v & 0x3fffffffu);
+        TileRec R;
+        R.f = (signed char)f; R.pad = 0;
+        if (f >= 2) {
+            R.base = (long long)I.wlo + ord * FTILE;
+            const long long left = (long long)I.whi - R.base;
+            R.nx = (short)(left < FTILE ? left : FTILE);
+            R.ylo = 0; R.yhi = 1; R.zlo = 0; R.zhi = 1;
+        } else {
+            const long long t0 = ord % I.nt0, q = ord / I.nt0, t1 = q % I.nt1, t2 = q / I.nt1;
+            const long long o[3] = {t0 * I.T0, t1 * I.T1, t2 * I.T2};
+            const long long ld[3] = {I.ld0, I.ld1, I.ld2};
+            const int T[3] = {I.T0, I.T1, I.T2};
+            int lo[3], hi[3];
+            for (int d = 0; d < 3; ++d) {
+                long long a = 0, b = ld[d] - o[d];
+                if (d == I.sd) { a = 1 - o[d]; b = (long long)I.lz - 1 - o[d]; }   // owned planes 1 .. lz-2 of the slab dimension
+                if (a < 0) a = 0;
+                if (b > T[d]) b = T[d];
+                if (b < a) b = a;
+                lo[d] = (int)a; hi[d] = (int)b;
+            }
+            R.base = o[0] + I.ld0 * (o[1] + I.ld1 * o[2]);
+            // x validity is [0, nx): the slab dimension is x only for 1-D grids, where the lower ghost is excluded by shifting the base
+            if (I.sd == 0) { R.base += lo[0]; R.nx = (short)(hi[0] - lo[0]); }
+            else R.nx = (short)hi[0];
+            R.ylo = (signed char)lo[1]; R.yhi = (signed char)hi[1]; R.zlo = (signed char)lo[2]; R.zhi = (signed char)hi[2];
+        }
+        rec[it] = R;
+    }
 }
 
 // result slots of the folded Krylov loops (dense-part and band-part partial sums are adjacent: one allreduce covers both)
-enum { FS_PAIR0 = 0, FS_PAIR1 = 2, FS_SIG_D = 4, FS_SIG_B = 5, FS_TS_D = 6, FS_TT_D = 7, FS_TS_B = 8, FS_TT_B = 9, FS_BB = 10, FS_RR0 = 11, FS_TMP = 12 };
+enum { FS_PAIR0 = 0, FS_PAIR1 = 2, FS_SIG_D = 4, FS_SIG_B = 5, FS_TS_D = 6, FS_TT_D = 7, FS_TS_B = 8, FS_TT_B = 9, FS_BB = 10, FS_RR0 = 11, FS_ITERS = 12, FS_TMP = 13 };
+
+// device-side stopping test: the Krylov kernels of an iteration turn into no-ops once ||r||^2 (slot `sl_rr`) is below the
+// tolerance, so the host may queue several iterations between two looks at the residual without doing extra work
+struct StopCrit { double rtol2, atol2; int sl_rr; };
+__device__ __forceinline__ bool fold_done(const double *res, const StopCrit &sc)
+{
+    const double rr = res[sc.sl_rr];
+    return rr <= fmax(sc.rtol2 * res[FS_BB], sc.atol2) || !(rr == rr);
+}
 
 // ---- face coefficients ---------------------------------------------------------------------------------------------------
 // lower face of cell l in direction d (id = coordinate of l along d): W!, (a, cw) on (u_l, w_l), (b, dw) on (u_{l-s}, w_{l-s})
@@ -309,48 +391,148 @@ __global__ void kf_blocks(Grid g, FoldDev fd)
     }
 }
 
-// active chunk census: flag[f * nchunk + ch] = 1 if any cell of the chunk carries a free unknown of bulk field f
-__global__ void kf_chunk_flags(Grid g, int nbulk, const unsigned char *__restrict__ m0, const unsigned char *__restrict__ m1, long long nchunk, int *flags)
+// active tile census: flags[f * ntile + tile] = 1 if any cell of the tile carries a free unknown of bulk field f
+__global__ void kf_tile_flags(Grid g, Items I, int nbulk, const unsigned char *__restrict__ m0, const unsigned char *__restrict__ m1, long long ntile, int *flags)
 {
     for (long long l = g.plane + blockIdx.x * (long long)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (long long)gridDim.x * blockDim.x) {
-        if (m0[l] & MB_FREE) flags[l / FCH] = 1;
-        if (nbulk > 1 && (m1[l] & MB_FREE)) flags[nchunk + l / FCH] = 1;
+        const bool a0 = m0[l] & MB_FREE, a1 = nbulk > 1 && (m1[l] & MB_FREE);
+        if (a0 || a1) {
+            const long long t = tile_of_cell(I, l);
+            if (a0) flags[t] = 1;
+            if (a1) flags[ntile + t] = 1;
+        }
     }
 }
-__global__ void kf_chunk_list(int nbulk, long long nchunk, const int *__restrict__ flags, int wchunks, int *items, int *count)
+__global__ void kf_tile_list(int nbulk, long long ntile, const int *__restrict__ flags, int wchunks, int *items, int *count)
 {
-    const long long tot = (long long)nbulk * nchunk + wchunks;
+    const long long tot = (long long)nbulk * ntile + wchunks;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
         int v = -1;
-        if (i < (long long)nbulk * nchunk) { if (flags[i]) v = (int)(((unsigned)(i / nchunk) << 30) | (unsigned)(i % nchunk)); }
-        else v = (int)((2u << 30) | (unsigned)(i - (long long)nbulk * nchunk));
+        if (i < (long long)nbulk * ntile) { if (flags[i]) v = (int)(((unsigned)(i / ntile) << 30) | (unsigned)(i % ntile)); }
+        else v = (int)((2u << 30) | (unsigned)(i - (long long)nbulk * ntile));
         if (v != -1) items[atomicAdd(count, 1)] = v;
     }
+}
+// per-item coefficient census: a tile whose coefficients off_d[l] and off_d[l + s_d] are one constant per direction over all its
+// cells (every tile of full cells away from the interface and the border) is applied without reading the coefficient arrays.
+// Also counts the cells of uniform / general tiles (results[0], results[1]) for the roofline accounting.
+template <int N>
+__global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I, unsigned char *uni, double *ucoef, double *partials, double *results, unsigned *counter)
+{
+    __shared__ double smn[PB_MAXD][FCH / 32], smx[PB_MAXD][FCH / 32];
+    __shared__ int s_uni;
+    double cnt[2] = {0.0, 0.0};
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        if (R.f >= 2) { if (threadIdx.x == 0) uni[it] = 0; continue; }   // uniform over the block
+        double mn[PB_MAXD], mx[PB_MAXD];
+        int nok = 0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) { mn[d] = 1e300; mx[d] = -1e300; }
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            long long l;
+            if (!tile_cell(I, R, k, l)) continue;
+            ++nok;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double *__restrict__ of = R.f == 0 ? fd.off[0][d] : fd.off[1][d];
+                const double a = of[l], b = of[l + g.stride[d]];
+                mn[d] = fmin(mn[d], fmin(a, b)); mx[d] = fmax(mx[d], fmax(a, b));
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o)); }
+            if ((threadIdx.x & 31) == 0) { smn[d][threadIdx.x >> 5] = mn[d]; smx[d][threadIdx.x >> 5] = mx[d]; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bool u = true;
+            for (int d = 0; d < N; ++d) {
+                double a = 1e300, b = -1e300;
+                for (int w = 0; w < FCH / 32; ++w) { a = fmin(a, smn[d][w]); b = fmax(b, smx[d][w]); }
+                u = u && (a == b);
+                ucoef[(size_t)it * PB_MAXD + d] = a;
+            }
+            uni[it] = u ? 1 : 0;
+            s_uni = u ? 1 : 0;
+        }
+        __syncthreads();
+        cnt[s_uni ? 0 : 1] += (double)nok;
+        __syncthreads();
+    }
+    block_reduce_publish<2>(cnt, partials, results, counter);
 }
 
 // ---- operator ---------------------------------------------------------------------------------------------------------------
 // dense part: y = x + sum_d off_d[l] x[l-s] + off_d[l+s] x[l+s] on the active chunks of each bulk field.
 // MODE 0: no dot; 1: publish (x, y); 2: publish (aux, y); 3: publish (y, x), (y, y)
 template <int N, int MODE>
-__global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items I, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter)
+__global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items I, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
+                                                      const double *res, StopCrit stop)
 {
+    if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
-        int f; long long l;
-        if (!item_index(I, it, f, l) || f >= 2) continue;
+        const TileRec R = I.rec[it];
+        if (R.f >= 2) continue;
+        const int f = R.f;
         const double *__restrict__ xf = f == 0 ? x.f[0] : x.f[1];
-        const double xl = xf[l];
-        double acc = xl;
+        double *__restrict__ yf = f == 0 ? y.f[0] : y.f[1];
+        const double *__restrict__ af = f == 0 ? aux.f[0] : aux.f[1];
+        const bool uni = I.uni[it] != 0;
+        long long l[FU];
+        bool ok[FU];
+        double xl[FU], xm[FU][N], xp[FU][N], cm[FU][N], cp[FU][N], av[FU];
+        // phase 1: every load of the FU cells is issued before the first use
 #pragma unroll
-        for (int d = 0; d < N; ++d) {
-            const long long s = g.stride[d];
-            const double *__restrict__ of = f == 0 ? fd.off[0][d] : fd.off[1][d];
-            acc += of[l] * xf[l - s] + of[l + s] * xf[l + s];
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, l[k]);
+            if (ok[k]) {
+                xl[k] = xf[l[k]];
+                if (MODE == 2) av[k] = af[l[k]];
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    const long long s = g.stride[d];
+                    xm[k][d] = xf[l[k] - s];
+                    xp[k][d] = xf[l[k] + s];
+                }
+            }
         }
-        (f == 0 ? y.f[0] : y.f[1])[l] = acc;
-        if (MODE == 1) v[0] += xl * acc;
-        if (MODE == 2) v[0] += (f == 0 ? aux.f[0] : aux.f[1])[l] * acc;
-        if (MODE == 3) { v[0] += acc * xl; v[1] += acc * acc; }
+        if (uni) {
+            const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double c = uc[d];
+#pragma unroll
+                for (int k = 0; k < FU; ++k) { cm[k][d] = c; cp[k][d] = c; }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < FU; ++k)
+                if (ok[k]) {
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        const double *__restrict__ of = f == 0 ? fd.off[0][d] : fd.off[1][d];
+                        cm[k][d] = of[l[k]];
+                        cp[k][d] = of[l[k] + g.stride[d]];
+                    }
+                }
+        }
+        // phase 2
+#pragma unroll
+        for (int k = 0; k < FU; ++k)
+            if (ok[k]) {
+                double acc = xl[k];
+#pragma unroll
+                for (int d = 0; d < N; ++d) acc += cm[k][d] * xm[k][d] + cp[k][d] * xp[k][d];
+                yf[l[k]] = acc;
+                if (MODE == 1) v[0] += xl[k] * acc;
+                if (MODE == 2) v[0] += av[k] * acc;
+                if (MODE == 3) { v[0] += acc * xl[k]; v[1] += acc * acc; }
+            }
     }
     if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
@@ -358,8 +540,10 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
 
 // band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here
 template <int N, int MODE>
-__global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter)
+__global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter, const double *res,
+                              StopCrit stop)
 {
+    if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
     const int nE = fd.nE;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
@@ -402,8 +586,10 @@ __global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, doub
 // ---- vector kernels over the item list (dense active chunks + compact w) ------------------------------------------------------
 #define FV_LOOP(I)                                                  \
     for (int it__ = blockIdx.x; it__ < (I).n; it__ += gridDim.x)    \
-        if (int f = 0; true)                                        \
-            if (long long i = 0; item_index((I), it__, f, i))
+        if (const TileRec R__ = (I).rec[it__]; true)                \
+            if (const int f = R__.f; true)                          \
+                _Pragma("unroll") for (int k__ = 0; k__ < FU; ++k__) \
+                    if (long long i = 0; tile_cell((I), R__, k__, i))
 
 __global__ void __launch_bounds__(FCH) kf_zero(Items I, FVec a) { FV_LOOP(I) a.f[f][i] = 0.0; }
 __global__ void __launch_bounds__(FCH) kf_copy2(Items I, FVec a, FVec b, FVec c) { FV_LOOP(I) { const double v = a.f[f][i]; b.f[f][i] = v; c.f[f][i] = v; } }
@@ -421,33 +607,70 @@ __global__ void __launch_bounds__(FCH) kf_dot(Items I, FVec a, FVec b, double *p
     block_reduce_publish<1>(v, partials, results, counter);
 }
 // CG: x += alpha p ; r -= alpha q ; publishes (rho_new, rr) = ((r, r), (r, r))
-__global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec q, FVec x, FVec r, double *partials, unsigned *counter)
+__global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec q, FVec x, FVec r, double *partials, unsigned *counter,
+                                                    StopCrit stop)
 {
+    if (fold_done(res, stop)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) res[FS_ITERS] += 1.0;
     const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
     double v[2] = {0.0, 0.0};
-    FV_LOOP(I) {
-        x.f[f][i] += alpha * p.f[f][i];
-        const double rn = r.f[f][i] - alpha * q.f[f][i];
-        r.f[f][i] = rn;
-        v[0] += rn * rn;
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        const int f = R.f;
+        const double *__restrict__ pf = f == 0 ? p.f[0] : (f == 1 ? p.f[1] : p.f[2]);
+        const double *__restrict__ qf = f == 0 ? q.f[0] : (f == 1 ? q.f[1] : q.f[2]);
+        double *__restrict__ xf = f == 0 ? x.f[0] : (f == 1 ? x.f[1] : x.f[2]);
+        double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
+        long long i[FU]; bool ok[FU]; double pv[FU], qv[FU], xv[FU], rv[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, i[k]);
+            if (ok[k]) { pv[k] = pf[i[k]]; qv[k] = qf[i[k]]; xv[k] = xf[i[k]]; rv[k] = rf[i[k]]; }
+        }
+#pragma unroll
+        for (int k = 0; k < FU; ++k)
+            if (ok[k]) {
+                xf[i[k]] = xv[k] + alpha * pv[k];
+                const double rn = rv[k] - alpha * qv[k];
+                rf[i[k]] = rn;
+                v[0] += rn * rn;
+            }
     }
     v[1] = v[0];
     block_reduce_publish<2>(v, partials, res + sl_new, counter);
 }
-__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec p)
+__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec p, StopCrit stop)
 {
+    if (fold_done(res, stop)) return;
     const double beta = safe_div(res[sl_new], res[sl_rho]);
-    FV_LOOP(I) p.f[f][i] = r.f[f][i] + beta * p.f[f][i];
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        const int f = R.f;
+        const double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
+        double *__restrict__ pf = f == 0 ? p.f[0] : (f == 1 ? p.f[1] : p.f[2]);
+        long long i[FU]; bool ok[FU]; double pv[FU], rv[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, i[k]);
+            if (ok[k]) { pv[k] = pf[i[k]]; rv[k] = rf[i[k]]; }
+        }
+#pragma unroll
+        for (int k = 0; k < FU; ++k)
+            if (ok[k]) pf[i[k]] = rv[k] + beta * pv[k];
+    }
 }
 // BiCGSTAB
-__global__ void __launch_bounds__(FCH) kf_bicg_s(Items I, const double *res, int sl_rho, FVec r, FVec v, FVec s)
+__global__ void __launch_bounds__(FCH) kf_bicg_s(Items I, const double *res, int sl_rho, FVec r, FVec v, FVec s, StopCrit stop)
 {
+    if (fold_done(res, stop)) return;
     const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
     FV_LOOP(I) s.f[f][i] = r.f[f][i] - alpha * v.f[f][i];
 }
 __global__ void __launch_bounds__(FCH) kf_bicg_xr(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec s, FVec t, FVec r0, FVec x, FVec r, double *partials,
-                                                  unsigned *counter)
+                                                  unsigned *counter, StopCrit stop)
 {
+    if (fold_done(res, stop)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) res[FS_ITERS] += 1.0;
     const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
     const double omega = safe_div(res[FS_TS_D] + res[FS_TS_B], res[FS_TT_D] + res[FS_TT_B]);
     double v[2] = {0.0, 0.0};
@@ -461,12 +684,19 @@ __global__ void __launch_bounds__(FCH) kf_bicg_xr(Items I, double *res, int sl_r
     }
     block_reduce_publish<2>(v, partials, res + sl_new, counter);
 }
-__global__ void __launch_bounds__(FCH) kf_bicg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec v, FVec p)
+__global__ void __launch_bounds__(FCH) kf_bicg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec v, FVec p, StopCrit stop)
 {
+    if (fold_done(res, stop)) return;
     const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
     const double omega = safe_div(res[FS_TS_D] + res[FS_TS_B], res[FS_TT_D] + res[FS_TT_B]);
     const double beta = safe_div(res[sl_new], res[sl_rho]) * safe_div(alpha, omega);
     FV_LOOP(I) p.f[f][i] = r.f[f][i] + beta * (p.f[f][i] - omega * v.f[f][i]);
+}
+
+// iteration skipped by the stopping test: copy the (rho, rr) pair forward
+__global__ void kf_carry_pair(double *res, int sl_old, int sl_new, StopCrit stop)
+{
+    if (threadIdx.x == 0 && fold_done(res, stop)) { res[sl_new] = res[sl_old]; res[sl_new + 1] = res[sl_old + 1]; }
 }
 
 // ---- transforms between the reference's unknowns / rows and the scaled ones ----------------------------------------------------
@@ -543,6 +773,10 @@ struct FoldSys {
     int *bord = nullptr, *EB = nullptr, *EnbrB = nullptr, *items = nullptr;
     double *Linv = nullptr, *Eblk = nullptr;
     int nitems = 0;
+    unsigned char *uni = nullptr;
+    double *ucoef = nullptr;
+    TileRec *rec = nullptr;
+    long long cells_uniform = 0, cells_general = 0;   // cells of tiles applied with constant / streamed coefficients (this rank)
     Items I;
     FVec x, b, r, p, v, r0, s, t;
     bool have_bicg = false;
@@ -555,6 +789,7 @@ static void fold_free(FoldSys &F)
 {
     for (int p = 0; p < 2; ++p) { dev_free(F.sc[p]); for (int d = 0; d < PB_MAXD; ++d) dev_free(F.off[p][d]); }
     if (F.Bcell) cudaFree(F.Bcell); if (F.Ecell) cudaFree(F.Ecell); if (F.bord) cudaFree(F.bord); if (F.EB) cudaFree(F.EB);
+    if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t};

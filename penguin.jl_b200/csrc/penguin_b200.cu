@@ -656,20 +656,32 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         DISPATCH_N(g.N, (kf_blocks<N><<<(d.nE + 127) / 128, 128, 0, ctx->stream>>>(g, d)));
         LAUNCH_CHECK(ctx);
     }
-    // active chunk list
+    // active tile list + per-tile coefficient census
     {
-        const long long nchunk = (g.nloc + FCH - 1) / FCH;
-        const int wchunks = d.has_w ? (d.nBown + FCH - 1) / FCH : 0;
-        const long long tot = (long long)d.nbulk * nchunk + wchunks;
+        Items &I = F.I;
+        memset(&I, 0, sizeof(I));
+        I.sd = g.sd; I.lz = g.lz;
+        I.ld0 = g.sd == 0 ? g.lz : g.pd[0];
+        I.ld1 = g.N < 2 ? 1 : (g.sd == 1 ? g.lz : g.pd[1]);
+        I.ld2 = g.N < 3 ? 1 : g.lz;
+        if (g.N == 1) { I.T0 = FTILE; I.T1 = 1; I.T2 = 1; I.shx = 8; I.kx = FCH; I.ky = 0; I.kz = 0; I.ustride = FCH; }
+        else if (g.N == 2) { I.T0 = 32; I.T1 = 32; I.T2 = 1; I.shx = 5; I.kx = 0; I.ky = 8; I.kz = 0; I.ustride = 8 * I.ld0; }
+        else { I.T0 = 32; I.T1 = 8; I.T2 = 4; I.shx = 5; I.kx = 0; I.ky = 0; I.kz = 1; I.ustride = I.ld0 * I.ld1; }
+        I.nt0 = (int)((I.ld0 + I.T0 - 1) / I.T0); I.nt1 = (int)((I.ld1 + I.T1 - 1) / I.T1);
+        const long long nt2 = (I.ld2 + I.T2 - 1) / I.T2;
+        const long long ntile = (long long)I.nt0 * I.nt1 * nt2;
+        if (ntile >= (1ll << 30)) return set_err(ctx, PB200_EUNSUPPORTED, "more than 2^30 tiles per rank");
+        const int wchunks = d.has_w ? (d.nBown + FTILE - 1) / FTILE : 0;
+        const long long tot = (long long)d.nbulk * ntile + wchunks;
         int *flags = nullptr, *d_cnt = nullptr;
-        CUDA_TRY(ctx, cudaMalloc((void **)&flags, sizeof(int) * (size_t)(d.nbulk * nchunk)));
-        CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(d.nbulk * nchunk), ctx->stream));
+        CUDA_TRY(ctx, cudaMalloc((void **)&flags, sizeof(int) * (size_t)(d.nbulk * ntile)));
+        CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(d.nbulk * ntile), ctx->stream));
         CUDA_TRY(ctx, cudaMalloc((void **)&d_cnt, sizeof(int)));
         CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
         CUDA_TRY(ctx, cudaMalloc((void **)&F.items, sizeof(int) * (size_t)(tot > 0 ? tot : 1)));
-        kf_chunk_flags<<<gown, RED_THREADS, 0, ctx->stream>>>(g, d.nbulk, d.m[0], d.m[1], nchunk, flags);
+        kf_tile_flags<<<gown, RED_THREADS, 0, ctx->stream>>>(g, I, d.nbulk, d.m[0], d.m[1], ntile, flags);
         LAUNCH_CHECK(ctx);
-        kf_chunk_list<<<red_grid(ctx, tot), RED_THREADS, 0, ctx->stream>>>(d.nbulk, nchunk, flags, wchunks, F.items, d_cnt);
+        kf_tile_list<<<red_grid(ctx, tot), RED_THREADS, 0, ctx->stream>>>(d.nbulk, ntile, flags, wchunks, F.items, d_cnt);
         LAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaMemcpyAsync(&F.nitems, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -680,7 +692,20 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         }
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(flags); cudaFree(d_cnt);
-        F.I.it = F.items; F.I.n = F.nitems; F.I.lo = g.plane; F.I.hi = g.plane + g.nown; F.I.wlo = d.nBlo; F.I.whi = d.nBlo + d.nBown;
+        I.it = F.items; I.n = F.nitems; I.wlo = d.nBlo; I.whi = d.nBlo + d.nBown;
+        const size_t ni = F.nitems > 0 ? F.nitems : 1;
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.rec, sizeof(TileRec) * ni));
+        if (F.nitems > 0) { kf_tile_records<<<(F.nitems + 255) / 256, 256, 0, ctx->stream>>>(I, F.rec); LAUNCH_CHECK(ctx); }
+        I.rec = F.rec;
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.uni, ni));
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.ucoef, sizeof(double) * PB_MAXD * ni));
+        I.uni = F.uni; I.ucoef = F.ucoef;
+        int gm = F.nitems; if (gm > ctx->sm_count * 8) gm = ctx->sm_count * 8; if (gm < 1) gm = 1;
+        DISPATCH_N(g.N, (kf_tile_meta<N><<<gm, FCH, 0, ctx->stream>>>(g, d, I, F.uni, F.ucoef, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
+        LAUNCH_CHECK(ctx);
+        double cnt[2];
+        if ((rc = fetch_results(ctx, SL_TMP, 2, cnt))) return rc;
+        F.cells_uniform = (long long)(cnt[0] + 0.5); F.cells_general = (long long)(cnt[1] + 0.5);
     }
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v};
     for (FVec *v : vs) if ((rc = fold_alloc_vec(s, v))) return rc;
@@ -694,7 +719,7 @@ static inline int fold_grid(pb200_solver *s) { int b = s->F.nitems; int cap = s-
 static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
 
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
-static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode)
+static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode, StopCrit stop = StopCrit{0.0, 0.0, -1})
 {
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
@@ -710,14 +735,14 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     double *slotD = res + (mode == 3 ? FS_TS_D : FS_SIG_D), *slotB = res + (mode == 3 ? FS_TS_B : FS_SIG_B);
     prof_mark(ctx);
     ctx->apply_launches++;
-#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<grid, FCH, 0, ctx->stream>>>(g, F.d, F.I, x, y, aux, ctx->d_partials, slotD, ctx->d_counter)))
+#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<grid, FCH, 0, ctx->stream>>>(g, F.d, F.I, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop)))
     if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else FOLD_DENSE(3);
 #undef FOLD_DENSE
     LAUNCH_CHECK(ctx);
     prof_mark(ctx);
     if (F.d.has_w && F.d.nE > 0) {
         const int gb = band_grid(F.d.nE);
-#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 128, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter)))
+#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 128, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
         if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else FOLD_BAND(3);
 #undef FOLD_BAND
         LAUNCH_CHECK(ctx);
@@ -770,41 +795,48 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         // (rho, rr) pair 0 = (rr0, rr0)
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        if (method == PB200_KRYLOV_CG) {
-            kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
-            while (it < o.maxit) {
-                if ((rc = fold_apply(s, F.p, F.v, F.v, 1))) return rc;
-                const int nxt = cur ^ 1;
-                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter); LAUNCH_CHECK(ctx);
+        const bool cg = method == PB200_KRYLOV_CG;
+        if (cg) { kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx); }
+        else { kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.r0, F.p); LAUNCH_CHECK(ctx); }
+        // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
+        // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
+        int queued = 0;
+        while (queued < o.maxit) {
+            const int nxt = cur ^ 1;
+            StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, 2 * cur + 1};
+            StopCrit stn = {o.rtol * o.rtol, o.atol * o.atol, 2 * nxt + 1};
+            if (cg) {
+                if ((rc = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc;
+                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
                 if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
-                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.p); LAUNCH_CHECK(ctx);
-                cur = nxt;
-                ++it;
-                if (it % o.check_every == 0 || it == o.maxit) {
-                    if ((rc = fetch_results(ctx, 2 * cur + 1, 1, h))) return rc;
-                    rnorm = sqrt(h[0]);
-                    if (rnorm <= tol) { converged = 1; break; }
-                    if (!(rnorm == rnorm)) break;
-                }
+                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.p, stn); LAUNCH_CHECK(ctx);
+            } else {
+                if ((rc = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc;
+                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
+                if ((rc = fold_apply(s, F.s, F.t, F.t, 3, st))) return rc;
+                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.v, F.p, stn); LAUNCH_CHECK(ctx);
             }
-        } else {
-            kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.r0, F.p); LAUNCH_CHECK(ctx);
-            while (it < o.maxit) {
-                if ((rc = fold_apply(s, F.p, F.v, F.r0, 2))) return rc;
-                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, F.r, F.v, F.s); LAUNCH_CHECK(ctx);
-                if ((rc = fold_apply(s, F.s, F.t, F.t, 3))) return rc;
-                const int nxt = cur ^ 1;
-                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter); LAUNCH_CHECK(ctx);
-                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
-                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.v, F.p); LAUNCH_CHECK(ctx);
-                cur = nxt;
-                ++it;
-                if (it % o.check_every == 0 || it == o.maxit) {
-                    if ((rc = fetch_results(ctx, 2 * cur + 1, 1, h))) return rc;
-                    rnorm = sqrt(h[0]);
-                    if (rnorm <= tol) { converged = 1; break; }
-                    if (!(rnorm == rnorm)) break;
+            // a skipped iteration publishes nothing: carry the converged pair over so that the next iteration sees it too
+            kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, 2 * cur, 2 * nxt, st); LAUNCH_CHECK(ctx);
+            cur = nxt;
+            ++queued;
+            if (queued % o.check_every == 0 || queued == o.maxit) {
+                double hh[2];
+                if ((rc = fetch_results(ctx, 2 * cur + 1, 1, hh))) return rc;
+                if ((rc = fetch_results(ctx, FS_ITERS, 1, hh + 1))) return rc;
+                rnorm = sqrt(hh[0]);
+                it = (int)(hh[1] + 0.5);
+                if (getenv("PB200_DEBUG")) {
+                    double all[16];
+                    fetch_results(ctx, 0, 16, all);
+                    fprintf(stderr, "[pb200] queued %d it %d rnorm %.3e tol %.3e | res:", queued, it, rnorm, tol);
+                    for (int q = 0; q < 14; ++q) fprintf(stderr, " %.3e", all[q]);
+                    fprintf(stderr, "\n");
                 }
+                if (rnorm <= tol) { converged = 1; break; }
+                if (!(rnorm == rnorm)) break;
             }
         }
     }
@@ -867,10 +899,12 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     const bool cn = unsteady && in->scheme == PB200_CN;
     int method = o.method;
     const bool nonconstD = s->D1arr != nullptr;
-    if (method == PB200_KRYLOV_AUTO) method = diph ? PB200_KRYLOV_BICGSTAB : PB200_KRYLOV_CG;
     if (o.path == PB200_PATH_FOLDED && !fold_eligible(s))
         return set_err(ctx, PB200_EUNSUPPORTED, "the folded path needs jump / Robin coefficients of one sign (alpha2/alpha1, beta1, beta2 > 0; beta > 0, alpha >= 0)");
     const bool use_fold = o.path != PB200_PATH_GENERIC && fold_eligible(s);
+    // AUTO: the folded system is symmetric positive definite for mono AND diphasic problems, so CG (one operator apply per
+    // iteration) is the cheaper choice there; the reference's rows of the diphasic system are not symmetric => BiCGSTAB.
+    if (method == PB200_KRYLOV_AUTO) method = (use_fold || !diph) ? PB200_KRYLOV_CG : PB200_KRYLOV_BICGSTAB;
     if (method == PB200_KRYLOV_CG && diph && !use_fold)
         return set_err(ctx, PB200_EUNSUPPORTED, "CG on the diphasic system needs the folded (symmetrised) path; use BiCGSTAB");
     (void)nonconstD;
@@ -1040,6 +1074,8 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         stats->launches = ctx->launches - launches0;
         stats->apply_ms = prof_collect(ctx);
         stats->apply_launches = ctx->apply_launches - applies0;
+        stats->apply_cells_uniform = use_fold ? s->F.cells_uniform : 0;
+        stats->apply_cells_general = use_fold ? s->F.cells_general : 0;
     }
     if (!converged) return set_err(ctx, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
     return PB200_OK;
