@@ -135,7 +135,9 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
 }
 
 // result slots of the folded Krylov loops (dense-part and band-part partial sums are adjacent: one allreduce covers both)
-enum { FS_PAIR0 = 0, FS_PAIR1 = 2, FS_SIG_D = 4, FS_SIG_B = 5, FS_TS_D = 6, FS_TT_D = 7, FS_TS_B = 8, FS_TT_B = 9, FS_BB = 10, FS_RR0 = 11, FS_ITERS = 12, FS_TMP = 13 };
+enum { FS_PAIR0 = 0, FS_PAIR1 = 2, FS_SIG_D = 4, FS_SIG_B = 5, FS_TS_D = 6, FS_TT_D = 7, FS_TS_B = 8, FS_TT_B = 9, FS_BB = 10, FS_RR0 = 11, FS_ITERS = 12, FS_RHOB0 = 13, FS_RHOB1 = 14, FS_TMP = 15 };
+// rho of the (rho, rr) pair at slot sl (0 or 2): with the band preconditioner rho = (r, r) + (r_B, z_B - r_B), the second part in FS_RHOB*
+__device__ __forceinline__ double rho_at(const double *res, int sl) { return res[sl] + res[FS_RHOB0 + (sl >> 1)]; }
 
 // device-side stopping test: the Krylov kernels of an iteration turn into no-ops once ||r||^2 (slot `sl_rr`) is below the
 // tolerance, so the host may queue several iterations between two looks at the residual without doing extra work
@@ -583,6 +585,72 @@ __global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, doub
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
 }
 
+// ---- band preconditioner -------------------------------------------------------------------------------------------------------
+// The spectrum of M^ is the bulk interval [1/(1+2N theta dt/h^2 ...)] plus a few low modes localised on neighbouring cut cells (their w
+// unknowns are coupled across faces; tools/krylov_experiment3.py).  They are removed by a low-degree Chebyshev polynomial of the band
+// block M^_BB (all unknowns of the band cells) used as preconditioner on the band only: z = r outside the band, z_B = q(M^_BB) r_B.
+// out[c][bo] = ca x_c + cb (M^_BB x)_c for every OWNED band cell; publishes sum_c x_c out_c  (x read from an FVec)
+template <int N>
+__global__ void kf_band_poly(Grid g, FoldDev fd, FVec x, double *out, double ca, double cb, double *partials, double *results, unsigned *counter,
+                             const double *res, StopCrit stop)
+{
+    if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
+    double v[1] = {0.0};
+    const int nE = fd.nE;
+    const bool two = fd.nbulk > 1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const int bo = fd.EB[e];
+        if (bo < 0) continue;
+        const long long l = fd.Ecell[e];
+        const double x0 = x.f[0][l], x1 = two ? x.f[1][l] : 0.0, xw = x.f[2][bo];
+        const double *__restrict__ blk = fd.Eblk + e;
+        double a0 = x0 + blk[0 * (size_t)nE] * x0 + blk[1 * (size_t)nE] * x1 + blk[2 * (size_t)nE] * xw;
+        double a1 = x1 + blk[3 * (size_t)nE] * x0 + blk[4 * (size_t)nE] * x1 + blk[5 * (size_t)nE] * xw;
+        double a2 = xw + blk[6 * (size_t)nE] * x0 + blk[7 * (size_t)nE] * x1 + blk[8 * (size_t)nE] * xw;
+#pragma unroll
+        for (int k = 0; k < 2 * N; ++k) {
+            const int nb = fd.EnbrB[(size_t)k * nE + e];
+            if (nb < 0) continue;
+            const int d = k >> 1;
+            const long long ln = (k & 1) ? l + g.stride[d] : l - g.stride[d];
+            const double *__restrict__ bk = blk + (size_t)((1 + k) * 9) * nE;
+            const double n0 = x.f[0][ln], n1 = two ? x.f[1][ln] : 0.0, nw = x.f[2][nb];
+            a0 += bk[0 * (size_t)nE] * n0 + bk[1 * (size_t)nE] * n1 + bk[2 * (size_t)nE] * nw;
+            a1 += bk[3 * (size_t)nE] * n0 + bk[4 * (size_t)nE] * n1 + bk[5 * (size_t)nE] * nw;
+            a2 += bk[6 * (size_t)nE] * n0 + bk[7 * (size_t)nE] * n1 + bk[8 * (size_t)nE] * nw;
+        }
+        const double o0 = ca * x0 + cb * a0, o1 = ca * x1 + cb * a1, o2 = ca * xw + cb * a2;
+        out[(size_t)0 * fd.nB + bo] = o0;
+        out[(size_t)1 * fd.nB + bo] = o1;
+        out[(size_t)2 * fd.nB + bo] = o2;
+        v[0] += x0 * o0 + x1 * o1 + xw * o2;
+    }
+    block_reduce_publish<1>(v, partials, results, counter);
+}
+// x_B = scale * in_B (band cells of an FVec), or x_B += in_B when add != 0
+__global__ void kf_band_put(FoldDev fd, FVec x, const double *in, double scale, int add, const double *res, StopCrit stop)
+{
+    if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
+    for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
+        const long long l = fd.Bcell[k];
+        const double v0 = scale * in[(size_t)0 * fd.nB + k], v1 = scale * in[(size_t)1 * fd.nB + k], v2 = scale * in[(size_t)2 * fd.nB + k];
+        if (add) { x.f[0][l] += v0; if (fd.nbulk > 1) x.f[1][l] += v1; x.f[2][k] += v2; }
+        else { x.f[0][l] = v0; if (fd.nbulk > 1) x.f[1][l] = v1; x.f[2][k] = v2; }
+    }
+}
+// deterministic pseudo-random start vector on the band (power iteration)
+__global__ void kf_band_seed(FoldDev fd, double *out)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < fd.nB; k += gridDim.x * blockDim.x) {
+        const long long l = fd.Bcell[k];
+        for (int c = 0; c < 3; ++c) {
+            unsigned long long h = (unsigned long long)(l * 3 + c) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
+            out[(size_t)c * fd.nB + k] = 0.5 + (double)(h >> 11) * (1.0 / 9007199254740992.0);
+        }
+    }
+}
+
 // ---- vector kernels over the item list (dense active chunks + compact w) ------------------------------------------------------
 #define FV_LOOP(I)                                                  \
     for (int it__ = blockIdx.x; it__ < (I).n; it__ += gridDim.x)    \
@@ -612,7 +680,7 @@ __global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl
 {
     if (fold_done(res, stop)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) res[FS_ITERS] += 1.0;
-    const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
+    const double alpha = safe_div(rho_at(res, sl_rho), res[FS_SIG_D] + res[FS_SIG_B]);
     double v[2] = {0.0, 0.0};
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
         const TileRec R = I.rec[it];
@@ -642,7 +710,7 @@ __global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl
 __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec p, StopCrit stop)
 {
     if (fold_done(res, stop)) return;
-    const double beta = safe_div(res[sl_new], res[sl_rho]);
+    const double beta = safe_div(rho_at(res, sl_new), rho_at(res, sl_rho));
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
         const TileRec R = I.rec[it];
         const int f = R.f;
@@ -696,7 +764,10 @@ __global__ void __launch_bounds__(FCH) kf_bicg_p(Items I, const double *res, int
 // iteration skipped by the stopping test: copy the (rho, rr) pair forward
 __global__ void kf_carry_pair(double *res, int sl_old, int sl_new, StopCrit stop)
 {
-    if (threadIdx.x == 0 && fold_done(res, stop)) { res[sl_new] = res[sl_old]; res[sl_new + 1] = res[sl_old + 1]; }
+    if (threadIdx.x == 0 && fold_done(res, stop)) {
+        res[sl_new] = res[sl_old]; res[sl_new + 1] = res[sl_old + 1];
+        res[FS_RHOB0 + (sl_new >> 1)] = res[FS_RHOB0 + (sl_old >> 1)];
+    }
 }
 
 // ---- transforms between the reference's unknowns / rows and the scaled ones ----------------------------------------------------
@@ -776,6 +847,10 @@ struct FoldSys {
     unsigned char *uni = nullptr;
     double *ucoef = nullptr;
     TileRec *rec = nullptr;
+    double *dz = nullptr;          // [3][nB] band preconditioner correction z_B - r_B
+    bool prec = false;             // band preconditioner available
+    double pa0 = 1.0, pa1 = 0.0;   // z_B = pa0 r_B + pa1 M^_BB r_B
+    double band_lmin = 0.0, band_lmax = 0.0;
     long long cells_uniform = 0, cells_general = 0;   // cells of tiles applied with constant / streamed coefficients (this rank)
     Items I;
     FVec x, b, r, p, v, r0, s, t;
@@ -789,7 +864,7 @@ static void fold_free(FoldSys &F)
 {
     for (int p = 0; p < 2; ++p) { dev_free(F.sc[p]); for (int d = 0; d < PB_MAXD; ++d) dev_free(F.off[p][d]); }
     if (F.Bcell) cudaFree(F.Bcell); if (F.Ecell) cudaFree(F.Ecell); if (F.bord) cudaFree(F.bord); if (F.EB) cudaFree(F.EB);
-    if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
+    if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t};

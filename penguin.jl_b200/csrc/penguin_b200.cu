@@ -570,6 +570,72 @@ static int fold_compact(pb200_ctx *ctx, Launch launch, long long **list, int *n)
     return PB200_OK;
 }
 
+
+static inline int band_grid(int n);
+// extreme eigenvalues of the band block M^_BB by power iteration (set-up, O(band) work) -> coefficients of the band preconditioner
+static int fold_band_spectrum(pb200_solver *s)
+{
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    FoldSys &F = s->F;
+    const FoldDev &d = F.d;
+    int rc;
+    const size_t nB = d.nB > 0 ? d.nB : 1;
+    CUDA_TRY(ctx, cudaMalloc((void **)&F.dz, sizeof(double) * 3 * nB));
+    CUDA_TRY(ctx, cudaMemsetAsync(F.dz, 0, sizeof(double) * 3 * nB, ctx->stream));
+    const int gb = band_grid(d.nE), gB = band_grid(d.nB);
+    const StopCrit none = {0.0, 0.0, -1};
+    double *res = ctx->d_results;
+    // the iteration vector lives in F.v (zero outside the band, restored to zero afterwards)
+    auto power = [&](double shift, double sign, int iters, double *lam) -> int {
+        kf_band_seed<<<gB, 128, 0, ctx->stream>>>(d, F.dz); LAUNCH_CHECK(ctx);
+        double nrm2 = 0.0, h[1];
+        // normalise the seed
+        kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 1.0, 0, res, none); LAUNCH_CHECK(ctx);
+        double rq = 0.0;
+        for (int it = 0; it < iters; ++it) {
+            // ||x||^2 via (x, 1 x + 0 A x)
+            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 128, 0, ctx->stream>>>(g, d, F.v, F.dz, 1.0, 0.0, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
+            LAUNCH_CHECK(ctx);
+            if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
+            if ((rc = fetch_results(ctx, SL_TMP, 1, h))) return rc;
+            nrm2 = h[0];
+            if (!(nrm2 > 0.0)) { *lam = 0.0; return PB200_OK; }
+            kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 1.0 / sqrt(nrm2), 0, res, none); LAUNCH_CHECK(ctx);
+            if (ctx->nranks > 1) { double *fl[2] = {F.v.f[0], F.v.f[1]}; if ((rc = halo_exchange(ctx, g, fl, d.nbulk))) return rc; if ((rc = fold_band_halo(ctx, F, s->bh, F.v.f[2], 1))) return rc; }
+            // y = (shift + sign A) x ; Rayleigh quotient (x, y)
+            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 128, 0, ctx->stream>>>(g, d, F.v, F.dz, shift, sign, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
+            LAUNCH_CHECK(ctx);
+            if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
+            if ((rc = fetch_results(ctx, SL_TMP, 1, h))) return rc;
+            rq = h[0];
+            kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 1.0, 0, res, none); LAUNCH_CHECK(ctx);
+        }
+        *lam = rq;
+        return PB200_OK;
+    };
+    double lmax = 0.0, lshift = 0.0;
+    if ((rc = power(0.0, 1.0, 40, &lmax))) return rc;
+    const double hi = 1.05 * lmax;
+    if ((rc = power(hi, -1.0, 60, &lshift))) return rc;
+    double lmin = hi - lshift;
+    // clean the work vector
+    CUDA_TRY(ctx, cudaMemsetAsync(F.dz, 0, sizeof(double) * 3 * nB, ctx->stream));
+    kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 0.0, 0, res, none); LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    F.band_lmin = lmin; F.band_lmax = lmax;
+    if (!(lmax > 0.0) || !(lmin > 0.0) || !(lmin < lmax)) { F.prec = false; return PB200_OK; }
+    const double lo = 0.7 * lmin;
+    // two Chebyshev steps on [lo, hi]: q(t) = a0 + a1 t, positive for t < lo + hi
+    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+    const double rho0 = 1.0 / sigma, rho1 = 1.0 / (2.0 * sigma - rho0);
+    F.pa0 = (1.0 + rho1 * rho0) / theta + 2.0 * rho1 / delta;
+    F.pa1 = -2.0 * rho1 / (delta * theta);
+    F.prec = true;
+    if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] band block spectrum ~ [%.4f, %.4f], prec q(t) = %.4f %+.4f t\n", lmin, lmax, F.pa0, F.pa1);
+    return PB200_OK;
+}
+
 static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 {
     pb200_ctx *ctx = s->ctx;
@@ -712,6 +778,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     F.key[0] = ac.cV; F.key[1] = ac.c; F.key[2] = ac.c2;
     F.built = true;
+    if (d.has_w && d.nE > 0 && !getenv("PB200_NO_BAND_PREC")) { if ((rc = fold_band_spectrum(s))) return rc; }
     return PB200_OK;
 }
 
@@ -796,7 +863,19 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         const bool cg = method == PB200_KRYLOV_CG;
-        if (cg) { kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx); }
+        const bool prec = cg && band && F.prec;
+        const int gE = band_grid(F.d.nE);
+        const StopCrit nostop = {0.0, 0.0, -1};
+        if (cg) {
+            kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
+            if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
+                if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc; if ((rc = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc; }
+                DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_RHOB0, ctx->d_counter, res, nostop)));
+                LAUNCH_CHECK(ctx);
+                if ((rc = allreduce_results(ctx, FS_RHOB0, 1))) return rc;
+                kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx);
+            }
+        }
         else { kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.r0, F.p); LAUNCH_CHECK(ctx); }
         // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
         // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
@@ -809,7 +888,14 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
                 if ((rc = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc;
                 kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
                 if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                if (prec) {   // z = r + (q(M^_BB) - 1) r_B on the band: rho_new = (r, r) + (r_B, dz_B)
+                    if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc; if ((rc = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc; }
+                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_RHOB0 + nxt, ctx->d_counter, res, st)));
+                    LAUNCH_CHECK(ctx);
+                    if ((rc = allreduce_results(ctx, FS_RHOB0 + nxt, 1))) return rc;
+                }
                 kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.p, stn); LAUNCH_CHECK(ctx);
+                if (prec) { kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, stn); LAUNCH_CHECK(ctx); }
             } else {
                 if ((rc = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc;
                 kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
