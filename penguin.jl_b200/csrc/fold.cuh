@@ -44,8 +44,8 @@ struct FoldDev {
     const int *bord;
     double *Linv;    // [5][nB]: i00 i11 i20 i21 i22
     int *EB;         // [nE]
-    int *EnbrB;      // [2N][nE]
-    double *Eblk;    // [(1+2N)*9][nE]
+    int *EnbrB;      // [nE][2N]   (AoS: one warp works on one band cell)
+    double *Eblk;    // [nE][(1+2N)*9]  block 0: self, 1+2d: lower neighbour in d, 2+2d: upper; each 3x3 row-major
 };
 
 struct FVec { double *f[3]; };   // f[0], f[1]: dense bulk fields; f[2]: compact w
@@ -355,8 +355,10 @@ __global__ void kf_blocks(Grid g, FoldDev fd)
 #pragma unroll
             for (int k = 0; k < 9; ++k) R[k] = 0.0;
         }
+        constexpr int NC = (1 + 2 * N) * 9;
+        double *__restrict__ eb = fd.Eblk + (size_t)e * NC;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) fd.Eblk[(size_t)k * fd.nE + e] = R[k];
+        for (int k = 0; k < 9; ++k) eb[k] = R[k];
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             const long long s = g.stride[d];
@@ -382,12 +384,12 @@ __global__ void kf_blocks(Grid g, FoldDev fd)
                     tri_sandwich(Li, O, Lj, RU);
                 }
             }
-            fd.EnbrB[(size_t)(2 * d) * fd.nE + e] = nbL;
-            fd.EnbrB[(size_t)(2 * d + 1) * fd.nE + e] = nbU;
+            fd.EnbrB[(size_t)e * (2 * N) + 2 * d] = nbL;
+            fd.EnbrB[(size_t)e * (2 * N) + 2 * d + 1] = nbU;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                fd.Eblk[(size_t)((1 + 2 * d) * 9 + k) * fd.nE + e] = RL[k];
-                fd.Eblk[(size_t)((2 + 2 * d) * 9 + k) * fd.nE + e] = RU[k];
+                eb[(1 + 2 * d) * 9 + k] = RL[k];
+                eb[(2 + 2 * d) * 9 + k] = RU[k];
             }
         }
     }
@@ -540,45 +542,79 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
 }
 
+// One WARP per band / fringe cell e: lanes 0..3(1+2N)-1 gather the 3 unknowns of the cell and of its 2N neighbours, every lane
+// multiplies its share of the (1+2N) 3x3 coefficient blocks (contiguous in memory: coalesced) and three shuffle reductions give the rows.
+// BAND_ONLY restricts the columns to band cells (the principal submatrix M^_BB) and adds the identity diagonal.
+template <int N, bool BAND_ONLY>
+__device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int e, const FVec &x, int lane, double &a0, double &a1, double &a2, double &x0,
+                                          double &x1, double &xw, long long &l, int &bo)
+{
+    constexpr int NB = 1 + 2 * N, NC = NB * 9, NX = NB * 3;
+    l = fd.Ecell[e];
+    bo = fd.EB[e];
+    double xv = 0.0;
+    if (lane < NX) {
+        const int k = lane / 3, c = lane - 3 * k;
+        long long ln = l;
+        int nb = bo;
+        if (k > 0) {
+            const int kk = k - 1, d = kk >> 1;
+            ln = (kk & 1) ? l + g.stride[d] : l - g.stride[d];
+            nb = fd.EnbrB[(size_t)e * (2 * N) + kk];
+        }
+        const bool use = !(BAND_ONLY && nb < 0);
+        if (use) {
+            if (c == 0) xv = x.f[0][ln];
+            else if (c == 1) { if (fd.nbulk > 1) xv = x.f[1][ln]; }
+            else if (nb >= 0) xv = x.f[2][nb];
+        }
+    }
+    x0 = __shfl_sync(0xffffffffu, xv, 0); x1 = __shfl_sync(0xffffffffu, xv, 1); xw = __shfl_sync(0xffffffffu, xv, 2);
+    const double *__restrict__ blk = fd.Eblk + (size_t)e * NC;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < (NC + 31) / 32; ++jj) {
+        const int j = jj * 32 + lane;
+        const bool in = j < NC;
+        const int jc = in ? j : 0;
+        const int k = jc / 9, rem = jc - 9 * k, r = rem / 3, c = rem - 3 * r;
+        const double xx = __shfl_sync(0xffffffffu, xv, k * 3 + c);
+        const double pr = in ? blk[jc] * xx : 0.0;
+        r0 += r == 0 ? pr : 0.0; r1 += r == 1 ? pr : 0.0; r2 += r == 2 ? pr : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o); r1 += __shfl_xor_sync(0xffffffffu, r1, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    a0 = r0; a1 = r1; a2 = r2;
+    if (BAND_ONLY) { a0 += x0; a1 += x1; a2 += xw; }
+}
+
 // band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here
 template <int N, int MODE>
-__global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter, const double *res,
-                              StopCrit stop)
+__global__ void __launch_bounds__(128) kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
+                                                     const double *res, StopCrit stop)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
-    const int nE = fd.nE;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
-        const long long l = fd.Ecell[e];
-        const int bo = fd.EB[e];
-        const bool two = fd.nbulk > 1;
-        const double x0 = x.f[0][l], x1 = two ? x.f[1][l] : 0.0, xw = bo >= 0 ? x.f[2][bo] : 0.0;
-        const double *__restrict__ blk = fd.Eblk + e;
-        double a0, a1, a2;
-        a0 = blk[0 * (size_t)nE] * x0 + blk[1 * (size_t)nE] * x1 + blk[2 * (size_t)nE] * xw;
-        a1 = blk[3 * (size_t)nE] * x0 + blk[4 * (size_t)nE] * x1 + blk[5 * (size_t)nE] * xw;
-        a2 = blk[6 * (size_t)nE] * x0 + blk[7 * (size_t)nE] * x1 + blk[8 * (size_t)nE] * xw;
-#pragma unroll
-        for (int k = 0; k < 2 * N; ++k) {
-            const int d = k >> 1;
-            const long long ln = (k & 1) ? l + g.stride[d] : l - g.stride[d];
-            const int nb = fd.EnbrB[(size_t)k * nE + e];
-            const double *__restrict__ bk = blk + (size_t)((1 + k) * 9) * nE;
-            const double n0 = x.f[0][ln], n1 = two ? x.f[1][ln] : 0.0, nw = nb >= 0 ? x.f[2][nb] : 0.0;
-            a0 += bk[0 * (size_t)nE] * n0 + bk[1 * (size_t)nE] * n1 + bk[2 * (size_t)nE] * nw;
-            a1 += bk[3 * (size_t)nE] * n0 + bk[4 * (size_t)nE] * n1 + bk[5 * (size_t)nE] * nw;
-            a2 += bk[6 * (size_t)nE] * n0 + bk[7 * (size_t)nE] * n1 + bk[8 * (size_t)nE] * nw;
-        }
-        const double y0p = y.f[0][l], y1p = two ? y.f[1][l] : 0.0;
-        y.f[0][l] = y0p + a0;
-        if (two) y.f[1][l] = y1p + a1;
-        double yw = 0.0;
-        if (bo >= 0) { yw = xw + a2; y.f[2][bo] = yw; }
-        if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
-        if (MODE == 2) v[0] += aux.f[0][l] * a0 + (two ? aux.f[1][l] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
-        if (MODE == 3) {
-            v[0] += x0 * a0 + x1 * a1 + xw * yw;
-            v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const bool two = fd.nbulk > 1;
+    for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < fd.nE; e += gridDim.x * wpb) {
+        double a0, a1, a2, x0, x1, xw;
+        long long l; int bo;
+        band_rows<N, false>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
+        if (lane == 0) {
+            const double y0p = y.f[0][l], y1p = two ? y.f[1][l] : 0.0;
+            y.f[0][l] = y0p + a0;
+            if (two) y.f[1][l] = y1p + a1;
+            double yw = 0.0;
+            if (bo >= 0) { yw = xw + a2; y.f[2][bo] = yw; }
+            if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
+            if (MODE == 2) v[0] += aux.f[0][l] * a0 + (two ? aux.f[1][l] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
+            if (MODE == 3) {
+                v[0] += x0 * a0 + x1 * a1 + xw * yw;
+                v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
+            }
         }
     }
     if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
@@ -591,39 +627,24 @@ __global__ void kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, doub
 // block M^_BB (all unknowns of the band cells) used as preconditioner on the band only: z = r outside the band, z_B = q(M^_BB) r_B.
 // out[c][bo] = ca x_c + cb (M^_BB x)_c for every OWNED band cell; publishes sum_c x_c out_c  (x read from an FVec)
 template <int N>
-__global__ void kf_band_poly(Grid g, FoldDev fd, FVec x, double *out, double ca, double cb, double *partials, double *results, unsigned *counter,
-                             const double *res, StopCrit stop)
+__global__ void __launch_bounds__(128) kf_band_poly(Grid g, FoldDev fd, FVec x, double *out, double ca, double cb, double *partials, double *results,
+                                                    unsigned *counter, const double *res, StopCrit stop)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[1] = {0.0};
-    const int nE = fd.nE;
-    const bool two = fd.nbulk > 1;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
-        const int bo = fd.EB[e];
-        if (bo < 0) continue;
-        const long long l = fd.Ecell[e];
-        const double x0 = x.f[0][l], x1 = two ? x.f[1][l] : 0.0, xw = x.f[2][bo];
-        const double *__restrict__ blk = fd.Eblk + e;
-        double a0 = x0 + blk[0 * (size_t)nE] * x0 + blk[1 * (size_t)nE] * x1 + blk[2 * (size_t)nE] * xw;
-        double a1 = x1 + blk[3 * (size_t)nE] * x0 + blk[4 * (size_t)nE] * x1 + blk[5 * (size_t)nE] * xw;
-        double a2 = xw + blk[6 * (size_t)nE] * x0 + blk[7 * (size_t)nE] * x1 + blk[8 * (size_t)nE] * xw;
-#pragma unroll
-        for (int k = 0; k < 2 * N; ++k) {
-            const int nb = fd.EnbrB[(size_t)k * nE + e];
-            if (nb < 0) continue;
-            const int d = k >> 1;
-            const long long ln = (k & 1) ? l + g.stride[d] : l - g.stride[d];
-            const double *__restrict__ bk = blk + (size_t)((1 + k) * 9) * nE;
-            const double n0 = x.f[0][ln], n1 = two ? x.f[1][ln] : 0.0, nw = x.f[2][nb];
-            a0 += bk[0 * (size_t)nE] * n0 + bk[1 * (size_t)nE] * n1 + bk[2 * (size_t)nE] * nw;
-            a1 += bk[3 * (size_t)nE] * n0 + bk[4 * (size_t)nE] * n1 + bk[5 * (size_t)nE] * nw;
-            a2 += bk[6 * (size_t)nE] * n0 + bk[7 * (size_t)nE] * n1 + bk[8 * (size_t)nE] * nw;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < fd.nE; e += gridDim.x * wpb) {
+        if (fd.EB[e] < 0) continue;   // warp-uniform
+        double a0, a1, a2, x0, x1, xw;
+        long long l; int bo;
+        band_rows<N, true>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
+        if (lane == 0) {
+            const double o0 = ca * x0 + cb * a0, o1 = ca * x1 + cb * a1, o2 = ca * xw + cb * a2;
+            out[(size_t)0 * fd.nB + bo] = o0;
+            out[(size_t)1 * fd.nB + bo] = o1;
+            out[(size_t)2 * fd.nB + bo] = o2;
+            v[0] += x0 * o0 + x1 * o1 + xw * o2;
         }
-        const double o0 = ca * x0 + cb * a0, o1 = ca * x1 + cb * a1, o2 = ca * xw + cb * a2;
-        out[(size_t)0 * fd.nB + bo] = o0;
-        out[(size_t)1 * fd.nB + bo] = o1;
-        out[(size_t)2 * fd.nB + bo] = o2;
-        v[0] += x0 * o0 + x1 * o1 + xw * o2;
     }
     block_reduce_publish<1>(v, partials, results, counter);
 }
@@ -851,6 +872,9 @@ struct FoldSys {
     bool prec = false;             // band preconditioner available
     double pa0 = 1.0, pa1 = 0.0;   // z_B = pa0 r_B + pa1 M^_BB r_B
     double band_lmin = 0.0, band_lmax = 0.0;
+    cudaGraphExec_t graph_exec = nullptr;   // `check_every` Krylov iterations captured as one graph (single GPU)
+    double graph_key[6] = {};
+    int64_t graph_launches = 0, graph_applies = 0;
     long long cells_uniform = 0, cells_general = 0;   // cells of tiles applied with constant / streamed coefficients (this rank)
     Items I;
     FVec x, b, r, p, v, r0, s, t;
@@ -862,6 +886,7 @@ struct FoldSys {
 static void fold_free_vec(FVec &a) { for (int f = 0; f < 3; ++f) { if (a.f[f]) cudaFree(a.f[f]); a.f[f] = nullptr; } }
 static void fold_free(FoldSys &F)
 {
+    if (F.graph_exec) { cudaGraphExecDestroy(F.graph_exec); F.graph_exec = nullptr; }
     for (int p = 0; p < 2; ++p) { dev_free(F.sc[p]); for (int d = 0; d < PB_MAXD; ++d) dev_free(F.off[p][d]); }
     if (F.Bcell) cudaFree(F.Bcell); if (F.Ecell) cudaFree(F.Ecell); if (F.bord) cudaFree(F.bord); if (F.EB) cudaFree(F.EB);
     if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;

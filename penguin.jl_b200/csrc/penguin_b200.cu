@@ -572,6 +572,7 @@ static int fold_compact(pb200_ctx *ctx, Launch launch, long long **list, int *n)
 
 
 static inline int band_grid(int n);
+static inline int band_wgrid(int n);
 // extreme eigenvalues of the band block M^_BB by power iteration (set-up, O(band) work) -> coefficients of the band preconditioner
 static int fold_band_spectrum(pb200_solver *s)
 {
@@ -583,7 +584,7 @@ static int fold_band_spectrum(pb200_solver *s)
     const size_t nB = d.nB > 0 ? d.nB : 1;
     CUDA_TRY(ctx, cudaMalloc((void **)&F.dz, sizeof(double) * 3 * nB));
     CUDA_TRY(ctx, cudaMemsetAsync(F.dz, 0, sizeof(double) * 3 * nB, ctx->stream));
-    const int gb = band_grid(d.nE), gB = band_grid(d.nB);
+    const int gb = band_wgrid(d.nE), gB = band_grid(d.nB);
     const StopCrit none = {0.0, 0.0, -1};
     double *res = ctx->d_results;
     // the iteration vector lives in F.v (zero outside the band, restored to zero afterwards)
@@ -784,6 +785,8 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 
 static inline int fold_grid(pb200_solver *s) { int b = s->F.nitems; int cap = s->ctx->sm_count * 8; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
 static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
+// kernels that put one warp on one band cell (4 warps per block)
+static inline int band_wgrid(int n) { int b = (n + 3) / 4; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
 
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
 static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode, StopCrit stop = StopCrit{0.0, 0.0, -1})
@@ -808,7 +811,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     LAUNCH_CHECK(ctx);
     prof_mark(ctx);
     if (F.d.has_w && F.d.nE > 0) {
-        const int gb = band_grid(F.d.nE);
+        const int gb = band_wgrid(F.d.nE);
 #define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 128, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
         if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else FOLD_BAND(3);
 #undef FOLD_BAND
@@ -864,7 +867,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         const bool cg = method == PB200_KRYLOV_CG;
         const bool prec = cg && band && F.prec;
-        const int gE = band_grid(F.d.nE);
+        const int gE = band_wgrid(F.d.nE);
         const StopCrit nostop = {0.0, 0.0, -1};
         if (cg) {
             kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
@@ -879,48 +882,81 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         else { kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.r0, F.p); LAUNCH_CHECK(ctx); }
         // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
         // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
-        int queued = 0;
-        while (queued < o.maxit) {
-            const int nxt = cur ^ 1;
-            StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, 2 * cur + 1};
+        auto enqueue = [&](int curp) -> int {   // one Krylov iteration reading pair `curp`, publishing pair curp ^ 1
+            const int nxt = curp ^ 1;
+            StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, 2 * curp + 1};
             StopCrit stn = {o.rtol * o.rtol, o.atol * o.atol, 2 * nxt + 1};
+            int rc2;
             if (cg) {
-                if ((rc = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc;
-                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
-                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
+                if ((rc2 = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc2;
+                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                if ((rc2 = allreduce_results(ctx, 2 * nxt, 2))) return rc2;
                 if (prec) {   // z = r + (q(M^_BB) - 1) r_B on the band: rho_new = (r, r) + (r_B, dz_B)
-                    if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc; if ((rc = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc; }
+                    if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc2 = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc2; if ((rc2 = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc2; }
                     DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_RHOB0 + nxt, ctx->d_counter, res, st)));
                     LAUNCH_CHECK(ctx);
-                    if ((rc = allreduce_results(ctx, FS_RHOB0 + nxt, 1))) return rc;
+                    if ((rc2 = allreduce_results(ctx, FS_RHOB0 + nxt, 1))) return rc2;
                 }
-                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.p, stn); LAUNCH_CHECK(ctx);
+                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.p, stn); LAUNCH_CHECK(ctx);
                 if (prec) { kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, stn); LAUNCH_CHECK(ctx); }
             } else {
-                if ((rc = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc;
-                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
-                if ((rc = fold_apply(s, F.s, F.t, F.t, 3, st))) return rc;
-                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
-                if ((rc = allreduce_results(ctx, 2 * nxt, 2))) return rc;
-                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * cur, 2 * nxt, F.r, F.v, F.p, stn); LAUNCH_CHECK(ctx);
+                if ((rc2 = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc2;
+                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
+                if ((rc2 = fold_apply(s, F.s, F.t, F.t, 3, st))) return rc2;
+                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                if ((rc2 = allreduce_results(ctx, 2 * nxt, 2))) return rc2;
+                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.v, F.p, stn); LAUNCH_CHECK(ctx);
             }
             // a skipped iteration publishes nothing: carry the converged pair over so that the next iteration sees it too
-            kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, 2 * cur, 2 * nxt, st); LAUNCH_CHECK(ctx);
-            cur = nxt;
-            ++queued;
-            if (queued % o.check_every == 0 || queued == o.maxit) {
+            kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, 2 * curp, 2 * nxt, st); LAUNCH_CHECK(ctx);
+            return PB200_OK;
+        };
+        // Single GPU, no per-launch profiling: the `check_every` iterations between two host looks are replayed as ONE CUDA graph
+        // (captured once per solver and parameter set), which removes the per-launch CPU cost and most of the inter-kernel gaps.
+        int chunk = o.check_every;
+        const bool use_graph = ctx->nranks == 1 && !ctx->profile && !getenv("PB200_NO_GRAPH") && o.maxit >= 2;
+        if (use_graph) {
+            if (chunk & 1) ++chunk;
+            if (chunk > o.maxit) chunk = o.maxit & ~1;
+            if (chunk < 2) chunk = 2;
+            const double gkey[6] = {(double)method, (double)chunk, o.rtol, o.atol, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
+            if (!F.graph_exec || memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
+                if (F.graph_exec) { cudaGraphExecDestroy(F.graph_exec); F.graph_exec = nullptr; }
+                cudaGraph_t gr = nullptr;
+                const int64_t l0 = ctx->launches, a0 = ctx->apply_launches;
+                CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                int rcc = PB200_OK;
+                for (int q = 0; q < chunk && !rcc; ++q) rcc = enqueue(q & 1);   // starts and ends on pair 0
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &gr);
+                if (rcc) { if (gr) cudaGraphDestroy(gr); return rcc; }
+                CUDA_TRY(ctx, ce);
+                CUDA_TRY(ctx, cudaGraphInstantiate(&F.graph_exec, gr, 0));
+                cudaGraphDestroy(gr);
+                F.graph_launches = ctx->launches - l0; F.graph_applies = ctx->apply_launches - a0;
+                ctx->launches = l0; ctx->apply_launches = a0;   // capturing launches nothing
+                memcpy(F.graph_key, gkey, sizeof(gkey));
+            }
+        }
+        // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
+        // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
+        int queued = 0;
+        while (queued < o.maxit) {
+            if (use_graph) {
+                CUDA_TRY(ctx, cudaGraphLaunch(F.graph_exec, ctx->stream));
+                ctx->launches += F.graph_launches; ctx->apply_launches += F.graph_applies;
+                queued += chunk;   // cur stays 0
+            } else {
+                if ((rc = enqueue(cur))) return rc;
+                cur ^= 1;
+                ++queued;
+            }
+            if (use_graph || queued % o.check_every == 0 || queued >= o.maxit) {
                 double hh[2];
                 if ((rc = fetch_results(ctx, 2 * cur + 1, 1, hh))) return rc;
                 if ((rc = fetch_results(ctx, FS_ITERS, 1, hh + 1))) return rc;
                 rnorm = sqrt(hh[0]);
                 it = (int)(hh[1] + 0.5);
-                if (getenv("PB200_DEBUG")) {
-                    double all[16];
-                    fetch_results(ctx, 0, 16, all);
-                    fprintf(stderr, "[pb200] queued %d it %d rnorm %.3e tol %.3e | res:", queued, it, rnorm, tol);
-                    for (int q = 0; q < 14; ++q) fprintf(stderr, " %.3e", all[q]);
-                    fprintf(stderr, "\n");
-                }
+                if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] queued %d it %d rnorm %.3e tol %.3e\n", queued, it, rnorm, tol);
                 if (rnorm <= tol) { converged = 1; break; }
                 if (!(rnorm == rnorm)) break;
             }
