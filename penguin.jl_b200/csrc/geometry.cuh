@@ -416,10 +416,11 @@ __device__ void interface_lowdim(const ShapeDev &s, const double *lo, const doub
 // local cell ordinal over ALL local planes (ghost planes inside the global domain included): t in [0, nloc)
 __device__ __forceinline__ bool local_coords(const Grid &g, int64_t l, int c[PB_MAXD])
 {
+    // local extents: the slab dimension (the slowest one) has lz planes including the two ghosts, so it must NOT be reduced modulo pd
     int64_t q = l;
-    c[0] = (int)(q % g.pd[0]); q /= g.pd[0];
-    c[1] = (int)(q % g.pd[1]); q /= g.pd[1];
-    c[2] = (int)q;
+    if (g.sd == 0) { c[0] = (int)q; c[1] = 0; c[2] = 0; }
+    else if (g.sd == 1) { c[0] = (int)(q % g.pd[0]); c[1] = (int)(q / g.pd[0]); c[2] = 0; }
+    else { c[0] = (int)(q % g.pd[0]); q /= g.pd[0]; c[1] = (int)(q % g.pd[1]); c[2] = (int)(q / g.pd[1]); }
     c[g.sd] += g.k0 - 1;
     return c[g.sd] >= 0 && c[g.sd] < g.pd[g.sd];
 }
