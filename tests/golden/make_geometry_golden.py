@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generates tests/golden/geometry_golden.json: capacities of two tiny meshes evaluated INDEPENDENTLY of oracle/ and of the
-CUDA kernels, with mpmath (30 significant digits) tanh-sinh quadrature of nested chord integrals, every integral split at
-its kinks.  Run:  python tests/golden/make_geometry_golden.py   (about a minute).
+CUDA kernels, with nested chord integrals split at every kink: mpmath (30 digits, tanh-sinh) for the 1-D / 2-D cases, SciPy QUADPACK in
+double precision for the 3-D cases.  Run:  python tests/golden/make_geometry_golden.py   (about 20 minutes on one core).
 
 Meaning of each array: SURVEY.md section 8a row a3 (/root/reference/src/capacity.jl:81-123 and, for the definitions,
 src/front_tracking.jl:814-1427): V fluid volume of cell [nodes_i, nodes_i+1]^N, C_omega its barycentre (cell centre when the
@@ -13,9 +13,36 @@ import itertools
 import json
 import os
 
-from mpmath import mp, mpf, quad, sqrt, acos, asin, pi, cos, sin
+import math
 
-mp.dps = 30
+import mpmath
+from scipy.integrate import quad as sp_quad
+
+mpmath.mp.dps = 30
+# Two arithmetic back-ends behind the same code.  "mp": 30-digit mpmath, tanh-sinh quadrature -- used for the 1-D and 2-D cases.
+# "float": IEEE double with SciPy's QUADPACK (adaptive Gauss-Kronrod 21, split at the same kinks, epsabs 1e-16) -- used for the 3-D
+# cases, where three nested 30-digit quadratures take hours; its accuracy (~1e-13 of a cell) is what bounds the 3-D tolerances.
+mpf, sqrt, acos, asin, cos, sin, pi = mpmath.mpf, mpmath.sqrt, mpmath.acos, mpmath.asin, mpmath.cos, mpmath.sin, mpmath.pi
+BACKEND = ["mp"]
+
+
+def set_backend(name):
+    global mpf, sqrt, acos, asin, cos, sin, pi
+    BACKEND[0] = name
+    if name == "mp":
+        mpf, sqrt, acos, asin, cos, sin, pi = mpmath.mpf, mpmath.sqrt, mpmath.acos, mpmath.asin, mpmath.cos, mpmath.sin, mpmath.pi
+    else:
+        mpf, sqrt, acos, asin, cos, sin, pi = float, math.sqrt, math.acos, math.asin, math.cos, math.sin, math.pi
+
+
+def quad(f, pts):
+    if BACKEND[0] == "mp":
+        return mpmath.quad(f, pts)
+    tot = 0.0
+    for a, b in zip(pts[:-1], pts[1:]):
+        if b - a > 1e-15 * (abs(a) + abs(b) + 1e-300):
+            tot += sp_quad(f, a, b, epsabs=1e-16, epsrel=1e-14, limit=400)[0]
+    return tot
 
 
 def chord(c, r2, lo, hi, mid):
@@ -150,6 +177,7 @@ def sphere_box(c, R, lo, hi):
 
 def capacity(nc, L, x0, center, R, inside):
     N = len(nc)
+    set_backend("float" if N == 3 else "mp")
     h = [mpf(L[d]) / nc[d] for d in range(N)]
     nodes = [[mpf(x0[d]) + (mpf(j) + mpf(1) / 2) * h[d] for j in range(nc[d] + 2)] for d in range(N)]
     pd = [v + 1 for v in nc]
@@ -234,11 +262,11 @@ if __name__ == "__main__":
     cases = {
         "circle_5x4_inside": capacity((5, 4), (4.0, 3.0), (0.0, 0.0), (1.9, 1.45), 1.05, True),
         "circle_5x4_outside": capacity((5, 4), (4.0, 3.0), (0.0, 0.0), (1.9, 1.45), 1.05, False),
-        "interval_6_inside": capacity((6,), (4.0,), (0.0,), (2.03,), 0.97, True),
+        "interval_6_inside": capacity((6,), (4.0,), (0.0,), (2.03,), 0.95, True),   # end points off the grid nodes
         "sphere_3x3x3_inside": capacity((3, 3, 3), (4.0, 4.0, 4.0), (0.0, 0.0, 0.0), (1.9, 2.1, 2.05), 1.2, True),
         "sphere_3x3x3_outside": capacity((3, 3, 3), (4.0, 4.0, 4.0), (0.0, 0.0, 0.0), (1.9, 2.1, 2.05), 1.2, False),
     }
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "geometry_golden.json")
     with open(out, "w") as fh:
-        json.dump(dict(generator="tests/golden/make_geometry_golden.py (mpmath, dps=30)", cases=cases), fh)
+        json.dump(dict(generator="tests/golden/make_geometry_golden.py (1-D/2-D: mpmath dps=30; 3-D: nested QUADPACK in double precision)", cases=cases), fh)
     print("wrote", out)
