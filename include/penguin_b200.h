@@ -135,6 +135,11 @@ int pb200_solver_set_border(pb200_solver *s, int side, int kind, double value, c
 /* state vector [T_omega; T_gamma] (2 nloc) or [T_omega1; T_gamma1; T_omega2; T_gamma2] (4 nloc) */
 int pb200_solver_set_state(pb200_solver *s, const double *x);
 int pb200_solver_get_state(pb200_solver *s, double *x);
+/* Streaming variant for time loops that keep every state on the host (solver.states, src/solver/diffusion.jl:296,450): the copy of the
+ * CURRENT state into `x` (pinned memory recommended) is queued on a separate copy stream and overlaps the next pb200_solver_step, whose
+ * write-back of the new state waits for the copy to finish.  `x` holds the state after pb200_solver_wait_state (or the next _async call). */
+int pb200_solver_get_state_async(pb200_solver *s, double *x);
+int pb200_solver_wait_state(pb200_solver *s);
 
 #define PB200_BE 0
 #define PB200_CN 1

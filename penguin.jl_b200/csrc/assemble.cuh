@@ -46,9 +46,9 @@ __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const 
         const bool wb = mb & MB_FREE, wi = bi && (mb & MB_IFREE);
         if (!wb && !wi) { bb[l] = 0.0; if (bi) bi[l] = 0.0; continue; }
         const double D = D_at(p, l), V = p.V[l], Gm = p.Gam[l];
-        double Rbk, Rik, Rbe = 0.0, Rie = 0.0;
+        double Rbk = 0.0, Rik = 0.0, Rbe = 0.0, Rie = 0.0;
         GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
-        phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
+        if (wi || (mb & MB_KNBR)) phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);   // zero for every other row: nothing known is within reach
         if (sc.cn) {
             GamSpec ge = {Tg, 1.0, nullptr, 0.0, 0.0};
             phase_rows<N>(p, g, l, c, Tw, ge, Rbe, Rie);
@@ -90,8 +90,9 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
         GamSpec gk1 = {gj.arr, 1.0 / sp.a1, nullptr, 0.0, gj.arr ? 0.0 : gj.cst / sp.a1};
         GamSpec gk2 = {nullptr, 0.0, nullptr, 0.0, 0.0};
         double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0, Rbe1 = 0, Rie1 = 0, Rbe2 = 0, Rie2 = 0;
-        if (w1 || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
-        if (w2 || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
+        // the known part is zero unless something known is within the row's reach (MB_KNBR) -- or the row is an interface row
+        if ((w1 && (a & MB_KNBR)) || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
+        if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
         if (sc.cn) {
             GamSpec ge1 = {Tg1, 1.0, nullptr, 0.0, 0.0}, ge2 = {Tg2, 1.0, nullptr, 0.0, 0.0};
             if (w1) phase_rows<N>(p1, g, l, c, Tw1, ge1, Rbe1, Rie1);

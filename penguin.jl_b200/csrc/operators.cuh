@@ -98,6 +98,8 @@ __device__ __forceinline__ void phase_diag(const PhaseDev &ph, const Grid &g, in
 #define MB_FIXED 2  // bulk unknown pinned by a border Dirichlet row
 #define MB_IFREE 4  // interface unknown solved for (mono Robin/Neumann: T_gamma ; diph: T_gamma2)
 #define MB_IKNOWN 8 // mono Dirichlet interface: T_gamma = g kept by the reference's trimming (Gamma != 0)
+#define MB_KNBR 16  // the bulk row of this cell couples to an eliminated value (a known T_gamma through H, or a border-Dirichlet neighbour):
+                    // only these rows need the "known part" of the right-hand side (assemble.cuh)
 
 struct BorderDev {
     int kind[6];
@@ -139,6 +141,34 @@ struct SysParams {
     double a1, a2, b1, b2;         // diph
 };
 
+// true if the bulk row of cell l (phase ph) has a non-zero coefficient on any T_gamma (H columns) or on a border-Dirichlet neighbour
+template <int N>
+__device__ __forceinline__ bool row_couples_to_known(const PhaseDev &ph, const Grid &g, int64_t l, const int c[PB_MAXD], const BorderDev &bd)
+{
+    bool k = false;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int64_t s = g.stride[d];
+        const int id = c[d], last = g.pd[d] - 1;
+        const double al = ph.A[d][l], bl = ph.B[d][l];
+        k = k || (al != bl);
+        if (id > 0) k = k || (al != ph.B[d][l - s]);
+        if (id < last) { const double au = ph.A[d][l + s]; k = k || (au != bl) || (au != ph.B[d][l + s]); }
+        // border-Dirichlet neighbours
+        for (int sg = -1; sg <= 1; sg += 2) {
+            int cn[PB_MAXD] = {c[0], c[1], c[2]};
+            cn[d] += sg;
+            if (cn[d] < 0 || cn[d] >= g.nc[d]) continue;
+            bool real = true;
+            for (int e = 0; e < N; ++e) real = real && (cn[e] < g.nc[e]);
+            if (!real) continue;
+            const int key = border_key(g, cn);
+            k = k || (key >= 0 && bd.kind[key] == PB200_BC_DIRICHLET);
+        }
+    }
+    return k;
+}
+
 // masks + pinned border values.  mono: phase 0 only.  (BC_border_mono!/diph!, remove_zero_rows_cols!)
 template <int N>
 __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__restrict__ ct1, const double *__restrict__ ct2, SysParams sp,
@@ -166,6 +196,7 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
             else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
             bool keptI = (sp.beta != 0.0 && hrow1) || (sp.alpha != 0.0 && p1.Gam[l] != 0.0);
             if (keptI) b1 |= (sp.beta != 0.0 ? MB_IFREE : MB_IKNOWN);
+            if ((b1 & MB_FREE) && row_couples_to_known<N>(p1, g, l, c, bd)) b1 |= MB_KNBR;
             m1[l] = b1;
         } else {
             bool rowG2;
@@ -176,6 +207,8 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
             if (d2) { b2 |= MB_FIXED; ufix2[l] = bval; } else { if (kept2) b2 |= MB_FREE; ufix2[l] = 0.0; }
             bool keptI = (sp.b1 != 0.0 && hrow1) || (sp.b2 != 0.0 && hrow2);
             if (keptI) b2 |= MB_IFREE;   // T_gamma2 is the interface unknown; T_gamma1 = (g + a2 T_gamma2) / a1 everywhere
+            if ((b1 & MB_FREE) && row_couples_to_known<N>(p1, g, l, c, bd)) b1 |= MB_KNBR;
+            if ((b2 & MB_FREE) && row_couples_to_known<N>(p2, g, l, c, bd)) b2 |= MB_KNBR;
             m1[l] = b1; m2[l] = b2;
         }
     }

@@ -354,6 +354,9 @@ struct pb200_solver {
     std::vector<double *> owned;
     FoldSys F;
     BandHalo bh;
+    cudaStream_t copy_stream = nullptr;      // pb200_solver_get_state_async
+    cudaEvent_t state_ready = nullptr, copy_done = nullptr;
+    bool copy_pending = false;
 };
 
 static int solver_vec(pb200_solver *s, MVec *v)
@@ -423,6 +426,7 @@ extern "C" int pb200_solver_destroy(pb200_solver *s)
     cudaStreamSynchronize(s->ctx->stream);
     for (double *p : s->owned) cudaFree(p);
     fold_free(s->F);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->state_ready); cudaEventDestroy(s->copy_done); }
     dev_free(s->D1arr); dev_free(s->D2arr); dev_free(s->ufix1); dev_free(s->ufix2); dev_free(s->gK);
     for (int k = 0; k < 6; ++k) dev_free(s->bvals[k]);
     for (int a = 0; a < 2; ++a) { dev_free(s->Tw[a]); dev_free(s->Tg[a]); dev_free(s->gS[a]); for (int b = 0; b < 2; ++b) dev_free(s->fS[a][b]); }
@@ -491,6 +495,35 @@ extern "C" int pb200_solver_get_state(pb200_solver *s, double *x)
         if ((rc = download_owned(ctx, g, x + (int64_t)(2 * ph + 1) * g.nown, s->Tg[ph]))) return rc;
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+
+extern "C" int pb200_solver_get_state_async(pb200_solver *s, double *x)
+{
+    if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!s->copy_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&s->state_ready, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(s->state_ready, ctx->stream));          // the state of the last step is complete here
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s->copy_stream, s->state_ready, 0));
+    const int np = s->sp.phase_type == PB200_DIPH ? 2 : 1;
+    for (int ph = 0; ph < np; ++ph) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(x + (int64_t)(2 * ph) * g.nown, s->Tw[ph] + g.plane, sizeof(double) * (size_t)g.nown, cudaMemcpyDeviceToHost, s->copy_stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(x + (int64_t)(2 * ph + 1) * g.nown, s->Tg[ph] + g.plane, sizeof(double) * (size_t)g.nown, cudaMemcpyDeviceToHost, s->copy_stream));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(s->copy_done, s->copy_stream));
+    s->copy_pending = true;
+    return PB200_OK;
+}
+extern "C" int pb200_solver_wait_state(pb200_solver *s)
+{
+    if (!s) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (s->copy_pending) { CUDA_TRY(s->ctx, cudaEventSynchronize(s->copy_done)); s->copy_pending = false; }
     return PB200_OK;
 }
 
@@ -1176,6 +1209,7 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     }
     }   // generic path
     // ---- write the new state ----------------------------------------------------------------------------------------------
+    if (s->copy_pending) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, s->copy_done, 0));   // pb200_solver_get_state_async still reads the old one
     k_store_bulk<<<grid, RED_THREADS, 0, ctx->stream>>>(g, z.f[0], s->ufix1, s->Tw[0]); LAUNCH_CHECK(ctx);
     if (!diph) {
         const double *src = s->nf == 2 ? z.f[1] : s->gK;

@@ -251,3 +251,26 @@ def test_diph_cg_on_folded_system(pb):
         pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, Tend, pb.BorderConditions(), icg, "CN", method=method, reltol=1e-13, path="folded")
         for a, b in zip(sg.states, so.states):
             assert rel_l2(a, b) < TOL
+
+
+def test_async_state_download(pb):
+    # pb200_solver_get_state_async / wait_state deliver the same state as the blocking call, also when the next step overlaps the copy
+    import ctypes as C
+    from penguin_b200 import _lib as L
+    nx = 24
+    mo, mg = _meshes(pb, (nx, nx), (4.0, 4.0))
+    f = lambda x, y, z, t: 1.0 + 0 * x
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((2.03, 1.98), 1.0), f, 1.0)
+    n = mo.n
+    dt = 0.25 * (4.0 / nx) ** 2
+    sg = pb.DiffusionUnsteadyMono(phg, pb.BorderConditions(), pb.Dirichlet(0.5), dt, np.zeros(2 * n), "BE")
+    pb.solve_DiffusionUnsteadyMono_(sg, phg, dt, 1.5 * dt, pb.BorderConditions(), pb.Dirichlet(0.5), "BE", reltol=1e-12)
+    ref = sg.states[-1].copy()
+    buf = np.full(2 * n, np.nan)
+    lib = L.lib()
+    L.check(lib.pb200_solver_get_state_async(sg._h, buf.ctypes.data_as(L.dp)), sg._ctx.h)
+    # queue another step right away: its write-back must wait for the copy
+    pb.api._step(sg, "BE", dt, 3 * dt, pb.Dirichlet(0.5), None, pb.api._krylov_opts("cg", dict(reltol=1e-12)))
+    L.check(lib.pb200_solver_wait_state(sg._h), sg._ctx.h)
+    assert np.array_equal(buf, ref)
+    assert not np.array_equal(sg.x, ref)
