@@ -234,13 +234,14 @@ def run_gpu(args):
 
     # ---- roofline pass: the same K steps again with every operator-apply launch bracketed by CUDA events on the launching stream
     # (pb200_set_profiling).  Kept out of the headline region because per-launch events force plain launches instead of graph replay.
-    apply_ms, apply_n = 0.0, 0
+    kms, kn = [0.0, 0.0, 0.0], [0, 0, 0]
     if not args.no_profile:
         lib.pb200_set_profiling(ctx.h, 1)
         for _ in range(args.steps):
             step()
-            apply_ms += st.apply_ms
-            apply_n += st.apply_launches
+            for q in range(3):
+                kms[q] += st.kernel_ms[q]
+                kn[q] += st.kernel_launches[q]
         lib.pb200_set_profiling(ctx.h, 0)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -276,23 +277,37 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel (the operator apply inside the Krylov loop) ---------------------------------------------
     peak, peak_src = peaks()
     roof = None
-    if apply_n and apply_ms > 0:
-        # algorithmic bytes of one apply launch on this rank: x and y for every cell of an active tile, plus the N
-        # coefficient arrays for the cells of tiles whose coefficients are not constants (interface band, domain border ring)
+    if kn[0] and kms[0] > 0:
+        # Algorithmic bytes per launch on this rank, from the tile census of the folded system:
+        #   apply   : x and y for every cell of an active tile + the N coefficient arrays for the cells of tiles whose coefficients are
+        #             not constants (interface band, domain border ring)
+        #   update  : x += a p, r -= a v with fused dots: read p, v, x, r, write x, r  -> 6 passes
+        #   p-update: p = r + b p: read r, p, write p -> 3 passes
         cu, cg = int(st.apply_cells_uniform), int(st.apply_cells_general)
-        launch_bytes = 8 * (2 * (cu + cg) + mesh.N * cg)
-        bytes_per_dof = launch_bytes / (dof / world)
-        achieved = launch_bytes / (apply_ms / apply_n * 1e-3) / 1e9
+        cells = cu + cg
+        names = ["operator apply, dense part (kf_apply_dense)", "x, r update + fused dots (kf_cg_update / kf_bicg_xr)", "search direction update (kf_cg_p)"]
+        abytes = [8 * (2 * cells + mesh.N * cg), 8 * 6 * cells, 8 * 3 * cells]
+        table = []
+        for q in range(3):
+            if kn[q] and kms[q] > 0:
+                us = 1e3 * kms[q] / kn[q]
+                table.append({"kernel": names[q], "launches_timed": int(kn[q]), "avg_launch_us": us, "algorithmic_bytes_per_launch": abytes[q],
+                              "achieved_gbs": abytes[q] / (us * 1e-6) / 1e9, "frac": abytes[q] / (us * 1e-6) / 1e9 / peak,
+                              "share_of_timed_kernels": kms[q] / sum(kms)})
+        dom = max(range(3), key=lambda q: kms[q])
+        us = 1e3 * kms[dom] / kn[dom]
+        achieved = abytes[dom] / (us * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            if tj.get("nx") == nx:
-                traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("nx") == nx and tj.get("n_gpus", 1) == world:
+                traffic = tj.get("dram_bytes_per_launch", {}).get(["apply", "update", "pupdate"][dom])
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "operator apply, dense part (kf_apply_dense)", "algorithmic_bytes_per_dof": bytes_per_dof, "algorithmic_bytes_per_launch": launch_bytes,
-                "cells_constant_coef_tiles": cu, "cells_streamed_coef_tiles": cg, "launches_timed": int(apply_n),
-                "avg_launch_us": 1e3 * apply_ms / apply_n, "peak_source": peak_src}
+                "kernel": names[dom], "algorithmic_bytes_per_dof": abytes[dom] / (dof / world), "algorithmic_bytes_per_launch": abytes[dom],
+                "cells_constant_coef_tiles": cu, "cells_streamed_coef_tiles": cg, "launches_timed": int(kn[dom]),
+                "avg_launch_us": us, "peak_source": peak_src, "timed": "CUDA events around every launch, separate pass of the same K steps",
+                "kernels": table}
 
     if rank == 0:
         cpu = None

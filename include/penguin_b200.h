@@ -188,6 +188,10 @@ typedef struct {
     /* folded path, this rank: cells of the tiles the apply kernel processes with per-tile constant coefficients (no coefficient
      * arrays read) and with streamed coefficient arrays -- the census behind bench.py's algorithmic-byte count */
     int64_t apply_cells_uniform, apply_cells_general;
+    /* profiling enabled: summed device time / launch count per hot kernel -- [0] operator apply (dense part), [1] x,r update with
+     * fused dots, [2] search-direction update */
+    double kernel_ms[3];
+    int64_t kernel_launches[3];
 } pb200_step_stats;
 
 /* one solve: builds b from the device-resident state (b_*_unstead_diff / b_*_stead_diff), applies the border

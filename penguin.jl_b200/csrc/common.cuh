@@ -38,32 +38,38 @@ struct pb200_ctx {
     // optional per-launch timing of the operator apply (pb200_set_profiling)
     bool profile = false;
     std::vector<cudaEvent_t> pev;   // event pairs
+    std::vector<int> ptag;
     size_t pev_used = 0;
     int64_t apply_launches = 0;
 };
 
-// event bracket around one launch (no-op unless profiling): PROF_BEGIN(ctx); kernel<<<>>>; PROF_END(ctx);
-static inline void prof_mark(pb200_ctx *ctx)
+// event bracket around one launch (no-op unless profiling): prof_mark(ctx, tag); kernel<<<>>>; prof_mark(ctx, tag);
+#define PB_PROF_APPLY 0    // operator apply, dense part
+#define PB_PROF_UPDATE 1   // x, r update + dots (CG) / x, r update (BiCGSTAB)
+#define PB_PROF_PUPD 2     // search-direction update
+#define PB_PROF_NTAG 3
+static inline void prof_mark(pb200_ctx *ctx, int tag)
 {
     if (!ctx->profile) return;
     if (ctx->pev_used == ctx->pev.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
         ctx->pev.push_back(e);
+        ctx->ptag.push_back(0);
     }
+    ctx->ptag[ctx->pev_used] = tag;
     cudaEventRecord(ctx->pev[ctx->pev_used++], ctx->stream);
 }
-// summed elapsed time of the recorded pairs (stream must be synchronised); resets the pool
-static inline double prof_collect(pb200_ctx *ctx)
+// summed elapsed time of the recorded pairs per tag (stream must be synchronised); resets the pool
+static inline void prof_collect(pb200_ctx *ctx, double ms[PB_PROF_NTAG], int64_t n[PB_PROF_NTAG])
 {
-    double ms = 0.0;
+    for (int t = 0; t < PB_PROF_NTAG; ++t) { ms[t] = 0.0; n[t] = 0; }
     for (size_t i = 0; i + 1 < ctx->pev_used; i += 2) {
         float t = 0.f;
         cudaEventElapsedTime(&t, ctx->pev[i], ctx->pev[i + 1]);
-        ms += t;
+        ms[ctx->ptag[i]] += t; n[ctx->ptag[i]]++;
     }
     ctx->pev_used = 0;
-    return ms;
 }
 
 static int set_err(pb200_ctx *ctx, int code, const std::string &msg)

@@ -18,6 +18,8 @@
 // phases of a diphasic problem are complementary, so streaming both dense would double the traffic); w lives in a compact
 // array over the band cells, sorted by cell index (ghost-plane entries form a prefix / suffix, so its halo is two contiguous ranges).
 #pragma once
+#include <map>
+
 #include <thrust/execution_policy.h>
 #include <thrust/sort.h>
 
@@ -63,19 +65,20 @@ struct __align__(16) TileRec {
     signed char f;         // field: 0, 1 bulk, 2 w
     signed char ylo, yhi;  // valid range of the tile-relative y coordinate
     signed char zlo, zhi;  // valid range of the tile-relative z coordinate
-    signed char pad;
+    signed char full;      // 1: every cell of the tile is valid (interior tile)
 };
 struct Items {
     const int *it; int n;
     const TileRec *rec;            // [n]
     int shx;                       // log2 of the thread extent in x: 8 (1-D, w items use this layout too) or 5
-    int kx, ky, kz;                // tile-relative coordinate advance per k: (256,0,0) 1-D, (0,8,0) 2-D, (0,0,1) 3-D
+    int kx, ky, kz;                // tile-relative coordinate advance per k: (256,0,0) 1-D, (0,1,0) 2-D, (0,0,1) 3-D
+    int tym;                       // thread row ty covers tile rows ty * tym + ky * k  (2-D: FU consecutive rows per thread; else 1)
     long long ustride;             // linear index advance per k
     long long ld0, ld1, ld2;       // local array extents
     int T0, T1, T2, nt0, nt1;      // tile extents and tiles per direction (build-time only)
     int sd, lz;                    // slab dimension and its local extent (first / last plane of it are ghosts)
     int wlo, whi;
-    const unsigned char *uni;      // [n] 1: the tile's coefficients are constants (ucoef) -- filled by kf_tile_meta
+    const unsigned char *uni;      // [n] bit 0: the tile's coefficients are constants (ucoef); bit 1: the tile holds band cells (kf_tile_meta)
     const double *ucoef;           // [n][PB_MAXD]
 };
 // cell k (0..FU-1) of this thread inside tile R: linear index and validity
@@ -87,8 +90,8 @@ __device__ __forceinline__ bool tile_cell(const Items &I, const TileRec &R, int 
         return xr < R.nx;
     }
     const int tx = (int)threadIdx.x & ((1 << I.shx) - 1), ty = (int)threadIdx.x >> I.shx;
-    const int xr = tx + I.kx * k, yr = ty + I.ky * k, zr = I.kz * k;
-    idx = R.base + tx + (long long)ty * I.ld0 + (long long)k * I.ustride;
+    const int xr = tx + I.kx * k, yr = ty * I.tym + I.ky * k, zr = I.kz * k;
+    idx = R.base + tx + (long long)(ty * I.tym) * I.ld0 + (long long)k * I.ustride;
     return xr < R.nx && yr >= R.ylo && yr < R.yhi && zr >= R.zlo && zr < R.zhi;
 }
 __device__ __forceinline__ long long tile_of_cell(const Items &I, long long l)
@@ -104,7 +107,7 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
         const int f = (int)(v >> 30);
         const long long ord = (long long)(v & 0x3fffffffu);
         TileRec R;
-        R.f = (signed char)f; R.pad = 0;
+        R.f = (signed char)f; R.full = 0;
         if (f >= 2) {
             R.base = (long long)I.wlo + ord * FTILE;
             const long long left = (long long)I.whi - R.base;
@@ -129,6 +132,7 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
             if (I.sd == 0) { R.base += lo[0]; R.nx = (short)(hi[0] - lo[0]); }
             else R.nx = (short)hi[0];
             R.ylo = (signed char)lo[1]; R.yhi = (signed char)hi[1]; R.zlo = (signed char)lo[2]; R.zhi = (signed char)hi[2];
+            R.full = (lo[0] == 0 && hi[0] == T[0] && lo[1] == 0 && hi[1] == T[1] && lo[2] == 0 && hi[2] == T[2]) ? 1 : 0;
         }
         rec[it] = R;
     }
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
         const TileRec R = I.rec[it];
         if (R.f >= 2) { if (threadIdx.x == 0) uni[it] = 0; continue; }   // uniform over the block
         double mn[PB_MAXD], mx[PB_MAXD];
-        int nok = 0;
+        int nok = 0, hasb = 0;
 #pragma unroll
         for (int d = 0; d < N; ++d) { mn[d] = 1e300; mx[d] = -1e300; }
 #pragma unroll
@@ -438,6 +442,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
             long long l;
             if (!tile_cell(I, R, k, l)) continue;
             ++nok;
+            if (fd.bord && fd.bord[l] >= 0) hasb = 1;
 #pragma unroll
             for (int d = 0; d < N; ++d) {
                 const double *__restrict__ of = R.f == 0 ? fd.off[0][d] : fd.off[1][d];
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
             for (int o = 16; o > 0; o >>= 1) { mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o)); }
             if ((threadIdx.x & 31) == 0) { smn[d][threadIdx.x >> 5] = mn[d]; smx[d][threadIdx.x >> 5] = mx[d]; }
         }
-        __syncthreads();
+        const int anyb = __syncthreads_or(hasb);
         if (threadIdx.x == 0) {
             bool u = true;
             for (int d = 0; d < N; ++d) {
@@ -460,7 +465,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
                 u = u && (a == b);
                 ucoef[(size_t)it * PB_MAXD + d] = a;
             }
-            uni[it] = u ? 1 : 0;
+            uni[it] = (unsigned char)((u ? 1 : 0) | (anyb ? 2 : 0));   // bit 0: constant coefficients, bit 1: holds band cells
             s_uni = u ? 1 : 0;
         }
         __syncthreads();
@@ -486,57 +491,74 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
         const double *__restrict__ xf = f == 0 ? x.f[0] : x.f[1];
         double *__restrict__ yf = f == 0 ? y.f[0] : y.f[1];
         const double *__restrict__ af = f == 0 ? aux.f[0] : aux.f[1];
-        const bool uni = I.uni[it] != 0;
-        long long l[FU];
-        bool ok[FU];
-        double xl[FU], xm[FU][N], xp[FU][N], cm[FU][N], cp[FU][N], av[FU];
-        // phase 1: every load of the FU cells is issued before the first use
-#pragma unroll
-        for (int k = 0; k < FU; ++k) {
-            ok[k] = tile_cell(I, R, k, l[k]);
-            if (ok[k]) {
-                xl[k] = xf[l[k]];
-                if (MODE == 2) av[k] = af[l[k]];
-#pragma unroll
-                for (int d = 0; d < N; ++d) {
-                    const long long s = g.stride[d];
-                    xm[k][d] = xf[l[k] - s];
-                    xp[k][d] = xf[l[k] + s];
-                }
-            }
-        }
-        if (uni) {
+        const bool uni = (I.uni[it] & 1) != 0;
+        if (N >= 2 && uni && R.full) {
+            // interior tile of full cells: constant coefficients, every cell valid.  The thread owns FU cells that are consecutive along
+            // the k direction (y in 2-D, z in 3-D): their k-neighbours are shared registers (FU + 2 loads for the column), the x-neighbours
+            // come from the adjacent lanes (a warp is one 32-cell row; only lanes 0 and 31 load the halo), y-neighbours are loaded in 3-D.
             const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
+            const int lane = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
+            const long long ks = I.ustride;
+            const long long l0 = R.base + lane + (long long)(ty * I.tym) * I.ld0;
+            const double *__restrict__ p0 = xf + l0;
+            double col[FU + 2], yn[FU][2], avv[FU];
+#pragma unroll
+            for (int k = -1; k <= FU; ++k) col[k + 1] = p0[k * ks];
+            if (N == 3) {
+#pragma unroll
+                for (int k = 0; k < FU; ++k) { yn[k][0] = p0[k * ks - I.ld0]; yn[k][1] = p0[k * ks + I.ld0]; }
+            }
+            if (MODE == 2) {
+#pragma unroll
+                for (int k = 0; k < FU; ++k) avv[k] = af[l0 + k * ks];
+            }
+            double lf[FU], rt[FU];
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+                lf[k] = __shfl_up_sync(0xffffffffu, col[k + 1], 1);
+                rt[k] = __shfl_down_sync(0xffffffffu, col[k + 1], 1);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < FU; ++k) lf[k] = p0[k * ks - 1];
+            }
+            if (lane == 31) {
+#pragma unroll
+                for (int k = 0; k < FU; ++k) rt[k] = p0[k * ks + 1];
+            }
+            const double cx = uc[0], ck = uc[N - 1], cy = uc[1];
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+                double acc = col[k + 1] + cx * (lf[k] + rt[k]) + ck * (col[k] + col[k + 2]);
+                if (N == 3) acc += cy * (yn[k][0] + yn[k][1]);
+                yf[l0 + k * ks] = acc;
+                if (MODE == 1) v[0] += col[k + 1] * acc;
+                if (MODE == 2) v[0] += avv[k] * acc;
+                if (MODE == 3) { v[0] += acc * col[k + 1]; v[1] += acc * acc; }
+            }
+            continue;
+        }
+        // general tiles (interface band, domain border ring, partially owned tiles): one cell at a time, coefficients streamed
+        // (or the tile constants when only the validity is partial); ~10 % of the cells
+        const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
+#pragma unroll 1
+        for (int k = 0; k < FU; ++k) {
+            long long l;
+            if (!tile_cell(I, R, k, l)) continue;
+            const double xl = xf[l];
+            double acc = xl;
 #pragma unroll
             for (int d = 0; d < N; ++d) {
-                const double c = uc[d];
-#pragma unroll
-                for (int k = 0; k < FU; ++k) { cm[k][d] = c; cp[k][d] = c; }
+                const long long s = g.stride[d];
+                const double *__restrict__ of = f == 0 ? fd.off[0][d] : fd.off[1][d];
+                const double cm = uni ? uc[d] : of[l], cp = uni ? uc[d] : of[l + s];
+                acc += cm * xf[l - s] + cp * xf[l + s];
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < FU; ++k)
-                if (ok[k]) {
-#pragma unroll
-                    for (int d = 0; d < N; ++d) {
-                        const double *__restrict__ of = f == 0 ? fd.off[0][d] : fd.off[1][d];
-                        cm[k][d] = of[l[k]];
-                        cp[k][d] = of[l[k] + g.stride[d]];
-                    }
-                }
+            yf[l] = acc;
+            if (MODE == 1) v[0] += xl * acc;
+            if (MODE == 2) v[0] += af[l] * acc;
+            if (MODE == 3) { v[0] += acc * xl; v[1] += acc * acc; }
         }
-        // phase 2
-#pragma unroll
-        for (int k = 0; k < FU; ++k)
-            if (ok[k]) {
-                double acc = xl[k];
-#pragma unroll
-                for (int d = 0; d < N; ++d) acc += cm[k][d] * xm[k][d] + cp[k][d] * xp[k][d];
-                yf[l[k]] = acc;
-                if (MODE == 1) v[0] += xl[k] * acc;
-                if (MODE == 2) v[0] += av[k] * acc;
-                if (MODE == 3) { v[0] += acc * xl[k]; v[1] += acc * acc; }
-            }
     }
     if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
@@ -728,8 +750,18 @@ __global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl
     v[1] = v[0];
     block_reduce_publish<2>(v, partials, res + sl_new, counter);
 }
-__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, const double *res, int sl_rho, int sl_new, FVec r, FVec p, StopCrit stop)
+// p = z + beta p with z = r + dz on the band cells (dz = (q(M^_BB) - 1) r_B from kf_band_poly; nullptr: no band preconditioner).
+// Also carries the (rho, rr) pair forward when the iteration was skipped by the stopping test (stop_old).
+__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho, int sl_new, FVec r, FVec p, const double *__restrict__ dz, const int *__restrict__ bord,
+                                               int nB, StopCrit stop_old, StopCrit stop)
 {
+    if (fold_done(res, stop_old)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1];
+            res[FS_RHOB0 + (sl_new >> 1)] = res[FS_RHOB0 + (sl_rho >> 1)];
+        }
+        return;
+    }
     if (fold_done(res, stop)) return;
     const double beta = safe_div(rho_at(res, sl_new), rho_at(res, sl_rho));
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
@@ -737,11 +769,20 @@ __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, const double *res, int s
         const int f = R.f;
         const double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
         double *__restrict__ pf = f == 0 ? p.f[0] : (f == 1 ? p.f[1] : p.f[2]);
+        const bool band_tile = dz != nullptr && (f == 2 || (I.uni[it] & 2));
         long long i[FU]; bool ok[FU]; double pv[FU], rv[FU];
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             ok[k] = tile_cell(I, R, k, i[k]);
             if (ok[k]) { pv[k] = pf[i[k]]; rv[k] = rf[i[k]]; }
+        }
+        if (band_tile) {
+#pragma unroll
+            for (int k = 0; k < FU; ++k)
+                if (ok[k]) {
+                    const long long bo = f == 2 ? i[k] : (long long)bord[i[k]];
+                    if (bo >= 0) rv[k] += dz[(size_t)f * nB + bo];
+                }
         }
 #pragma unroll
         for (int k = 0; k < FU; ++k)
@@ -856,6 +897,7 @@ __global__ void kf_from_scaled_band(FoldDev fd, FVec xh, MVec x)
 // =================================================================================================================================
 // host side
 // =================================================================================================================================
+struct FoldGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0, applies = 0; };
 struct FoldSys {
     bool built = false;
     FoldDev d;
@@ -872,9 +914,9 @@ struct FoldSys {
     bool prec = false;             // band preconditioner available
     double pa0 = 1.0, pa1 = 0.0;   // z_B = pa0 r_B + pa1 M^_BB r_B
     double band_lmin = 0.0, band_lmax = 0.0;
-    cudaGraphExec_t graph_exec = nullptr;   // `check_every` Krylov iterations captured as one graph (single GPU)
-    double graph_key[6] = {};
-    int64_t graph_launches = 0, graph_applies = 0;
+    std::map<int, FoldGraph> graphs;        // chunks of Krylov iterations captured as CUDA graphs, by chunk length (single GPU)
+    double graph_key[5] = {};
+    int last_iters = 0;                     // iteration count of the previous solve (sizes the first chunk of the next one)
     long long cells_uniform = 0, cells_general = 0;   // cells of tiles applied with constant / streamed coefficients (this rank)
     Items I;
     FVec x, b, r, p, v, r0, s, t;
@@ -886,7 +928,9 @@ struct FoldSys {
 static void fold_free_vec(FVec &a) { for (int f = 0; f < 3; ++f) { if (a.f[f]) cudaFree(a.f[f]); a.f[f] = nullptr; } }
 static void fold_free(FoldSys &F)
 {
-    if (F.graph_exec) { cudaGraphExecDestroy(F.graph_exec); F.graph_exec = nullptr; }
+    for (auto &kv : F.graphs) cudaGraphExecDestroy(kv.second.exec);
+    F.graphs.clear();
+    memset(F.graph_key, 0, sizeof(F.graph_key));
     for (int p = 0; p < 2; ++p) { dev_free(F.sc[p]); for (int d = 0; d < PB_MAXD; ++d) dev_free(F.off[p][d]); }
     if (F.Bcell) cudaFree(F.Bcell); if (F.Ecell) cudaFree(F.Ecell); if (F.bord) cudaFree(F.bord); if (F.EB) cudaFree(F.EB);
     if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;

@@ -535,7 +535,7 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
     int rc;
     if ((rc = halo_exchange(ctx, g, in.f, s->nf))) return rc;
     const int grid = sgrid(ctx, g.nown);
-    prof_mark(ctx);
+    prof_mark(ctx, PB_PROF_APPLY);
     ctx->apply_launches++;
     if (s->sp.phase_type == PB200_MONO) {
         GamSpec gs = {s->nf == 2 ? in.f[1] : nullptr, 1.0, nullptr, 0.0, 0.0};
@@ -548,7 +548,7 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
                                                                                  out.f[0], out.f[1], out.f[2])));
     }
     LAUNCH_CHECK(ctx);
-    prof_mark(ctx);
+    prof_mark(ctx, PB_PROF_APPLY);
     return PB200_OK;
 }
 
@@ -764,9 +764,9 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         I.ld0 = g.sd == 0 ? g.lz : g.pd[0];
         I.ld1 = g.N < 2 ? 1 : (g.sd == 1 ? g.lz : g.pd[1]);
         I.ld2 = g.N < 3 ? 1 : g.lz;
-        if (g.N == 1) { I.T0 = FTILE; I.T1 = 1; I.T2 = 1; I.shx = 8; I.kx = FCH; I.ky = 0; I.kz = 0; I.ustride = FCH; }
-        else if (g.N == 2) { I.T0 = 32; I.T1 = 32; I.T2 = 1; I.shx = 5; I.kx = 0; I.ky = 8; I.kz = 0; I.ustride = 8 * I.ld0; }
-        else { I.T0 = 32; I.T1 = 8; I.T2 = 4; I.shx = 5; I.kx = 0; I.ky = 0; I.kz = 1; I.ustride = I.ld0 * I.ld1; }
+        if (g.N == 1) { I.T0 = FTILE; I.T1 = 1; I.T2 = 1; I.shx = 8; I.kx = FCH; I.ky = 0; I.kz = 0; I.tym = 1; I.ustride = FCH; }
+        else if (g.N == 2) { I.T0 = 32; I.T1 = 32; I.T2 = 1; I.shx = 5; I.kx = 0; I.ky = 1; I.kz = 0; I.tym = FU; I.ustride = I.ld0; }
+        else { I.T0 = 32; I.T1 = 8; I.T2 = 4; I.shx = 5; I.kx = 0; I.ky = 0; I.kz = 1; I.tym = 1; I.ustride = I.ld0 * I.ld1; }
         I.nt0 = (int)((I.ld0 + I.T0 - 1) / I.T0); I.nt1 = (int)((I.ld1 + I.T1 - 1) / I.T1);
         const long long nt2 = (I.ld2 + I.T2 - 1) / I.T2;
         const long long ntile = (long long)I.nt0 * I.nt1 * nt2;
@@ -819,7 +819,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 static inline int fold_grid(pb200_solver *s) { int b = s->F.nitems; int cap = s->ctx->sm_count * 8; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
 static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
 // kernels that put one warp on one band cell (4 warps per block)
-static inline int band_wgrid(int n) { int b = (n + 3) / 4; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
+static inline int band_wgrid(int n) { int b = (n + 3) / 4; if (b > 592) b = 592; if (b < 1) b = 1; return b; }
 
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
 static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode, StopCrit stop = StopCrit{0.0, 0.0, -1})
@@ -836,13 +836,13 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     double *res = ctx->d_results;
     const int grid = fold_grid(s);
     double *slotD = res + (mode == 3 ? FS_TS_D : FS_SIG_D), *slotB = res + (mode == 3 ? FS_TS_B : FS_SIG_B);
-    prof_mark(ctx);
+    prof_mark(ctx, PB_PROF_APPLY);
     ctx->apply_launches++;
 #define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<grid, FCH, 0, ctx->stream>>>(g, F.d, F.I, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop)))
     if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else FOLD_DENSE(3);
 #undef FOLD_DENSE
     LAUNCH_CHECK(ctx);
-    prof_mark(ctx);
+    prof_mark(ctx, PB_PROF_APPLY);
     if (F.d.has_w && F.d.nE > 0) {
         const int gb = band_wgrid(F.d.nE);
 #define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 128, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
@@ -887,14 +887,12 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, F.r, ctx->d_partials, res + FS_RR0, ctx->d_counter); LAUNCH_CHECK(ctx);
     }
     if ((rc = allreduce_results(ctx, FS_BB, 2))) return rc;
-    double h[2];
-    if ((rc = fetch_results(ctx, FS_BB, 2, h))) return rc;
-    const double bnorm = sqrt(h[0]);
-    double rnorm = sqrt(h[1]);
-    const double tol = fmax(o.rtol * bnorm, o.atol);
-    int it = 0, converged = rnorm <= tol ? 1 : 0;
+    // No host look at ||b||, ||r0|| here: the device-side stopping test (fold_done) needs neither, and a converged start simply turns
+    // every kernel of the first chunk into a no-op.  bnorm / rnorm / iteration count come back with the first fetch.
+    double bnorm = 0.0, rnorm = 0.0, tol = 0.0;
+    int it = 0, converged = 0;
     int cur = 0;
-    if (!converged) {
+    {
         // (rho, rr) pair 0 = (rr0, rr0)
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -922,7 +920,9 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
             int rc2;
             if (cg) {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc2;
+                prof_mark(ctx, PB_PROF_UPDATE);
                 kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                prof_mark(ctx, PB_PROF_UPDATE);
                 if ((rc2 = allreduce_results(ctx, 2 * nxt, 2))) return rc2;
                 if (prec) {   // z = r + (q(M^_BB) - 1) r_B on the band: rho_new = (r, r) + (r_B, dz_B)
                     if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc2 = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc2; if ((rc2 = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc2; }
@@ -930,8 +930,9 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
                     LAUNCH_CHECK(ctx);
                     if ((rc2 = allreduce_results(ctx, FS_RHOB0 + nxt, 1))) return rc2;
                 }
-                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.p, stn); LAUNCH_CHECK(ctx);
-                if (prec) { kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, stn); LAUNCH_CHECK(ctx); }
+                prof_mark(ctx, PB_PROF_PUPD);
+                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.p, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
+                prof_mark(ctx, PB_PROF_PUPD);
             } else {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc2;
                 kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
@@ -940,60 +941,62 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
                 if ((rc2 = allreduce_results(ctx, 2 * nxt, 2))) return rc2;
                 kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.v, F.p, stn); LAUNCH_CHECK(ctx);
             }
-            // a skipped iteration publishes nothing: carry the converged pair over so that the next iteration sees it too
-            kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, 2 * curp, 2 * nxt, st); LAUNCH_CHECK(ctx);
+            // a skipped iteration publishes nothing: carry the converged pair over so that the next iteration sees it too (CG: inside kf_cg_p)
+            if (!cg) { kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, 2 * curp, 2 * nxt, st); LAUNCH_CHECK(ctx); }
             return PB200_OK;
         };
-        // Single GPU, no per-launch profiling: the `check_every` iterations between two host looks are replayed as ONE CUDA graph
-        // (captured once per solver and parameter set), which removes the per-launch CPU cost and most of the inter-kernel gaps.
-        int chunk = o.check_every;
+        // Chunks of iterations between two host looks at the residual: the first chunk is sized by the iteration count of the previous
+        // solve (time steps resemble each other), later ones are short.  Single GPU, no per-launch profiling: a chunk is replayed as ONE
+        // CUDA graph (captured once per chunk length and parameter set), which removes the per-launch CPU cost and most inter-kernel gaps.
         const bool use_graph = ctx->nranks == 1 && !ctx->profile && !getenv("PB200_NO_GRAPH") && o.maxit >= 2;
-        if (use_graph) {
-            if (chunk & 1) ++chunk;
-            if (chunk > o.maxit) chunk = o.maxit & ~1;
-            if (chunk < 2) chunk = 2;
-            const double gkey[6] = {(double)method, (double)chunk, o.rtol, o.atol, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
-            if (!F.graph_exec || memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
-                if (F.graph_exec) { cudaGraphExecDestroy(F.graph_exec); F.graph_exec = nullptr; }
-                cudaGraph_t gr = nullptr;
-                const int64_t l0 = ctx->launches, a0 = ctx->apply_launches;
-                CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-                int rcc = PB200_OK;
-                for (int q = 0; q < chunk && !rcc; ++q) rcc = enqueue(q & 1);   // starts and ends on pair 0
-                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &gr);
-                if (rcc) { if (gr) cudaGraphDestroy(gr); return rcc; }
-                CUDA_TRY(ctx, ce);
-                CUDA_TRY(ctx, cudaGraphInstantiate(&F.graph_exec, gr, 0));
-                cudaGraphDestroy(gr);
-                F.graph_launches = ctx->launches - l0; F.graph_applies = ctx->apply_launches - a0;
-                ctx->launches = l0; ctx->apply_launches = a0;   // capturing launches nothing
-                memcpy(F.graph_key, gkey, sizeof(gkey));
-            }
+        auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
+        const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
+        const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
+        const double gkey[5] = {(double)method, o.rtol, o.atol, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
+        if (use_graph && memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
+            for (auto &kv : F.graphs) cudaGraphExecDestroy(kv.second.exec);
+            F.graphs.clear();
+            memcpy(F.graph_key, gkey, sizeof(gkey));
         }
-        // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
-        // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
         int queued = 0;
         while (queued < o.maxit) {
+            int chunk = queued == 0 ? first_chunk : later_chunk;
+            if (chunk > o.maxit - queued) chunk = even_up(o.maxit - queued);
             if (use_graph) {
-                CUDA_TRY(ctx, cudaGraphLaunch(F.graph_exec, ctx->stream));
-                ctx->launches += F.graph_launches; ctx->apply_launches += F.graph_applies;
-                queued += chunk;   // cur stays 0
+                auto gi = F.graphs.find(chunk);
+                if (gi == F.graphs.end()) {
+                    cudaGraph_t gr = nullptr;
+                    const int64_t l0 = ctx->launches, a0 = ctx->apply_launches;
+                    CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                    int rcc = PB200_OK;
+                    for (int q = 0; q < chunk && !rcc; ++q) rcc = enqueue(q & 1);   // even length: starts and ends on pair 0
+                    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &gr);
+                    if (rcc) { if (gr) cudaGraphDestroy(gr); return rcc; }
+                    CUDA_TRY(ctx, ce);
+                    FoldGraph fg;
+                    CUDA_TRY(ctx, cudaGraphInstantiate(&fg.exec, gr, 0));
+                    cudaGraphDestroy(gr);
+                    fg.launches = ctx->launches - l0; fg.applies = ctx->apply_launches - a0;
+                    ctx->launches = l0; ctx->apply_launches = a0;   // capturing launches nothing
+                    gi = F.graphs.emplace(chunk, fg).first;
+                }
+                CUDA_TRY(ctx, cudaGraphLaunch(gi->second.exec, ctx->stream));
+                ctx->launches += gi->second.launches; ctx->apply_launches += gi->second.applies;
             } else {
-                if ((rc = enqueue(cur))) return rc;
-                cur ^= 1;
-                ++queued;
+                for (int q = 0; q < chunk; ++q) { if ((rc = enqueue(cur))) return rc; cur ^= 1; }
             }
-            if (use_graph || queued % o.check_every == 0 || queued >= o.maxit) {
-                double hh[2];
-                if ((rc = fetch_results(ctx, 2 * cur + 1, 1, hh))) return rc;
-                if ((rc = fetch_results(ctx, FS_ITERS, 1, hh + 1))) return rc;
-                rnorm = sqrt(hh[0]);
-                it = (int)(hh[1] + 0.5);
-                if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] queued %d it %d rnorm %.3e tol %.3e\n", queued, it, rnorm, tol);
-                if (rnorm <= tol) { converged = 1; break; }
-                if (!(rnorm == rnorm)) break;
-            }
+            queued += chunk;
+            double all[16];
+            if ((rc = fetch_results(ctx, 0, 16, all))) return rc;   // one look: rr, iteration count, ||b||^2
+            bnorm = sqrt(all[FS_BB]);
+            tol = fmax(o.rtol * bnorm, o.atol);
+            rnorm = sqrt(all[2 * cur + 1]);
+            it = (int)(all[FS_ITERS] + 0.5);
+            if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] queued %d it %d rnorm %.3e tol %.3e\n", queued, it, rnorm, tol);
+            if (rnorm <= tol) { converged = 1; break; }
+            if (!(rnorm == rnorm)) break;
         }
+        F.last_iters = it;
     }
     kf_from_scaled_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, F.x, s->x); LAUNCH_CHECK(ctx);
     if (band) { kf_from_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, F.x, s->x); LAUNCH_CHECK(ctx); }
@@ -1228,7 +1231,8 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         stats->solve_ms = ms_solve; stats->setup_ms = ms_setup;
         stats->dof_bulk = s->dof_bulk; stats->dof_ifc = s->dof_ifc;
         stats->launches = ctx->launches - launches0;
-        stats->apply_ms = prof_collect(ctx);
+        prof_collect(ctx, stats->kernel_ms, stats->kernel_launches);
+        stats->apply_ms = stats->kernel_ms[PB_PROF_APPLY];
         stats->apply_launches = ctx->apply_launches - applies0;
         stats->apply_cells_uniform = use_fold ? s->F.cells_uniform : 0;
         stats->apply_cells_general = use_fold ? s->F.cells_general : 0;
