@@ -131,7 +131,7 @@ def run_reference(args):
            "data": "synthetic", "config": {"workload": "Heat_2ph_2D diphasic BE step (BASELINE.json configs[1])", "sample": sample},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -145,6 +145,7 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
@@ -309,6 +310,7 @@ def run_gpu(args):
                 "avg_launch_us": us, "peak_source": peak_src, "timed": "CUDA events around every launch, separate pass of the same K steps",
                 "kernels": table}
 
+    vec_len = int(allsum(4 * nloc))     # collective: every rank calls it
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
@@ -320,20 +322,38 @@ def run_gpu(args):
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": "Heat_2ph_2D diphasic BE step (BASELINE.json configs[1])", "grid": [nx, nx * N], "cells_per_gpu": [nx, nx],
-                          "dof": dof, "vector_length_4n": int(allsum(4 * nloc)), "scheme": "BE", "dt": dt, "krylov": "BiCGSTAB" if args.method == 2 else "CG (symmetrised, block-Jacobi-scaled system)",
+                          "dof": dof, "vector_length_4n": vec_len, "scheme": "BE", "dt": dt, "krylov": "BiCGSTAB" if args.method == 2 else "CG (symmetrised, block-Jacobi-scaled system)",
                           "rtol": 1e-10, "iters_per_step": float(np.mean(iters)), "final_rel_residual": rnorm_rel,
                           "parallelism": f"y-slab x{world}" if world > 1 else "single GPU",
                           "l2": f"inputs larger than L2: {fields_mb:.0f} MB per field, > 30 fields streamed per step vs {L2_MB} MB L2",
                           "capacity_build_s": cap_s},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     pb.finalize()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line, on the process's original stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    # Libraries (NCCL's version banner, torch warnings) write to fd 1: point it at stderr for the whole run and keep the original
+    # stdout for the result line only.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

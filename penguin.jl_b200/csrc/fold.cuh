@@ -139,9 +139,11 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
 }
 
 // result slots of the folded Krylov loops (dense-part and band-part partial sums are adjacent: one allreduce covers both)
-enum { FS_PAIR0 = 0, FS_PAIR1 = 2, FS_SIG_D = 4, FS_SIG_B = 5, FS_TS_D = 6, FS_TT_D = 7, FS_TS_B = 8, FS_TT_B = 9, FS_BB = 10, FS_RR0 = 11, FS_ITERS = 12, FS_RHOB0 = 13, FS_RHOB1 = 14, FS_TMP = 15 };
-// rho of the (rho, rr) pair at slot sl (0 or 2): with the band preconditioner rho = (r, r) + (r_B, z_B - r_B), the second part in FS_RHOB*
-__device__ __forceinline__ double rho_at(const double *res, int sl) { return res[sl] + res[FS_RHOB0 + (sl >> 1)]; }
+// (rho, rr, rho_band) triples live in two ping-pong groups {0,1,2} and {3,4,5}: one allreduce of 3 doubles publishes a new triple
+enum { FS_PAIR0 = 0, FS_PAIR1 = 3, FS_SIG_D = 6, FS_SIG_B = 7, FS_TS_D = 8, FS_TT_D = 9, FS_TS_B = 10, FS_TT_B = 11, FS_BB = 12, FS_RR0 = 13, FS_ITERS = 14, FS_TMP = 15 };
+#define FS_TRIPLE(p) (3 * (p))
+// rho of the triple at slot sl: with the band preconditioner rho = (r, r) + (r_B, z_B - r_B), the second part in slot sl + 2
+__device__ __forceinline__ double rho_at(const double *res, int sl) { return res[sl] + res[sl + 2]; }
 
 // device-side stopping test: the Krylov kernels of an iteration turn into no-ops once ||r||^2 (slot `sl_rr`) is below the
 // tolerance, so the host may queue several iterations between two looks at the residual without doing extra work
@@ -584,7 +586,9 @@ __device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int 
             ln = (kk & 1) ? l + g.stride[d] : l - g.stride[d];
             nb = fd.EnbrB[(size_t)e * (2 * N) + kk];
         }
-        const bool use = !(BAND_ONLY && nb < 0);
+        // BAND_ONLY: the preconditioner block is the band block of THIS rank (neighbours in the ghost planes are left out), so that
+        // applying it needs no halo exchange; the operator itself (BAND_ONLY == false) couples across ranks as usual
+        const bool use = !(BAND_ONLY && (nb < 0 || (k > 0 && (nb < fd.nBlo || nb >= fd.nBlo + fd.nBown))));
         if (use) {
             if (c == 0) xv = x.f[0][ln];
             else if (c == 1) { if (fd.nbulk > 1) xv = x.f[1][ln]; }
@@ -758,7 +762,7 @@ __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho,
     if (fold_done(res, stop_old)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1];
-            res[FS_RHOB0 + (sl_new >> 1)] = res[FS_RHOB0 + (sl_rho >> 1)];
+            res[sl_new + 2] = res[sl_rho + 2];
         }
         return;
     }
@@ -828,7 +832,7 @@ __global__ void kf_carry_pair(double *res, int sl_old, int sl_new, StopCrit stop
 {
     if (threadIdx.x == 0 && fold_done(res, stop)) {
         res[sl_new] = res[sl_old]; res[sl_new + 1] = res[sl_old + 1];
-        res[FS_RHOB0 + (sl_new >> 1)] = res[FS_RHOB0 + (sl_old >> 1)];
+        res[sl_new + 2] = res[sl_old + 2];
     }
 }
 

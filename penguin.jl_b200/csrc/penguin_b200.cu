@@ -636,7 +636,6 @@ static int fold_band_spectrum(pb200_solver *s)
             nrm2 = h[0];
             if (!(nrm2 > 0.0)) { *lam = 0.0; return PB200_OK; }
             kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 1.0 / sqrt(nrm2), 0, res, none); LAUNCH_CHECK(ctx);
-            if (ctx->nranks > 1) { double *fl[2] = {F.v.f[0], F.v.f[1]}; if ((rc = halo_exchange(ctx, g, fl, d.nbulk))) return rc; if ((rc = fold_band_halo(ctx, F, s->bh, F.v.f[2], 1))) return rc; }
             // y = (shift + sign A) x ; Rayleigh quotient (x, y)
             DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 128, 0, ctx->stream>>>(g, d, F.v, F.dz, shift, sign, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
             LAUNCH_CHECK(ctx);
@@ -821,6 +820,43 @@ static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLO
 // kernels that put one warp on one band cell (4 warps per block)
 static inline int band_wgrid(int n) { int b = (n + 3) / 4; if (b > 592) b = 592; if (b < 1) b = 1; return b; }
 
+// ghost planes of the bulk fields and ghost entries of the compact w of one Krylov vector, ONE NCCL group (one launch)
+static int fold_halo(pb200_solver *s, const FVec &x)
+{
+    pb200_ctx *ctx = s->ctx;
+    if (ctx->nranks == 1) return PB200_OK;
+    const Grid &g = s->g;
+    const FoldSys &F = s->F;
+    const int nB = F.d.nB, nBlo = F.d.nBlo, nBown = F.d.nBown, nBhi = nB - nBlo - nBown;
+    const BandHalo &bh = s->bh;
+    const size_t cnt = (size_t)g.plane;
+    NCCL_TRY(ctx, g_nccl.GroupStart());
+    for (int f = 0; f < F.d.nbulk; ++f) {
+        double *p = x.f[f];
+        if (ctx->rank > 0) {
+            NCCL_TRY(ctx, g_nccl.Send(p + g.plane, cnt, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx, g_nccl.Recv(p, cnt, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+        }
+        if (ctx->rank < ctx->nranks - 1) {
+            NCCL_TRY(ctx, g_nccl.Send(p + (long long)(g.lz - 2) * g.plane, cnt, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx, g_nccl.Recv(p + (long long)(g.lz - 1) * g.plane, cnt, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+        }
+    }
+    if (F.d.has_w && nB > 0) {
+        double *p = x.f[2];
+        if (ctx->rank > 0) {
+            if (bh.lo_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.lo_send0, (size_t)bh.lo_sendn, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+            if (nBlo) NCCL_TRY(ctx, g_nccl.Recv(p, (size_t)nBlo, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+        }
+        if (ctx->rank < ctx->nranks - 1) {
+            if (bh.hi_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.hi_send0, (size_t)bh.hi_sendn, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+            if (nBhi) NCCL_TRY(ctx, g_nccl.Recv(p + nBlo + nBown, (size_t)nBhi, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+        }
+    }
+    NCCL_TRY(ctx, g_nccl.GroupEnd());
+    return PB200_OK;
+}
+
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
 static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode, StopCrit stop = StopCrit{0.0, 0.0, -1})
 {
@@ -828,11 +864,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     const Grid &g = s->g;
     FoldSys &F = s->F;
     int rc;
-    if (ctx->nranks > 1) {
-        double *fl[2] = {x.f[0], x.f[1]};
-        if ((rc = halo_exchange(ctx, g, fl, F.d.nbulk))) return rc;
-        if (F.d.has_w && (rc = fold_band_halo(ctx, F, s->bh, x.f[2], 1))) return rc;
-    }
+    if ((rc = fold_halo(s, x))) return rc;
     double *res = ctx->d_results;
     const int grid = fold_grid(s);
     double *slotD = res + (mode == 3 ? FS_TS_D : FS_SIG_D), *slotB = res + (mode == 3 ? FS_TS_B : FS_SIG_B);
@@ -903,10 +935,9 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         if (cg) {
             kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
             if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
-                if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc; if ((rc = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc; }
-                DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_RHOB0, ctx->d_counter, res, nostop)));
+                DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
                 LAUNCH_CHECK(ctx);
-                if ((rc = allreduce_results(ctx, FS_RHOB0, 1))) return rc;
+                if ((rc = allreduce_results(ctx, FS_PAIR0 + 2, 1))) return rc;
                 kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx);
             }
         }
@@ -915,40 +946,39 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
         auto enqueue = [&](int curp) -> int {   // one Krylov iteration reading pair `curp`, publishing pair curp ^ 1
             const int nxt = curp ^ 1;
-            StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, 2 * curp + 1};
-            StopCrit stn = {o.rtol * o.rtol, o.atol * o.atol, 2 * nxt + 1};
+            StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, FS_TRIPLE(curp) + 1};
+            StopCrit stn = {o.rtol * o.rtol, o.atol * o.atol, FS_TRIPLE(nxt) + 1};
             int rc2;
             if (cg) {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc2;
                 prof_mark(ctx, PB_PROF_UPDATE);
-                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
                 prof_mark(ctx, PB_PROF_UPDATE);
-                if ((rc2 = allreduce_results(ctx, 2 * nxt, 2))) return rc2;
+                if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 2))) return rc2;
                 if (prec) {   // z = r + (q(M^_BB) - 1) r_B on the band: rho_new = (r, r) + (r_B, dz_B)
-                    if (ctx->nranks > 1) { double *fl[2] = {F.r.f[0], F.r.f[1]}; if ((rc2 = halo_exchange(ctx, s->g, fl, F.d.nbulk))) return rc2; if ((rc2 = fold_band_halo(ctx, F, s->bh, F.r.f[2], 1))) return rc2; }
-                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_RHOB0 + nxt, ctx->d_counter, res, st)));
+                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
                     LAUNCH_CHECK(ctx);
-                    if ((rc2 = allreduce_results(ctx, FS_RHOB0 + nxt, 1))) return rc2;
+                    if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 3))) return rc2;
                 }
                 prof_mark(ctx, PB_PROF_PUPD);
-                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.p, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
+                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.r, F.p, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
                 prof_mark(ctx, PB_PROF_PUPD);
             } else {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc2;
-                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
+                kf_bicg_s<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), F.r, F.v, F.s, st); LAUNCH_CHECK(ctx);
                 if ((rc2 = fold_apply(s, F.s, F.t, F.t, 3, st))) return rc2;
-                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
-                if ((rc2 = allreduce_results(ctx, 2 * nxt, 2))) return rc2;
-                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, 2 * curp, 2 * nxt, F.r, F.v, F.p, stn); LAUNCH_CHECK(ctx);
+                kf_bicg_xr<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.p, F.s, F.t, F.r0, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 2))) return rc2;
+                kf_bicg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.r, F.v, F.p, stn); LAUNCH_CHECK(ctx);
             }
             // a skipped iteration publishes nothing: carry the converged pair over so that the next iteration sees it too (CG: inside kf_cg_p)
-            if (!cg) { kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, 2 * curp, 2 * nxt, st); LAUNCH_CHECK(ctx); }
+            if (!cg) { kf_carry_pair<<<1, 32, 0, ctx->stream>>>(res, FS_TRIPLE(curp), FS_TRIPLE(nxt), st); LAUNCH_CHECK(ctx); }
             return PB200_OK;
         };
         // Chunks of iterations between two host looks at the residual: the first chunk is sized by the iteration count of the previous
         // solve (time steps resemble each other), later ones are short.  Single GPU, no per-launch profiling: a chunk is replayed as ONE
         // CUDA graph (captured once per chunk length and parameter set), which removes the per-launch CPU cost and most inter-kernel gaps.
-        const bool use_graph = ctx->nranks == 1 && !ctx->profile && !getenv("PB200_NO_GRAPH") && o.maxit >= 2;
+        const bool use_graph = (ctx->nranks == 1 || getenv("PB200_GRAPH_NCCL")) && !ctx->profile && !getenv("PB200_NO_GRAPH") && o.maxit >= 2;
         auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
         const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
         const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
@@ -990,7 +1020,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
             if ((rc = fetch_results(ctx, 0, 16, all))) return rc;   // one look: rr, iteration count, ||b||^2
             bnorm = sqrt(all[FS_BB]);
             tol = fmax(o.rtol * bnorm, o.atol);
-            rnorm = sqrt(all[2 * cur + 1]);
+            rnorm = sqrt(all[FS_TRIPLE(cur) + 1]);
             it = (int)(all[FS_ITERS] + 0.5);
             if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] queued %d it %d rnorm %.3e tol %.3e\n", queued, it, rnorm, tol);
             if (rnorm <= tol) { converged = 1; break; }
