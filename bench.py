@@ -282,12 +282,12 @@ def run_gpu(args):
         # Algorithmic bytes per launch on this rank, from the tile census of the folded system:
         #   apply   : x and y for every cell of an active tile + the N coefficient arrays for the cells of tiles whose coefficients are
         #             not constants (interface band, domain border ring)
-        #   update  : x += a p, r -= a v with fused dots: read p, v, x, r, write x, r  -> 6 passes
-        #   p-update: p = r + b p: read r, p, write p -> 3 passes
+        #   update  : r -= a v with fused dots: read v, r, write r -> 3 passes
+        #   p-update: x += a p, p = z + b p: read r, p, x, write p, x -> 5 passes
         cu, cg = int(st.apply_cells_uniform), int(st.apply_cells_general)
         cells = cu + cg
-        names = ["operator apply, dense part (kf_apply_dense)", "x, r update + fused dots (kf_cg_update / kf_bicg_xr)", "search direction update (kf_cg_p)"]
-        abytes = [8 * (2 * cells + mesh.N * cg), 8 * 6 * cells, 8 * 3 * cells]
+        names = ["operator apply, dense part (kf_apply_dense)", "residual update + fused dots (kf_cg_update)", "solution + search direction update (kf_cg_p)"]
+        abytes = [8 * (2 * cells + mesh.N * cg), 8 * 3 * cells, 8 * 5 * cells]
         table = []
         for q in range(3):
             if kn[q] and kms[q] > 0:

@@ -301,8 +301,15 @@ __device__ __forceinline__ void block_reduce_publish(double (&v)[K], double *__r
         __threadfence();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            double s = 0.0;
-            for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(&partials[(size_t)k * RED_MAXBLOCKS + i]);
+            // four independent accumulators: the loads of a thread are in flight together (the summation order stays fixed)
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            const double *__restrict__ pk = partials + (size_t)k * RED_MAXBLOCKS;
+            unsigned i = threadIdx.x;
+            for (; i + 3 * blockDim.x < gridDim.x; i += 4 * blockDim.x) {
+                s0 += __ldcg(pk + i); s1 += __ldcg(pk + i + blockDim.x); s2 += __ldcg(pk + i + 2 * blockDim.x); s3 += __ldcg(pk + i + 3 * blockDim.x);
+            }
+            for (; i < gridDim.x; i += blockDim.x) s0 += __ldcg(pk + i);
+            double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
             __syncthreads();

@@ -618,7 +618,7 @@ __device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int 
 
 // band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here
 template <int N, int MODE>
-__global__ void __launch_bounds__(128) kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
+__global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
                                                      const double *res, StopCrit stop)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(128) kf_apply_band(Grid g, FoldDev fd, FVec x,
 // block M^_BB (all unknowns of the band cells) used as preconditioner on the band only: z = r outside the band, z_B = q(M^_BB) r_B.
 // out[c][bo] = ca x_c + cb (M^_BB x)_c for every OWNED band cell; publishes sum_c x_c out_c  (x read from an FVec)
 template <int N>
-__global__ void __launch_bounds__(128) kf_band_poly(Grid g, FoldDev fd, FVec x, double *out, double ca, double cb, double *partials, double *results,
+__global__ void __launch_bounds__(256) kf_band_poly(Grid g, FoldDev fd, FVec x, double *out, double ca, double cb, double *partials, double *results,
                                                     unsigned *counter, const double *res, StopCrit stop)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
@@ -721,9 +721,8 @@ __global__ void __launch_bounds__(FCH) kf_dot(Items I, FVec a, FVec b, double *p
     FV_LOOP(I) v[0] += a.f[f][i] * b.f[f][i];
     block_reduce_publish<1>(v, partials, results, counter);
 }
-// CG: x += alpha p ; r -= alpha q ; publishes (rho_new, rr) = ((r, r), (r, r))
-__global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec q, FVec x, FVec r, double *partials, unsigned *counter,
-                                                    StopCrit stop)
+// CG: r -= alpha q ; publishes (rho_new, rr) = ((r, r), (r, r)).  (x += alpha p is done by kf_cg_p, which reads p anyway.)
+__global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl_rho, int sl_new, FVec q, FVec r, double *partials, unsigned *counter, StopCrit stop)
 {
     if (fold_done(res, stop)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) res[FS_ITERS] += 1.0;
@@ -732,20 +731,17 @@ __global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
         const TileRec R = I.rec[it];
         const int f = R.f;
-        const double *__restrict__ pf = f == 0 ? p.f[0] : (f == 1 ? p.f[1] : p.f[2]);
         const double *__restrict__ qf = f == 0 ? q.f[0] : (f == 1 ? q.f[1] : q.f[2]);
-        double *__restrict__ xf = f == 0 ? x.f[0] : (f == 1 ? x.f[1] : x.f[2]);
         double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
-        long long i[FU]; bool ok[FU]; double pv[FU], qv[FU], xv[FU], rv[FU];
+        long long i[FU]; bool ok[FU]; double qv[FU], rv[FU];
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             ok[k] = tile_cell(I, R, k, i[k]);
-            if (ok[k]) { pv[k] = pf[i[k]]; qv[k] = qf[i[k]]; xv[k] = xf[i[k]]; rv[k] = rf[i[k]]; }
+            if (ok[k]) { qv[k] = qf[i[k]]; rv[k] = rf[i[k]]; }
         }
 #pragma unroll
         for (int k = 0; k < FU; ++k)
             if (ok[k]) {
-                xf[i[k]] = xv[k] + alpha * pv[k];
                 const double rn = rv[k] - alpha * qv[k];
                 rf[i[k]] = rn;
                 v[0] += rn * rn;
@@ -756,31 +752,31 @@ __global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl
 }
 // p = z + beta p with z = r + dz on the band cells (dz = (q(M^_BB) - 1) r_B from kf_band_poly; nullptr: no band preconditioner).
 // Also carries the (rho, rr) pair forward when the iteration was skipped by the stopping test (stop_old).
-__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho, int sl_new, FVec r, FVec p, const double *__restrict__ dz, const int *__restrict__ bord,
-                                               int nB, StopCrit stop_old, StopCrit stop)
+__global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho, int sl_new, FVec r, FVec p, FVec x, const double *__restrict__ dz,
+                                               const int *__restrict__ bord, int nB, StopCrit stop_old, StopCrit stop)
 {
     if (fold_done(res, stop_old)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1];
-            res[sl_new + 2] = res[sl_rho + 2];
-        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; }
         return;
     }
-    if (fold_done(res, stop)) return;
+    // x += alpha p_old belongs to this iteration even when it is the one that converged; the new direction is only needed otherwise
+    const bool last = fold_done(res, stop);
+    const double alpha = safe_div(rho_at(res, sl_rho), res[FS_SIG_D] + res[FS_SIG_B]);
     const double beta = safe_div(rho_at(res, sl_new), rho_at(res, sl_rho));
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
         const TileRec R = I.rec[it];
         const int f = R.f;
         const double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
         double *__restrict__ pf = f == 0 ? p.f[0] : (f == 1 ? p.f[1] : p.f[2]);
+        double *__restrict__ xf = f == 0 ? x.f[0] : (f == 1 ? x.f[1] : x.f[2]);
         const bool band_tile = dz != nullptr && (f == 2 || (I.uni[it] & 2));
-        long long i[FU]; bool ok[FU]; double pv[FU], rv[FU];
+        long long i[FU]; bool ok[FU]; double pv[FU], rv[FU], xv[FU];
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             ok[k] = tile_cell(I, R, k, i[k]);
-            if (ok[k]) { pv[k] = pf[i[k]]; rv[k] = rf[i[k]]; }
+            if (ok[k]) { pv[k] = pf[i[k]]; xv[k] = xf[i[k]]; rv[k] = last ? 0.0 : rf[i[k]]; }
         }
-        if (band_tile) {
+        if (band_tile && !last) {
 #pragma unroll
             for (int k = 0; k < FU; ++k)
                 if (ok[k]) {
@@ -790,7 +786,10 @@ __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho,
         }
 #pragma unroll
         for (int k = 0; k < FU; ++k)
-            if (ok[k]) pf[i[k]] = rv[k] + beta * pv[k];
+            if (ok[k]) {
+                xf[i[k]] = xv[k] + alpha * pv[k];
+                if (!last) pf[i[k]] = rv[k] + beta * pv[k];
+            }
     }
 }
 // BiCGSTAB

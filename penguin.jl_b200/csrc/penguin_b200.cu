@@ -629,7 +629,7 @@ static int fold_band_spectrum(pb200_solver *s)
         double rq = 0.0;
         for (int it = 0; it < iters; ++it) {
             // ||x||^2 via (x, 1 x + 0 A x)
-            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 128, 0, ctx->stream>>>(g, d, F.v, F.dz, 1.0, 0.0, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
+            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 256, 0, ctx->stream>>>(g, d, F.v, F.dz, 1.0, 0.0, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
             LAUNCH_CHECK(ctx);
             if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
             if ((rc = fetch_results(ctx, SL_TMP, 1, h))) return rc;
@@ -637,7 +637,7 @@ static int fold_band_spectrum(pb200_solver *s)
             if (!(nrm2 > 0.0)) { *lam = 0.0; return PB200_OK; }
             kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 1.0 / sqrt(nrm2), 0, res, none); LAUNCH_CHECK(ctx);
             // y = (shift + sign A) x ; Rayleigh quotient (x, y)
-            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 128, 0, ctx->stream>>>(g, d, F.v, F.dz, shift, sign, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
+            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 256, 0, ctx->stream>>>(g, d, F.v, F.dz, shift, sign, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
             LAUNCH_CHECK(ctx);
             if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
             if ((rc = fetch_results(ctx, SL_TMP, 1, h))) return rc;
@@ -817,8 +817,8 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 
 static inline int fold_grid(pb200_solver *s) { int b = s->F.nitems; int cap = s->ctx->sm_count * 8; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
 static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
-// kernels that put one warp on one band cell (4 warps per block)
-static inline int band_wgrid(int n) { int b = (n + 3) / 4; if (b > 592) b = 592; if (b < 1) b = 1; return b; }
+// kernels that put one warp on one band cell (8 warps per block, every cell in flight at once)
+static inline int band_wgrid(int n) { int b = (n + 7) / 8; if (b > 2048) b = 2048; if (b < 1) b = 1; return b; }   // 8 warps per block
 
 // ghost planes of the bulk fields and ghost entries of the compact w of one Krylov vector, ONE NCCL group (one launch)
 static int fold_halo(pb200_solver *s, const FVec &x)
@@ -877,7 +877,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     prof_mark(ctx, PB_PROF_APPLY);
     if (F.d.has_w && F.d.nE > 0) {
         const int gb = band_wgrid(F.d.nE);
-#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 128, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
+#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 256, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
         if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else FOLD_BAND(3);
 #undef FOLD_BAND
         LAUNCH_CHECK(ctx);
@@ -935,7 +935,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         if (cg) {
             kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
             if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
-                DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
+                DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
                 LAUNCH_CHECK(ctx);
                 if ((rc = allreduce_results(ctx, FS_PAIR0 + 2, 1))) return rc;
                 kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx);
@@ -952,16 +952,16 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
             if (cg) {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc2;
                 prof_mark(ctx, PB_PROF_UPDATE);
-                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.p, F.v, F.x, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                kf_cg_update<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
                 prof_mark(ctx, PB_PROF_UPDATE);
                 if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 2))) return rc2;
                 if (prec) {   // z = r + (q(M^_BB) - 1) r_B on the band: rho_new = (r, r) + (r_B, dz_B)
-                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 128, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
+                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
                     LAUNCH_CHECK(ctx);
                     if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 3))) return rc2;
                 }
                 prof_mark(ctx, PB_PROF_PUPD);
-                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.r, F.p, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
+                kf_cg_p<<<grid, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.r, F.p, F.x, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
                 prof_mark(ctx, PB_PROF_PUPD);
             } else {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc2;

@@ -76,7 +76,7 @@ def main():
     lib.pb200_set_profiling(ctx.h, 0)
     cu, cg = int(st.apply_cells_uniform), int(st.apply_cells_general)
     cells = cu + cg
-    abytes = [8 * (2 * cells + 3 * cg), 8 * 6 * cells, 8 * 3 * cells]
+    abytes = [8 * (2 * cells + 3 * cg), 8 * 3 * cells, 8 * 5 * cells]
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     kern = []
     for q, nm in enumerate(["apply", "update", "p-update"]):
