@@ -168,7 +168,7 @@ typedef struct {
     double rtol; /* stop when ||r|| <= max(rtol ||b||, atol)  (IterativeSolvers convention) */
     double atol;
     int maxit;
-    int warm_start; /* 1: start from the previous state, 0: zero initial guess like the reference */
+    int warm_start; /* 0: zero initial guess like the reference; 1: previous state; m >= 2: polynomial extrapolation through the last m states (m <= 5) */
     int check_every; /* convergence is tested on the host every this many iterations (>= 1) */
     int path;        /* PB200_PATH_*: which implementation of the solve runs */
 } pb200_krylov_opts;

@@ -110,10 +110,21 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
 }
 
 // initial guess: previous state restricted to the free sets (warm) or zero
-__global__ void k_guess(Grid g, int warm, const unsigned char *__restrict__ m, unsigned char bit, const double *__restrict__ T, double *__restrict__ x)
+// Initial guess by polynomial extrapolation in time: x = sum_j c_j T^(n-j), m = number of states used (0: zero guess, 1: T^n,
+// 2: 2 T^n - T^(n-1), 3: 3, -3, 1, ...: the unique polynomial of degree m-1 through the last m states, evaluated one step ahead).
+#define PB_MAXHIST 5
+struct GuessSpec { int m; const double *T[PB_MAXHIST]; double c[PB_MAXHIST]; };
+__global__ void k_guess(Grid g, GuessSpec gs, const unsigned char *__restrict__ m, unsigned char bit, double *__restrict__ x)
 {
-    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x)
-        x[l] = (warm && (m[l] & bit)) ? T[l] : 0.0;
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (gs.m && (m[l] & bit)) {
+#pragma unroll
+            for (int j = 0; j < PB_MAXHIST; ++j)
+                if (j < gs.m) v += gs.c[j] * gs.T[j][l];
+        }
+        x[l] = v;
+    }
 }
 
 // state write-back (solve_system!: removed DOFs are exactly 0; border rows hold their value)

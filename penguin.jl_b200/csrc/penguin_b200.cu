@@ -345,6 +345,10 @@ struct pb200_solver {
     unsigned char *m1 = nullptr, *m2 = nullptr;
     double *ufix1 = nullptr, *ufix2 = nullptr;
     double *Tw[2] = {}, *Tg[2] = {};
+    // older states T^(n-1), T^(n-2), ... for the extrapolated initial guess; the buffers rotate with Tw / Tg (no copies)
+    std::vector<double *> histW[2], histG[2];
+    int n_prev = 0;                      // how many of them are valid
+    double prev_dt = 0.0;
     int nf = 1;
     MVec x, b, r, r0, p, ph, v, s, sh, t, dinv;
     double *gK = nullptr;
@@ -429,6 +433,7 @@ extern "C" int pb200_solver_destroy(pb200_solver *s)
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->state_ready); cudaEventDestroy(s->copy_done); }
     dev_free(s->D1arr); dev_free(s->D2arr); dev_free(s->ufix1); dev_free(s->ufix2); dev_free(s->gK);
     for (int k = 0; k < 6; ++k) dev_free(s->bvals[k]);
+    for (int a = 0; a < 2; ++a) { for (double *p : s->histW[a]) cudaFree(p); for (double *p : s->histG[a]) cudaFree(p); }
     for (int a = 0; a < 2; ++a) { dev_free(s->Tw[a]); dev_free(s->Tg[a]); dev_free(s->gS[a]); for (int b = 0; b < 2; ++b) dev_free(s->fS[a][b]); }
     cudaFree(s->m1); cudaFree(s->m2);
     delete s;
@@ -479,6 +484,7 @@ extern "C" int pb200_solver_set_state(pb200_solver *s, const double *x)
         if ((rc = upload_owned(ctx, g, s->Tw[ph], x + (int64_t)(2 * ph) * g.nown))) return rc;
         if ((rc = upload_owned(ctx, g, s->Tg[ph], x + (int64_t)(2 * ph + 1) * g.nown))) return rc;
     }
+    s->n_prev = 0;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
 }
@@ -1122,6 +1128,24 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         if ((rc = stage_src(s, &s->gS[w], in->g_arr[w], in->g_const[w], &gsp[w]))) return rc;
 
     const int grid = sgrid(ctx, g.nown);
+    // initial guess: 0 none, 1 previous state, 2 linear extrapolation from the two previous states (needs one earlier step with the same dt)
+    int warm = (!unsteady || !o.warm_start) ? 0 : 1;
+    if (warm && o.warm_start >= 2 && in->dt == s->prev_dt) warm = 1 + (s->n_prev < o.warm_start - 1 ? s->n_prev : o.warm_start - 1);
+    if (warm > PB_MAXHIST) warm = PB_MAXHIST;
+    auto guess_spec = [&](double *cur, const std::vector<double *> &hist) {
+        GuessSpec gsx;
+        gsx.m = warm;
+        double binom = 1.0;   // c_j = (-1)^j C(m, j+1)
+        for (int j = 0; j < PB_MAXHIST; ++j) {
+            gsx.T[j] = nullptr; gsx.c[j] = 0.0;
+            if (j < warm) {
+                binom = binom * (double)(warm - j) / (double)(j + 1);
+                gsx.c[j] = (j & 1) ? -binom : binom;
+                gsx.T[j] = j == 0 ? cur : hist[j - 1];
+            }
+        }
+        return gsx;
+    };
     // ghost planes of the state (stencil inputs of the explicit part)
     {
         double *fl[4] = {s->Tw[0], s->Tg[0], s->Tw[1], s->Tg[1]};
@@ -1135,18 +1159,18 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         DISPATCH_N(g.N, (k_rhs_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Tw[0], s->Tg[0], s->ufix1, s->gK, f[0][0],
                                                                                f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr)));
         LAUNCH_CHECK(ctx);
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m1, MB_FREE, s->Tw[0], s->x.f[0]);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]);
         LAUNCH_CHECK(ctx);
-        if (s->nf == 2) { k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m1, MB_IFREE, s->Tg[0], s->x.f[1]); LAUNCH_CHECK(ctx); }
+        if (s->nf == 2) { k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[0], s->histG[0]), s->m1, MB_IFREE, s->x.f[1]); LAUNCH_CHECK(ctx); }
     } else {
         if (gsp[0].arr) { double *fl[1] = {s->gS[0]}; if ((rc = halo_exchange(ctx, g, fl, 1))) return rc; }
         DISPATCH_N(g.N, (k_rhs_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
                                                                                s->Tg[1], s->ufix1, s->ufix2, f[0][0], f[0][1], f[1][0], f[1][1], gsp[0],
                                                                                gsp[1], s->b.f[0], s->b.f[1], s->b.f[2])));
         LAUNCH_CHECK(ctx);
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m1, MB_FREE, s->Tw[0], s->x.f[0]); LAUNCH_CHECK(ctx);
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m2, MB_FREE, s->Tw[1], s->x.f[1]); LAUNCH_CHECK(ctx);
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, o.warm_start && unsteady, s->m2, MB_IFREE, s->Tg[1], s->x.f[2]); LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]); LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[1], s->histW[1]), s->m2, MB_FREE, s->x.f[1]); LAUNCH_CHECK(ctx);
+        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[1], s->histG[1]), s->m2, MB_IFREE, s->x.f[2]); LAUNCH_CHECK(ctx);
     }
     if (use_fold) {
         // folded system (cached per coefficient set and mask set)
@@ -1243,6 +1267,26 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     }   // generic path
     // ---- write the new state ----------------------------------------------------------------------------------------------
     if (s->copy_pending) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, s->copy_done, 0));   // pb200_solver_get_state_async still reads the old one
+    if (unsteady && o.warm_start >= 2) {
+        // keep the last states for the next step's extrapolated guess: the new state is written into the oldest buffer (rotation, no copy)
+        const int np = diph ? 2 : 1;
+        int keep = o.warm_start - 1;
+        if (keep > PB_MAXHIST - 1) keep = PB_MAXHIST - 1;
+        for (int ph = 0; ph < np; ++ph) {
+            std::vector<double *> *hs[2] = {&s->histW[ph], &s->histG[ph]};
+            double **cur[2] = {&s->Tw[ph], &s->Tg[ph]};
+            for (int q = 0; q < 2; ++q) {
+                std::vector<double *> &h = *hs[q];
+                double *fresh = nullptr;
+                if ((int)h.size() < keep) { if ((rc = dev_alloc(ctx, &fresh, g.nloc))) return rc; }
+                else { fresh = h.back(); h.pop_back(); }
+                h.insert(h.begin(), *cur[q]);     // T^n becomes T^(n-1)
+                *cur[q] = fresh;                  // receives T^(n+1)
+            }
+        }
+        s->n_prev = s->prev_dt == in->dt ? (s->n_prev < keep ? s->n_prev + 1 : keep) : 1;
+        s->prev_dt = in->dt;
+    } else s->n_prev = 0;
     k_store_bulk<<<grid, RED_THREADS, 0, ctx->stream>>>(g, z.f[0], s->ufix1, s->Tw[0]); LAUNCH_CHECK(ctx);
     if (!diph) {
         const double *src = s->nf == 2 ? z.f[1] : s->gK;

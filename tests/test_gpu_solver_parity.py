@@ -274,3 +274,31 @@ def test_async_state_download(pb):
     L.check(lib.pb200_solver_wait_state(sg._h), sg._ctx.h)
     assert np.array_equal(buf, ref)
     assert not np.array_equal(sg.x, ref)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_extrapolated_initial_guess_keeps_parity(pb, order):
+    # warm_start = m: initial guess by polynomial extrapolation through the last m states (buffers rotate on the device);
+    # the converged states must still match the oracle step by step, for the diphasic CN loop and with time-dependent data
+    nx = 28
+    mo, mg = _meshes(pb, (nx, nx), (8.0, 8.0))
+    f = lambda x, y, z, t: 0.3 * np.cos(x) * (1 + 5 * t)
+    ls = geom.LevelSet.ball((4.02, 3.97), 2.0)
+    p1o, p1g = _phases(pb, mo, mg, ls, f, 1.0)
+    p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, 2.0)
+    n = mo.n
+    u0 = np.concatenate([np.ones(n), np.ones(n), np.zeros(n), np.zeros(n)])
+    dt = 0.5 * (8.0 / nx) ** 2
+    Tend = 8.5 * dt
+    ico = po.InterfaceConditions(po.ScalarJump(1.0, 0.5, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+    icg = pb.InterfaceConditions(pb.ScalarJump(1.0, 0.5, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+    so = po.DiffusionUnsteadyDiph(p1o, p2o, po.BorderConditions(), ico, dt, u0, "BE")
+    po.solve_DiffusionUnsteadyDiph(so, p1o, p2o, dt, Tend, po.BorderConditions(), ico, "CN")
+    sg = pb.DiffusionUnsteadyDiph(p1g, p2g, pb.BorderConditions(), icg, dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, Tend, pb.BorderConditions(), icg, "CN", reltol=1e-13, warm_start=order)
+    assert len(sg.states) == len(so.states) == 10
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
+    # later steps start closer to the solution than the first ones
+    its = [c["iters"] for c in sg.ch]
+    assert min(its[4:]) <= its[1]
