@@ -36,7 +36,7 @@ __global__ void k_gamma_known(Grid g, StepCoef sc, const unsigned char *__restri
 template <int N>
 __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m, const double *__restrict__ Tw,
                            const double *__restrict__ Tg, const double *__restrict__ ufix, const double *__restrict__ gK, SrcSpec f0, SrcSpec f1,
-                           SrcSpec g0, SrcSpec g1, double *__restrict__ bb, double *__restrict__ bi)
+                           SrcSpec g0, SrcSpec g1, double *__restrict__ bb, double *__restrict__ bi, int skip_known)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
         int c[PB_MAXD];
@@ -48,7 +48,8 @@ __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const 
         const double D = D_at(p, l), V = p.V[l], Gm = p.Gam[l];
         double Rbk = 0.0, Rik = 0.0, Rbe = 0.0, Rie = 0.0;
         GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
-        if (wi || (mb & MB_KNBR)) phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);   // zero for every other row: nothing known is within reach
+        // zero for every other row: nothing known is within reach; skip_known: k_rhs_known_mono adds it for the listed rows afterwards
+        if (!skip_known && (wi || (mb & MB_KNBR))) phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
         if (sc.cn) {
             GamSpec ge = {Tg, 1.0, nullptr, 0.0, 0.0};
             phase_rows<N>(p, g, l, c, Tw, ge, Rbe, Rie);
@@ -78,7 +79,7 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
                            const unsigned char *__restrict__ m2, const double *__restrict__ Tw1, const double *__restrict__ Tg1,
                            const double *__restrict__ Tw2, const double *__restrict__ Tg2, const double *__restrict__ ufix1,
                            const double *__restrict__ ufix2, SrcSpec f10, SrcSpec f11, SrcSpec f20, SrcSpec f21, SrcSpec gj, SrcSpec hj,
-                           double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw)
+                           double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw, int skip_known)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
         int c[PB_MAXD];
@@ -91,8 +92,10 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
         GamSpec gk2 = {nullptr, 0.0, nullptr, 0.0, 0.0};
         double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0, Rbe1 = 0, Rie1 = 0, Rbe2 = 0, Rie2 = 0;
         // the known part is zero unless something known is within the row's reach (MB_KNBR) -- or the row is an interface row
-        if ((w1 && (a & MB_KNBR)) || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
-        if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
+        if (!skip_known) {
+            if ((w1 && (a & MB_KNBR)) || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
+            if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
+        }
         if (sc.cn) {
             GamSpec ge1 = {Tg1, 1.0, nullptr, 0.0, 0.0}, ge2 = {Tg2, 1.0, nullptr, 0.0, 0.0};
             if (w1) phase_rows<N>(p1, g, l, c, Tw1, ge1, Rbe1, Rie1);
@@ -110,6 +113,57 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
 }
 
 // initial guess: previous state restricted to the free sets (warm) or zero
+// The "known part" of the right-hand side (couplings of a row to eliminated values) for the compact, sorted list of rows that have
+// one (MB_KNBR rows and interface rows): subtracts it from the b written by k_rhs_* with skip_known = 1.  One thread per listed cell --
+// the heavy unfolded stencil evaluations run side by side instead of stalling the warps of the streaming kernel.
+template <int N>
+__global__ void k_rhs_known_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m, const long long *__restrict__ list, int n,
+                                 const double *__restrict__ ufix, const double *__restrict__ gK, double *__restrict__ bb, double *__restrict__ bi)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int64_t l = list[i];
+        int c[PB_MAXD];
+        cell_coords(g, l - g.plane, c);
+        const unsigned char mb = m[l];
+        const bool wb = mb & MB_FREE, wi = bi && (mb & MB_IFREE);
+        if (!wb && !wi) continue;
+        double Rbk, Rik;
+        GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
+        phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
+        if (wb) { double v = sc.c * D_at(p, l) * Rbk; if (sc.sym) v /= D_at(p, l); bb[l] -= v; }
+        if (wi) { double v = sc.c2 * sp.beta * Rik; if (sc.sym) v *= sc.c / (sc.c2 * sp.beta); bi[l] -= v; }
+    }
+}
+template <int N>
+__global__ void k_rhs_known_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m1, const unsigned char *__restrict__ m2,
+                                 const long long *__restrict__ list, int n, const double *__restrict__ ufix1, const double *__restrict__ ufix2, SrcSpec gj,
+                                 double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int64_t l = list[i];
+        int c[PB_MAXD];
+        cell_coords(g, l - g.plane, c);
+        const unsigned char a = m1[l], b = m2[l];
+        const bool w1 = a & MB_FREE, w2 = b & MB_FREE, ww = b & MB_IFREE;
+        GamSpec gk1 = {gj.arr, 1.0 / sp.a1, nullptr, 0.0, gj.arr ? 0.0 : gj.cst / sp.a1};
+        GamSpec gk2 = {nullptr, 0.0, nullptr, 0.0, 0.0};
+        double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0;
+        if ((w1 && (a & MB_KNBR)) || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
+        if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
+        if (w1) b1[l] -= sc.c * D_at(p1, l) * Rbk1;
+        if (w2) b2[l] -= sc.c * D_at(p2, l) * Rbk2;
+        if (ww) bw[l] -= sp.b1 * Rik1 + sp.b2 * Rik2;
+    }
+}
+// rows that need the known part: MB_KNBR bulk rows and every interface row
+__global__ void k_mark_known_rows(Grid g, const unsigned char *__restrict__ m1, const unsigned char *__restrict__ m2, long long *list, int *count, int cap)
+{
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char a = m1[l], b = m2 ? m2[l] : 0;
+        if ((a | b) & (MB_KNBR | MB_IFREE)) { const int k = atomicAdd(count, 1); if (k < cap) list[k] = l; }
+    }
+}
+
 // Initial guess by polynomial extrapolation in time: x = sum_j c_j T^(n-j), m = number of states used (0: zero guess, 1: T^n,
 // 2: 2 T^n - T^(n-1), 3: 3, -3, 1, ...: the unique polynomial of degree m-1 through the last m states, evaluated one step ahead).
 #define PB_MAXHIST 5

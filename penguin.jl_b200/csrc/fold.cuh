@@ -569,11 +569,14 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
 // One WARP per band / fringe cell e: lanes 0..3(1+2N)-1 gather the 3 unknowns of the cell and of its 2N neighbours, every lane
 // multiplies its share of the (1+2N) 3x3 coefficient blocks (contiguous in memory: coalesced) and three shuffle reductions give the rows.
 // BAND_ONLY restricts the columns to band cells (the principal submatrix M^_BB) and adds the identity diagonal.
+// LPC lanes work on one cell: 16 in 1-D / 2-D (3 (1 + 2N) <= 15 gathered values), 32 in 3-D -- two cells per warp halve the number of
+// warps, so that the whole band is in flight in one wave.
+template <int N> struct BandLanes { static constexpr int LPC = (3 * (1 + 2 * N) <= 16) ? 16 : 32; };
 template <int N, bool BAND_ONLY>
 __device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int e, const FVec &x, int lane, double &a0, double &a1, double &a2, double &x0,
                                           double &x1, double &xw, long long &l, int &bo)
 {
-    constexpr int NB = 1 + 2 * N, NC = NB * 9, NX = NB * 3;
+    constexpr int NB = 1 + 2 * N, NC = NB * 9, NX = NB * 3, LPC = BandLanes<N>::LPC;
     l = fd.Ecell[e];
     bo = fd.EB[e];
     double xv = 0.0;
@@ -595,22 +598,22 @@ __device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int 
             else if (nb >= 0) xv = x.f[2][nb];
         }
     }
-    x0 = __shfl_sync(0xffffffffu, xv, 0); x1 = __shfl_sync(0xffffffffu, xv, 1); xw = __shfl_sync(0xffffffffu, xv, 2);
+    x0 = __shfl_sync(0xffffffffu, xv, 0, LPC); x1 = __shfl_sync(0xffffffffu, xv, 1, LPC); xw = __shfl_sync(0xffffffffu, xv, 2, LPC);
     const double *__restrict__ blk = fd.Eblk + (size_t)e * NC;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < (NC + 31) / 32; ++jj) {
-        const int j = jj * 32 + lane;
+    for (int jj = 0; jj < (NC + LPC - 1) / LPC; ++jj) {
+        const int j = jj * LPC + lane;
         const bool in = j < NC;
         const int jc = in ? j : 0;
         const int k = jc / 9, rem = jc - 9 * k, r = rem / 3, c = rem - 3 * r;
-        const double xx = __shfl_sync(0xffffffffu, xv, k * 3 + c);
+        const double xx = __shfl_sync(0xffffffffu, xv, k * 3 + c, LPC);
         const double pr = in ? blk[jc] * xx : 0.0;
         r0 += r == 0 ? pr : 0.0; r1 += r == 1 ? pr : 0.0; r2 += r == 2 ? pr : 0.0;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        r0 += __shfl_xor_sync(0xffffffffu, r0, o); r1 += __shfl_xor_sync(0xffffffffu, r1, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    for (int o = LPC / 2; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o, LPC); r1 += __shfl_xor_sync(0xffffffffu, r1, o, LPC); r2 += __shfl_xor_sync(0xffffffffu, r2, o, LPC);
     }
     a0 = r0; a1 = r1; a2 = r2;
     if (BAND_ONLY) { a0 += x0; a1 += x1; a2 += xw; }
@@ -623,13 +626,19 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    constexpr int LPC = BandLanes<N>::LPC;
+    const int lane = threadIdx.x & (LPC - 1), gpb = blockDim.x / LPC;   // groups of LPC lanes per block
     const bool two = fd.nbulk > 1;
-    for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < fd.nE; e += gridDim.x * wpb) {
+    // every group runs the same number of rounds (the shuffles inside band_rows are warp-wide); out-of-range groups redo the last cell
+    const int rounds = (fd.nE + gridDim.x * gpb - 1) / (gridDim.x * gpb);
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int e_raw = (rd * gridDim.x + blockIdx.x) * gpb + (int)threadIdx.x / LPC;
+        const bool live = e_raw < fd.nE;
+        const int e = live ? e_raw : fd.nE - 1;
         double a0, a1, a2, x0, x1, xw;
         long long l; int bo;
         band_rows<N, false>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
-        if (lane == 0) {
+        if (lane == 0 && live) {
             const double y0p = y.f[0][l], y1p = two ? y.f[1][l] : 0.0;
             y.f[0][l] = y0p + a0;
             if (two) y.f[1][l] = y1p + a1;
@@ -658,13 +667,17 @@ __global__ void __launch_bounds__(256) kf_band_poly(Grid g, FoldDev fd, FVec x, 
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[1] = {0.0};
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < fd.nE; e += gridDim.x * wpb) {
-        if (fd.EB[e] < 0) continue;   // warp-uniform
+    constexpr int LPC = BandLanes<N>::LPC;
+    const int lane = threadIdx.x & (LPC - 1), gpb = blockDim.x / LPC;
+    const int rounds = (fd.nE + gridDim.x * gpb - 1) / (gridDim.x * gpb);
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int e_raw = (rd * gridDim.x + blockIdx.x) * gpb + (int)threadIdx.x / LPC;
+        const bool live = e_raw < fd.nE;
+        const int e = live ? e_raw : fd.nE - 1;
         double a0, a1, a2, x0, x1, xw;
         long long l; int bo;
-        band_rows<N, true>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
-        if (lane == 0) {
+        band_rows<N, true>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);   // fringe cells (bo < 0) are computed and dropped
+        if (lane == 0 && live && bo >= 0) {
             const double o0 = ca * x0 + cb * a0, o1 = ca * x1 + cb * a1, o2 = ca * xw + cb * a2;
             out[(size_t)0 * fd.nB + bo] = o0;
             out[(size_t)1 * fd.nB + bo] = o1;

@@ -358,6 +358,8 @@ struct pb200_solver {
     std::vector<double *> owned;
     FoldSys F;
     BandHalo bh;
+    long long *Kcell = nullptr;   // sorted list of the rows whose right-hand side has a known part (built with the masks)
+    int nK = 0;
     cudaStream_t copy_stream = nullptr;      // pb200_solver_get_state_async
     cudaEvent_t state_ready = nullptr, copy_done = nullptr;
     bool copy_pending = false;
@@ -430,6 +432,7 @@ extern "C" int pb200_solver_destroy(pb200_solver *s)
     cudaStreamSynchronize(s->ctx->stream);
     for (double *p : s->owned) cudaFree(p);
     fold_free(s->F);
+    if (s->Kcell) cudaFree(s->Kcell);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->state_ready); cudaEventDestroy(s->copy_done); }
     dev_free(s->D1arr); dev_free(s->D2arr); dev_free(s->ufix1); dev_free(s->ufix2); dev_free(s->gK);
     for (int k = 0; k < 6; ++k) dev_free(s->bvals[k]);
@@ -823,8 +826,9 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 
 static inline int fold_grid(pb200_solver *s) { int b = s->F.nitems; int cap = s->ctx->sm_count * 8; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
 static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
-// kernels that put one warp on one band cell (8 warps per block, every cell in flight at once)
-static inline int band_wgrid(int n) { int b = (n + 7) / 8; if (b > 2048) b = 2048; if (b < 1) b = 1; return b; }   // 8 warps per block
+// kernels that put one warp on one band cell: 1024-thread blocks, so that every cell is in flight at once while the number of
+// blocks (= serialised ticket atomics and partial sums of the fused reduction) stays small
+static inline int band_wgrid(int n) { int b = (n + 15) / 16; if (b > 2048) b = 2048; if (b < 1) b = 1; return b; }   // >= 8 cells per 256-thread block
 
 // ghost planes of the bulk fields and ghost entries of the compact w of one Krylov vector, ONE NCCL group (one launch)
 static int fold_halo(pb200_solver *s, const FVec &x)
@@ -1059,6 +1063,13 @@ static int build_masks(pb200_solver *s)
     if ((rc = fetch_results(ctx, SL_TMP, 2, cnt))) return rc;
     s->dof_bulk = (int64_t)(cnt[0] + 0.5);
     s->dof_ifc = (int64_t)(cnt[1] + 0.5);
+    {
+        if (s->Kcell) { cudaFree(s->Kcell); s->Kcell = nullptr; }
+        const unsigned char *ma = s->m1, *mb = s->sp.phase_type == PB200_DIPH ? s->m2 : nullptr;
+        Grid gg = g;
+        cudaStream_t st = ctx->stream;
+        if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { k_mark_known_rows<<<grid, RED_THREADS, 0, st>>>(gg, ma, mb, list, cnt, cap); }, &s->Kcell, &s->nK))) return rc;
+    }
     s->masks_dirty = false;
     s->diag_key.cV = -1;
     s->F.built = false;
@@ -1157,8 +1168,13 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         double *fl[1] = {s->gK};
         if ((rc = halo_exchange(ctx, g, fl, 1))) return rc;
         DISPATCH_N(g.N, (k_rhs_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Tw[0], s->Tg[0], s->ufix1, s->gK, f[0][0],
-                                                                               f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr)));
+                                                                               f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr, 1)));
         LAUNCH_CHECK(ctx);
+        if (s->nK > 0) {
+            DISPATCH_N(g.N, (k_rhs_known_mono<N><<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Kcell, s->nK, s->ufix1, s->gK, s->b.f[0],
+                                                                                              s->nf == 2 ? s->b.f[1] : nullptr)));
+            LAUNCH_CHECK(ctx);
+        }
         k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]);
         LAUNCH_CHECK(ctx);
         if (s->nf == 2) { k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[0], s->histG[0]), s->m1, MB_IFREE, s->x.f[1]); LAUNCH_CHECK(ctx); }
@@ -1166,8 +1182,13 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         if (gsp[0].arr) { double *fl[1] = {s->gS[0]}; if ((rc = halo_exchange(ctx, g, fl, 1))) return rc; }
         DISPATCH_N(g.N, (k_rhs_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
                                                                                s->Tg[1], s->ufix1, s->ufix2, f[0][0], f[0][1], f[1][0], f[1][1], gsp[0],
-                                                                               gsp[1], s->b.f[0], s->b.f[1], s->b.f[2])));
+                                                                               gsp[1], s->b.f[0], s->b.f[1], s->b.f[2], 1)));
         LAUNCH_CHECK(ctx);
+        if (s->nK > 0) {
+            DISPATCH_N(g.N, (k_rhs_known_diph<N><<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Kcell, s->nK, s->ufix1, s->ufix2,
+                                                                                              gsp[0], s->b.f[0], s->b.f[1], s->b.f[2])));
+            LAUNCH_CHECK(ctx);
+        }
         k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]); LAUNCH_CHECK(ctx);
         k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[1], s->histW[1]), s->m2, MB_FREE, s->x.f[1]); LAUNCH_CHECK(ctx);
         k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[1], s->histG[1]), s->m2, MB_IFREE, s->x.f[2]); LAUNCH_CHECK(ctx);
