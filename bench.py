@@ -282,8 +282,9 @@ def run_gpu(args):
     L.check(lib.pb200_solver_wait_state(s._h), ctx.h)
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
+    state_absmax = allmax(float(np.max(np.abs(x_bufs[(e2e_steps - 1) & 1]))))   # the reference prints max|x| every step (diffusion.jl:448)
     e2e = {"value": dof * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(allsum(2 * 8 * nloc)),
-           "d2h_bytes_per_step": int(allsum(4 * 8 * nloc)), "steps": e2e_steps, "timing": "host wall clock between device syncs, max over ranks; per step: H2D of the jump data g, h from pinned memory, "
+           "d2h_bytes_per_step": int(allsum(4 * 8 * nloc)), "steps": e2e_steps, "max_abs_state": state_absmax, "timing": "host wall clock between device syncs, max over ranks; per step: H2D of the jump data g, h from pinned memory, "
                      "the solve, D2H of the full state [T_w1; T_g1; T_w2; T_g2] into pinned memory (double-buffered: it overlaps the next step)"}
 
     # ---- roofline of the dominant kernel (the operator apply inside the Krylov loop) ---------------------------------------------

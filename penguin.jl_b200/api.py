@@ -12,6 +12,7 @@ reference evaluates them (src/solver.jl:230-323).
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 
@@ -86,6 +87,16 @@ def init_distributed(rank, nranks, device, bcast):
 
 def context():
     return _ctx if _ctx is not None else init()
+
+
+@atexit.register
+def _finalize_at_exit():
+    # handles that are still alive when the interpreter shuts down must not call into a CUDA runtime that is being torn down:
+    # finalising here (before module teardown) makes their __del__ a no-op
+    try:
+        finalize()
+    except Exception:
+        pass
 
 
 def finalize():

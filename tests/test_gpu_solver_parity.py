@@ -302,3 +302,26 @@ def test_extrapolated_initial_guess_keeps_parity(pb, order):
     # later steps start closer to the solution than the first ones
     its = [c["iters"] for c in sg.ch]
     assert min(its[4:]) <= its[1]
+
+
+def test_unsteady_diph_3d(pb, kw):
+    # examples/3D/Diffusion/Heat_2ph.jl:13-30 at 12^3: sphere interface, ScalarJump(1, 2, 0), FluxJump(1, 1, 0), empty borders, BE
+    nx = 12
+    mo, mg = _meshes(pb, (nx, nx, nx), (4.0, 4.0, 4.0))
+    f = lambda x, y, z, t: 0.0 * x
+    ls = geom.LevelSet.ball((2.0, 2.0, 2.0), 1.0)
+    p1o, p1g = _phases(pb, mo, mg, ls, f, 1.0)
+    p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, 1.0)
+    n = mo.n
+    u0 = np.concatenate([np.ones(2 * n), np.zeros(2 * n)])
+    dt = 0.5 * (4.0 / nx) ** 2
+    Tend = 3.5 * dt
+    ico = po.InterfaceConditions(po.ScalarJump(1.0, 2.0, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+    icg = pb.InterfaceConditions(pb.ScalarJump(1.0, 2.0, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+    so = po.DiffusionUnsteadyDiph(p1o, p2o, po.BorderConditions(), ico, dt, u0, "BE")
+    po.solve_DiffusionUnsteadyDiph(so, p1o, p2o, dt, Tend, po.BorderConditions(), ico, "BE")
+    sg = pb.DiffusionUnsteadyDiph(p1g, p2g, pb.BorderConditions(), icg, dt, u0, "BE")
+    pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, Tend, pb.BorderConditions(), icg, "BE", **kw)
+    assert len(sg.states) == len(so.states) == 5
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
