@@ -427,7 +427,8 @@ __global__ void kf_tile_list(int nbulk, long long ntile, const int *__restrict__
 // cells (every tile of full cells away from the interface and the border) is applied without reading the coefficient arrays.
 // Also counts the cells of uniform / general tiles (results[0], results[1]) for the roofline accounting.
 template <int N>
-__global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I, unsigned char *uni, double *ucoef, double *partials, double *results, unsigned *counter)
+__global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I, unsigned char *uni, double *ucoef, double utol, double *partials, double *results,
+                                                    unsigned *counter)
 {
     __shared__ double smn[PB_MAXD][FCH / 32], smx[PB_MAXD][FCH / 32];
     __shared__ int s_uni;
@@ -464,8 +465,11 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
             for (int d = 0; d < N; ++d) {
                 double a = 1e300, b = -1e300;
                 for (int w = 0; w < FCH / 32; ++w) { a = fmin(a, smn[d][w]); b = fmax(b, smx[d][w]); }
-                u = u && (a == b);
-                ucoef[(size_t)it * PB_MAXD + d] = a;
+                // equal up to round-off of the geometry: on grids whose spacing is not a power of two the capacities of full cells carry the
+                // cancellation error of h_j = x_{j+1} - x_j (~1e-14 relative), and so do the folded coefficients.  Tiles whose coefficients
+                // agree to 1e-12 relative use the mid value -- three orders below the 1e-9 parity bar; utol = 0 demands bitwise equality.
+                u = u && (b - a <= utol * fmax(fabs(a), fabs(b)));
+                ucoef[(size_t)it * PB_MAXD + d] = 0.5 * (a + b);
             }
             uni[it] = (unsigned char)((u ? 1 : 0) | (anyb ? 2 : 0));   // bit 0: constant coefficients, bit 1: holds band cells
             s_uni = u ? 1 : 0;

@@ -809,7 +809,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         CUDA_TRY(ctx, cudaMalloc((void **)&F.ucoef, sizeof(double) * PB_MAXD * ni));
         I.uni = F.uni; I.ucoef = F.ucoef;
         int gm = F.nitems; if (gm > ctx->sm_count * 8) gm = ctx->sm_count * 8; if (gm < 1) gm = 1;
-        DISPATCH_N(g.N, (kf_tile_meta<N><<<gm, FCH, 0, ctx->stream>>>(g, d, I, F.uni, F.ucoef, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
+        DISPATCH_N(g.N, (kf_tile_meta<N><<<gm, FCH, 0, ctx->stream>>>(g, d, I, F.uni, F.ucoef, getenv("PB200_EXACT_TILES") ? 0.0 : 1e-12, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
         LAUNCH_CHECK(ctx);
         double cnt[2];
         if ((rc = fetch_results(ctx, SL_TMP, 2, cnt))) return rc;
