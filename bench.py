@@ -216,7 +216,7 @@ def run_gpu(args):
     # workload untimed for ~0.75 s, then RESET the state to the initial condition so that the W warm-up steps and the K timed steps are
     # steps 1..W and W+1..W+K of the run, exactly as without spin-up (later steps of the transient need fewer Krylov iterations).
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < args.spinup:
+    while allmax(time.perf_counter() - t_spin) < args.spinup:     # a COLLECTIVE decision: every rank runs the same number of steps
         step()
     ctx.sync()
     L.check(lib.pb200_solver_set_state(s._h, u0.ctypes.data_as(L.dp)), ctx.h)
