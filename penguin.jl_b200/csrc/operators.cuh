@@ -103,6 +103,7 @@ __device__ __forceinline__ void phase_diag(const PhaseDev &ph, const Grid &g, in
 
 struct BorderDev {
     int kind[6];
+    int present[6];           // the key exists in BorderConditions (whatever its type): the Periodic rows look at that (src/solver.jl:458)
     double value[6];
     const double *values[6];  // device arrays (one entry per real cell of the side) or nullptr
 };
@@ -135,6 +136,33 @@ __device__ __forceinline__ int64_t side_index(const Grid &g, int key, const int 
     return idx;
 }
 
+// Is the bulk row of the real cell c replaced by a row that pins its value, and to what?  (apply_boundary_condition_fast!, src/solver.jl:450-499)
+//   Dirichlet: x = value.   Periodic (only if the opposite key is present): x_row - x_partner = 0 with the partner found by
+//   find_corresponding_cell_optimized (src/solver.jl:506-530): for a LOW side it is the PAD cell of the opposite end, which the zero-row
+//   trimming removes => x_row = 0; for a HIGH side it is the first real cell of that dimension, itself a border cell: pinned => same value.
+//   returns 0 not pinned, 1 pinned (val), -1 periodic row whose partner is a free unknown (a genuine coupling row: not supported)
+__device__ __forceinline__ int border_pinned(const Grid &g, const BorderDev &bd, const int c[PB_MAXD], double &val, int depth = 0)
+{
+    val = 0.0;
+    const int key = border_key(g, c);
+    if (key < 0) return 0;
+    const int kind = bd.kind[key];
+    if (kind == PB200_BC_DIRICHLET) { val = bd.values[key] ? bd.values[key][side_index(g, key, c)] : bd.value[key]; return 1; }
+    if (kind == PB200_BC_PERIODIC) {
+        const int opp = key ^ 1;   // LEFT<->RIGHT, BOTTOM<->TOP, BACKWARD<->FORWARD
+        if (!bd.present[opp]) return 0;
+        const bool hi = key & 1;
+        if (!hi) return 1;         // partner = pad cell, removed => 0
+        if (depth > 0) return -1;
+        const int dim = (key == PB200_LEFT || key == PB200_RIGHT) ? 1 : (key == PB200_BOTTOM || key == PB200_TOP) ? 0 : 2;
+        int cp[PB_MAXD] = {c[0], c[1], c[2]};
+        cp[dim] = 0;
+        const int r = border_pinned(g, bd, cp, val, 1);
+        return r == 1 ? 1 : -1;
+    }
+    return 0;
+}
+
 struct SysParams {
     int phase_type, time_type, ifc_kind;
     double alpha, beta;            // mono
@@ -162,8 +190,8 @@ __device__ __forceinline__ bool row_couples_to_known(const PhaseDev &ph, const G
             bool real = true;
             for (int e = 0; e < N; ++e) real = real && (cn[e] < g.nc[e]);
             if (!real) continue;
-            const int key = border_key(g, cn);
-            k = k || (key >= 0 && bd.kind[key] == PB200_BC_DIRICHLET);
+            double vv;
+            k = k || (border_pinned(g, bd, cn, vv) == 1);
         }
     }
     return k;
@@ -173,7 +201,7 @@ __device__ __forceinline__ bool row_couples_to_known(const PhaseDev &ph, const G
 template <int N>
 __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__restrict__ ct1, const double *__restrict__ ct2, SysParams sp,
                               BorderDev bd, unsigned char *__restrict__ m1, unsigned char *__restrict__ m2, double *__restrict__ ufix1,
-                              double *__restrict__ ufix2)
+                              double *__restrict__ ufix2, int *__restrict__ err)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
         int c[PB_MAXD];
@@ -181,10 +209,10 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
         const int64_t l = t + g.plane;
         bool real = true;
         for (int d = 0; d < N; ++d) real = real && (c[d] < g.nc[d]);
-        int key = real ? border_key(g, c) : -1;
-        bool dirichlet = key >= 0 && bd.kind[key] == PB200_BC_DIRICHLET;
         double bval = 0.0;
-        if (dirichlet) bval = bd.values[key] ? bd.values[key][side_index(g, key, c)] : bd.value[key];
+        const int pin = real ? border_pinned(g, bd, c, bval) : 0;
+        if (pin < 0) *err = 1;
+        const bool dirichlet = pin == 1;   // the row pins the value (Dirichlet, or a Periodic row that resolves to a known value)
         const bool unsteady = sp.time_type == PB200_UNSTEADY;
         double GG, HH;
         bool rowG, hrow1, hrow2 = false;

@@ -407,7 +407,7 @@ extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, p
     }
     s->p1 = phase_dev(d->ops1, s->D1arr, d->D1);
     if (d->ops2) s->p2 = phase_dev(d->ops2, s->D2arr, d->D2); else s->p2 = s->p1;
-    for (int k = 0; k < 6; ++k) { s->bd.kind[k] = PB200_BC_NONE; s->bd.value[k] = 0.0; s->bd.values[k] = nullptr; }
+    for (int k = 0; k < 6; ++k) { s->bd.kind[k] = PB200_BC_NONE; s->bd.present[k] = 0; s->bd.value[k] = 0.0; s->bd.values[k] = nullptr; }
     const bool diph = d->phase_type == PB200_DIPH;
     s->nf = diph ? 3 : (s->sp.beta != 0.0 ? 2 : 1);
     CUDA_TRY(ctx, cudaMalloc((void **)&s->m1, (size_t)g.nloc));
@@ -457,11 +457,12 @@ extern "C" int pb200_solver_set_border(pb200_solver *s, int side, int kind, doub
     pb200_ctx *ctx = s->ctx;
     const int dim = (side == PB200_LEFT || side == PB200_RIGHT) ? 1 : (side == PB200_BOTTOM || side == PB200_TOP) ? 0 : 2;
     if (dim >= s->g.N) return PB200_OK;   // keys of absent dimensions never match a cell (src/solver.jl:379-409)
-    if (kind == PB200_BC_PERIODIC) return set_err(ctx, PB200_EUNSUPPORTED, "Periodic borders are not supported by libpenguin_b200 yet");
     if (kind == PB200_BC_NEUMANN && s->g.N == 1) return set_err(ctx, PB200_EUNSUPPORTED, "1-D Neumann border rows are not supported by libpenguin_b200 yet");
-    // Neumann (>= 2-D) and Robin borders are no-ops in the reference (src/solver.jl:471-498): record as NONE
-    if (kind != PB200_BC_DIRICHLET) kind = PB200_BC_NONE;
+    // Neumann (>= 2-D) and Robin borders are no-ops in the reference (src/solver.jl:471-498): record as NONE -- but the key is PRESENT,
+    // which is what a Periodic row on the opposite side tests (src/solver.jl:458)
+    if (kind != PB200_BC_DIRICHLET && kind != PB200_BC_PERIODIC) kind = PB200_BC_NONE;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    s->bd.present[side] = 1;
     s->bd.kind[side] = kind;
     s->bd.value[side] = value;
     if (values && kind == PB200_BC_DIRICHLET) {
@@ -1050,8 +1051,23 @@ static int build_masks(pb200_solver *s)
     const Grid &g = s->g;
     const int grid = sgrid(ctx, g.nown);
     const double *ct1 = s->o1->cap->ct, *ct2 = s->o2 ? s->o2->cap->ct : s->o1->cap->ct;
-    DISPATCH_N(g.N, (k_build_masks<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, ct1, ct2, s->sp, s->bd, s->m1, s->m2, s->ufix1, s->ufix2)));
+    // a HIGH-side Periodic row equals its LOW-side partner (same dimension): that partner must be pinned by a Dirichlet or Periodic row,
+    // otherwise the row couples two free unknowns (checked on the host so that every rank takes the same decision)
+    for (int lo = 0; lo < 6; lo += 2) {
+        const int hi = lo + 1;
+        if (s->bd.kind[hi] == PB200_BC_PERIODIC && s->bd.present[lo] && s->bd.kind[lo] != PB200_BC_DIRICHLET && s->bd.kind[lo] != PB200_BC_PERIODIC)
+            return set_err(ctx, PB200_EUNSUPPORTED, "a Periodic border row couples to a FREE unknown (the opposite side has neither a Dirichlet nor a Periodic row): "
+                                                    "such coupling rows are not supported; Periodic on both sides or Periodic + Dirichlet is");
+    }
+    int *d_err = nullptr, h_err = 0;
+    CUDA_TRY(ctx, cudaMalloc((void **)&d_err, sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+    DISPATCH_N(g.N, (k_build_masks<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, ct1, ct2, s->sp, s->bd, s->m1, s->m2, s->ufix1, s->ufix2, d_err)));
     LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_err);
+    (void)h_err;   // cannot trigger after the host check above (kept as a device-side assertion)
     double *fl[2] = {s->ufix1, s->ufix2};
     int rc;
     if ((rc = halo_exchange(ctx, g, fl, 2))) return rc;

@@ -325,3 +325,27 @@ def test_unsteady_diph_3d(pb, kw):
     assert len(sg.states) == len(so.states) == 5
     for a, b in zip(sg.states, so.states):
         assert rel_l2(a, b) < TOL
+
+
+@pytest.mark.parametrize("which", ["x", "y", "full"])
+def test_periodic_borders(pb, kw, which):
+    # test/solver_test.jl:78-171: Periodic rows (x_row - x_partner = 0; the low side's partner is the pad cell, which the trimming removes)
+    nx = 20
+    mo, mg = _meshes(pb, (nx, nx), (4.0, 4.0))
+    f = lambda x, y, z: 1.0 + 0 * x
+    pho, phg = _phases(pb, mo, mg, geom.LevelSet.ball((2.03, 1.98), 1.0, False), f, 1.0)
+    if which == "x":
+        bo = {"left": po.Periodic(), "right": po.Periodic(), "top": po.Dirichlet(0.0), "bottom": po.Dirichlet(0.0)}
+        bg = {"left": pb.Periodic(), "right": pb.Periodic(), "top": pb.Dirichlet(0.0), "bottom": pb.Dirichlet(0.0)}
+    elif which == "y":
+        bo = {"left": po.Dirichlet(0.25), "right": po.Dirichlet(0.25), "top": po.Periodic(), "bottom": po.Periodic()}
+        bg = {"left": pb.Dirichlet(0.25), "right": pb.Dirichlet(0.25), "top": pb.Periodic(), "bottom": pb.Periodic()}
+    else:
+        bo = {k: po.Periodic() for k in ("left", "right", "top", "bottom")}
+        bg = {k: pb.Periodic() for k in ("left", "right", "top", "bottom")}
+    so = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(pho, po.BorderConditions(bo), po.Dirichlet(1.0)))
+    sg = pb.solve_DiffusionSteadyMono_(pb.DiffusionSteadyMono(phg, pb.BorderConditions(bg), pb.Dirichlet(1.0)), **kw)
+    assert rel_l2(sg.x, so.x) < TOL
+    sol = sg.x[:mo.n].reshape(nx + 1, nx + 1)
+    if which == "x":       # the reference's own assertion (:41): opposite columns agree
+        assert np.allclose(sol[1:nx - 1, 0], sol[1:nx - 1, nx - 1], atol=1e-8)
