@@ -35,6 +35,9 @@ struct pb200_ctx {
     unsigned *d_counter = nullptr;
     double *h_results = nullptr;   // pinned mirror
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // peer-memory exchange (p2p.cuh): every rank's mailbox is mapped into every other rank with CUDA IPC; halos and the Krylov
+    // scalar reductions are then plain kernels that store into the peers' mailboxes over NVLink and spin on sequence flags
+    struct P2PState *p2p = nullptr;
     // optional per-launch timing of the operator apply (pb200_set_profiling)
     bool profile = false;
     std::vector<cudaEvent_t> pev;   // event pairs
@@ -197,6 +200,7 @@ struct NcclApi {
     int (*CommInitRank)(void **, int, pb_ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -204,7 +208,7 @@ struct NcclApi {
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
-static const int PB_NCCL_FLOAT64 = 8, PB_NCCL_SUM = 0, PB_NCCL_MAX = 2;
+static const int PB_NCCL_FLOAT64 = 8, PB_NCCL_SUM = 0, PB_NCCL_MAX = 2, PB_NCCL_UINT8_T = 1;
 
 static int nccl_load(pb200_ctx *ctx)
 {
@@ -222,6 +226,7 @@ static int nccl_load(pb200_ctx *ctx)
     PB_SYM(CommInitRank, "ncclCommInitRank")
     PB_SYM(CommDestroy, "ncclCommDestroy")
     PB_SYM(AllReduce, "ncclAllReduce")
+    PB_SYM(AllGather, "ncclAllGather")
     PB_SYM(Send, "ncclSend")
     PB_SYM(Recv, "ncclRecv")
     PB_SYM(GroupStart, "ncclGroupStart")
@@ -336,10 +341,14 @@ static inline int red_grid(pb200_ctx *ctx, int64_t n, int per_thread = 1)
     return (int)b;
 }
 
+static int p2p_allreduce(pb200_ctx *ctx, int slot, int K, bool *done);
 // sum the K results of slot over the ranks (in stream order)
 static int allreduce_results(pb200_ctx *ctx, int slot, int K)
 {
     if (ctx->nranks == 1) return PB200_OK;
+    bool done = false;
+    int rc = p2p_allreduce(ctx, slot, K, &done);
+    if (rc || done) return rc;
     NCCL_TRY(ctx, g_nccl.AllReduce(ctx->d_results + slot, ctx->d_results + slot, (size_t)K, PB_NCCL_FLOAT64, PB_NCCL_SUM, ctx->comm, ctx->stream));
     return PB200_OK;
 }

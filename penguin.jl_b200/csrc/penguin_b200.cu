@@ -5,6 +5,7 @@
 #include "krylov.cuh"
 #include "assemble.cuh"
 #include "geometry.cuh"
+#include "p2p.cuh"
 #include "fold.cuh"
 
 #define DISPATCH_N(N_, ...)                  \
@@ -87,6 +88,7 @@ extern "C" int pb200_finalize(pb200_ctx *c)
     if (!c) return PB200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    p2p_free(c);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_partials); cudaFree(c->d_results); cudaFree(c->d_counter); cudaFreeHost(c->h_results);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
@@ -734,6 +736,13 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         d.Linv = F.Linv;
         fold_band_ranges(ctx, g, hB, d.nBlo, d.nBown, &s->bh);
     }
+    {
+        const int nBhi = d.nB - d.nBlo - d.nBown;
+        int mb = d.nBlo > nBhi ? d.nBlo : nBhi;
+        if (s->bh.lo_sendn > mb) mb = s->bh.lo_sendn;
+        if (s->bh.hi_sendn > mb) mb = s->bh.hi_sendn;
+        if ((rc = p2p_setup(ctx, (size_t)d.nbulk * g.plane + mb))) return rc;   // collective (every rank builds its folded system here)
+    }
     const int gown = red_grid(ctx, g.nown);
     DISPATCH_N(g.N, (kf_diag<N><<<gown, RED_THREADS, 0, ctx->stream>>>(g, d)));
     LAUNCH_CHECK(ctx);
@@ -841,6 +850,32 @@ static int fold_halo(pb200_solver *s, const FVec &x)
     const int nB = F.d.nB, nBlo = F.d.nBlo, nBown = F.d.nBown, nBhi = nB - nBlo - nBown;
     const BandHalo &bh = s->bh;
     const size_t cnt = (size_t)g.plane;
+    if (ctx->p2p && ctx->p2p->on) {
+        // peer-memory path (p2p.cuh): one kernel stores the boundary data into the neighbours' mailboxes and unpacks what they stored here
+        P2PState *P = ctx->p2p;
+        HaloDirArgs lo, hi;
+        memset(&lo, 0, sizeof(lo)); memset(&hi, 0, sizeof(hi));
+        const bool band = F.d.has_w && nB > 0;
+        size_t total = 0;
+        if (ctx->rank > 0) {
+            lo.active = 1; lo.remote = P->peer[ctx->rank - 1]; lo.remote_dir = 1; lo.local_dir = 0;
+            for (int f = 0; f < F.d.nbulk; ++f) { lo.send[lo.nseg] = {x.f[f] + g.plane, nullptr, (int)cnt}; lo.recv[lo.nseg] = {nullptr, x.f[f], (int)cnt}; ++lo.nseg; total += cnt; }
+            if (band) { lo.send[lo.nseg] = {x.f[2] + bh.lo_send0, nullptr, bh.lo_sendn}; lo.recv[lo.nseg] = {nullptr, x.f[2], nBlo}; ++lo.nseg; }
+        }
+        if (ctx->rank < ctx->nranks - 1) {
+            hi.active = 1; hi.remote = P->peer[ctx->rank + 1]; hi.remote_dir = 0; hi.local_dir = 1;
+            for (int f = 0; f < F.d.nbulk; ++f) {
+                hi.send[hi.nseg] = {x.f[f] + (long long)(g.lz - 2) * g.plane, nullptr, (int)cnt};
+                hi.recv[hi.nseg] = {nullptr, x.f[f] + (long long)(g.lz - 1) * g.plane, (int)cnt};
+                ++hi.nseg; total += cnt;
+            }
+            if (band) { hi.send[hi.nseg] = {x.f[2] + bh.hi_send0, nullptr, bh.hi_sendn}; hi.recv[hi.nseg] = {nullptr, x.f[2] + nBlo + nBown, nBhi}; ++hi.nseg; }
+        }
+        int blocks = (int)(total / 8192); if (blocks < 1) blocks = 1; if (blocks > 64) blocks = 64;
+        k_p2p_halo<<<blocks, 512, 0, ctx->stream>>>(P->mbox, P->zone_doubles, lo, hi);
+        LAUNCH_CHECK(ctx);
+        return PB200_OK;
+    }
     NCCL_TRY(ctx, g_nccl.GroupStart());
     for (int f = 0; f < F.d.nbulk; ++f) {
         double *p = x.f[f];
@@ -989,7 +1024,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         // Chunks of iterations between two host looks at the residual: the first chunk is sized by the iteration count of the previous
         // solve (time steps resemble each other), later ones are short.  Single GPU, no per-launch profiling: a chunk is replayed as ONE
         // CUDA graph (captured once per chunk length and parameter set), which removes the per-launch CPU cost and most inter-kernel gaps.
-        const bool use_graph = (ctx->nranks == 1 || getenv("PB200_GRAPH_NCCL")) && !ctx->profile && !getenv("PB200_NO_GRAPH") && o.maxit >= 2;
+        // (with several ranks graphs need the peer-memory exchange: NCCL nodes inside a captured graph ran 8x slower)
+        const bool use_graph = (ctx->nranks == 1 || (ctx->p2p && ctx->p2p->on) || getenv("PB200_GRAPH_NCCL")) && !ctx->profile && !getenv("PB200_NO_GRAPH") && o.maxit >= 2;
         auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
         const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
         const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
@@ -1029,6 +1065,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
             queued += chunk;
             double all[16];
             if ((rc = fetch_results(ctx, 0, 16, all))) return rc;   // one look: rr, iteration count, ||b||^2
+            if ((rc = p2p_check(ctx))) return rc;
             bnorm = sqrt(all[FS_BB]);
             tol = fmax(o.rtol * bnorm, o.atol);
             rnorm = sqrt(all[FS_TRIPLE(cur) + 1]);
