@@ -38,6 +38,7 @@ struct pb200_ctx {
     // peer-memory exchange (p2p.cuh): every rank's mailbox is mapped into every other rank with CUDA IPC; halos and the Krylov
     // scalar reductions are then plain kernels that store into the peers' mailboxes over NVLink and spin on sequence flags
     struct P2PState *p2p = nullptr;
+    int p2p_gen = 0;   // bumped whenever the mailboxes are re-mapped (captured graphs that hold the old pointers are rebuilt)
     // optional per-launch timing of the operator apply (pb200_set_profiling)
     bool profile = false;
     std::vector<cudaEvent_t> pev;   // event pairs

@@ -173,9 +173,8 @@ static void p2p_free(pb200_ctx *ctx)
 static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
 {
     if (ctx->nranks == 1 || ctx->nranks > P2P_MAXR || getenv("PB200_NO_P2P")) return PB200_OK;
-    if (ctx->p2p && ctx->p2p->on && ctx->p2p->zone_doubles >= zone_doubles) return PB200_OK;
-    if (ctx->p2p && !ctx->p2p->on) return PB200_OK;   // tried before, not available
-    // the zone size must be the same everywhere: take the maximum
+    if (ctx->p2p && !ctx->p2p->on) return PB200_OK;   // tried before, not available (the same on every rank)
+    // the zone size must be the same everywhere and so must the decision to (re)build: take the maximum of the requests first
     double want = (double)zone_doubles;
     double *d_tmp = nullptr;
     CUDA_TRY(ctx, cudaMalloc((void **)&d_tmp, sizeof(double)));
@@ -183,8 +182,12 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     NCCL_TRY(ctx, g_nccl.AllReduce(d_tmp, d_tmp, 1, PB_NCCL_FLOAT64, PB_NCCL_MAX, ctx->comm, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&want, d_tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    zone_doubles = (size_t)want + 64;
+    if (ctx->p2p && ctx->p2p->on && (double)ctx->p2p->zone_doubles >= want) { cudaFree(d_tmp); return PB200_OK; }
+    // generous first allocation (>= 1 Mi doubles per zone, twice the request) so that later, larger problems rarely force a re-mapping
+    zone_doubles = (size_t)(2.0 * want) + 64;
+    if (zone_doubles < (1u << 20)) zone_doubles = 1u << 20;
     p2p_free(ctx);
+    ctx->p2p_gen++;
     P2PState *P = new P2PState();
     ctx->p2p = P;
     P->n = ctx->nranks; P->rank = ctx->rank; P->zone_doubles = zone_doubles;

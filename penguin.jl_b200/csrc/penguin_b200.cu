@@ -830,7 +830,15 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     F.key[0] = ac.cV; F.key[1] = ac.c; F.key[2] = ac.c2;
     F.built = true;
-    if (d.has_w && d.nE > 0 && !getenv("PB200_NO_BAND_PREC")) { if ((rc = fold_band_spectrum(s))) return rc; }
+    // the band preconditioner is a COLLECTIVE decision (its set-up and every iteration contain reductions over the ranks): it is used
+    // when ANY rank holds band cells, and ranks without band cells simply contribute zeros
+    if (d.has_w && !getenv("PB200_NO_BAND_PREC")) {
+        double ne = (double)d.nE;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_results + SL_TMP, &ne, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
+        if ((rc = fetch_results(ctx, SL_TMP, 1, &ne))) return rc;
+        if (ne > 0.5 && (rc = fold_band_spectrum(s))) return rc;
+    }
     return PB200_OK;
 }
 
@@ -921,7 +929,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
 #undef FOLD_DENSE
     LAUNCH_CHECK(ctx);
     prof_mark(ctx, PB_PROF_APPLY);
-    if (F.d.has_w && F.d.nE > 0) {
+    if (F.d.has_w) {   // also on a rank without band cells: the kernel must refresh its partial-sum slots (to 0) before the in-place reduction
         const int gb = band_wgrid(F.d.nE);
 #define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 256, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
         if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else FOLD_BAND(3);
@@ -975,7 +983,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         const bool cg = method == PB200_KRYLOV_CG;
-        const bool prec = cg && band && F.prec;
+        const bool prec = cg && F.d.has_w && F.prec;   // F.prec is the same on every rank
         const int gE = band_wgrid(F.d.nE);
         const StopCrit nostop = {0.0, 0.0, -1};
         if (cg) {
@@ -1029,7 +1037,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
         const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
         const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
-        const double gkey[5] = {(double)method, o.rtol, o.atol, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
+        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen, o.rtol, o.atol, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
         if (use_graph && memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
             for (auto &kv : F.graphs) cudaGraphExecDestroy(kv.second.exec);
             F.graphs.clear();

@@ -29,7 +29,7 @@ def main():
             dims, L = (40, 36), (8.0, 7.2)
             body = pb.Balls([[4.03, 3.67]], [2.0])   # no tangency to a grid line
         else:
-            dims, L = (14, 12, 13), (4.0, 4.0, 4.0)
+            dims, L = (14, 12, int(os.environ.get("PARITY_NZ", "13"))), (4.0, 4.0, 4.0)
             body = -pb.Sphere((2.01, 2.01, 2.01), 1.0)
         mesh = pb.Mesh(dims, L)
         n = int(np.prod([d + 1 for d in dims]))
@@ -57,6 +57,8 @@ def main():
             pb.solve_DiffusionUnsteadyMono_(s, p1, dt, 2.5 * dt, bc, pb.Robin(1.0, 0.5, 0.3), "BE", reltol=1e-13)
             nblk = 2
         nloc = c1.nloc
+        if rank == 0:
+            print(case, "solver log:", [(c["iters"], c["converged"], "%.1e" % c["rnorm"]) for c in s.ch], flush=True)
         gathered = [None] * world
         dist.all_gather_object(gathered, [st for st in s.states])
         caps = [None] * world
