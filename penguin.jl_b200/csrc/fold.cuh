@@ -726,11 +726,21 @@ __global__ void kf_band_seed(FoldDev fd, double *out)
 __global__ void __launch_bounds__(FCH) kf_zero(Items I, FVec a) { FV_LOOP(I) a.f[f][i] = 0.0; }
 __global__ void __launch_bounds__(FCH) kf_copy2(Items I, FVec a, FVec b, FVec c) { FV_LOOP(I) { const double v = a.f[f][i]; b.f[f][i] = v; c.f[f][i] = v; } }
 // r = b - q ; publishes (r, r)
-__global__ void __launch_bounds__(FCH) kf_resid(Items I, FVec b, FVec q, FVec r, double *partials, double *results, unsigned *counter)
+// first residual of a solve, one pass: r = b - q (q == nullptr fields: r = b), copies of r into p (and r0), publishes ((b, b), (r, r))
+__global__ void __launch_bounds__(FCH) kf_resid(Items I, FVec b, FVec q, int have_q, FVec r, FVec p, FVec r0, int have_r0, double *partials, double *results,
+                                                unsigned *counter)
 {
-    double v[1] = {0.0};
-    FV_LOOP(I) { const double x = b.f[f][i] - q.f[f][i]; r.f[f][i] = x; v[0] += x * x; }
-    block_reduce_publish<1>(v, partials, results, counter);
+    double v[2] = {0.0, 0.0};
+    FV_LOOP(I) {
+        const double bv = b.f[f][i];
+        const double x = have_q ? bv - q.f[f][i] : bv;
+        r.f[f][i] = x;
+        p.f[f][i] = x;
+        if (have_r0) r0.f[f][i] = x;
+        v[0] += bv * bv;
+        v[1] += x * x;
+    }
+    block_reduce_publish<2>(v, partials, results, counter);   // results = FS_BB, FS_RR0 (adjacent)
 }
 __global__ void __launch_bounds__(FCH) kf_dot(Items I, FVec a, FVec b, double *partials, double *results, unsigned *counter)
 {
@@ -875,12 +885,25 @@ __global__ void kf_to_scaled_band(FoldDev fd, MVec b, FVec bh)
         bh.f[2][k] = I5[2] * v0 + I5[3] * v1 + I5[4] * vw;
     }
 }
-// x^ = L^T x (initial guess)
-__global__ void __launch_bounds__(FCH) kf_guess_dense(FoldDev fd, Items I, MVec x, FVec xh)
+// x^ = L^T x0 with x0 the extrapolated initial guess sum_j c_j T^(n-j) (GuessSpec, assemble.cuh), evaluated on the fly
+__device__ __forceinline__ double guess_at(const GuessSpec &gs, long long l)
 {
-    FV_LOOP(I) { if (f < 2) { const double s = fd.sc[f][i]; xh.f[f][i] = s != 0.0 ? x.f[f][i] / s : 0.0; } }
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < PB_MAXHIST; ++j)
+        if (j < gs.m) v += gs.c[j] * gs.T[j][l];
+    return v;
 }
-__global__ void kf_guess_band(FoldDev fd, MVec x, FVec xh)
+__global__ void __launch_bounds__(FCH) kf_guess_dense(FoldDev fd, Items I, GuessSpec g0, GuessSpec g1, FVec xh)
+{
+    FV_LOOP(I) {
+        if (f < 2) {
+            const double s = fd.sc[f][i];     // non-zero exactly on the free, non-band unknowns
+            xh.f[f][i] = s != 0.0 ? guess_at(f == 0 ? g0 : g1, i) / s : 0.0;
+        }
+    }
+}
+__global__ void kf_guess_band(FoldDev fd, GuessSpec g0, GuessSpec g1, GuessSpec gw, FVec xh)
 {
     for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
         const long long l = fd.Bcell[k];
@@ -889,7 +912,7 @@ __global__ void kf_guess_band(FoldDev fd, MVec x, FVec xh)
         for (int q = 0; q < 5; ++q) I5[q] = fd.Linv[(size_t)q * fd.nB + k];
         const double l00 = I5[0] != 0.0 ? 1.0 / I5[0] : 0.0, l11 = I5[1] != 0.0 ? 1.0 / I5[1] : 0.0, l22 = 1.0 / I5[4];
         const double l20 = -I5[2] * l00 * l22, l21 = -I5[3] * l11 * l22;
-        const double x0 = x.f[0][l], x1 = fd.nbulk > 1 ? x.f[1][l] : 0.0, xw = x.f[fd.nbulk][l];
+        const double x0 = I5[0] != 0.0 ? guess_at(g0, l) : 0.0, x1 = (fd.nbulk > 1 && I5[1] != 0.0) ? guess_at(g1, l) : 0.0, xw = guess_at(gw, l);
         xh.f[0][l] = l00 * x0 + l20 * xw;
         if (fd.nbulk > 1) xh.f[1][l] = l11 * x1 + l21 * xw;
         xh.f[2][k] = l22 * xw;

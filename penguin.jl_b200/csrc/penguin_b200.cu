@@ -942,7 +942,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
 
 // Krylov solve of the folded system.  In: s->b (reference rows, known parts eliminated), s->x (initial guess on the free sets).
 // Out: s->x.  The stopping test ||r^|| <= max(rtol ||b^||, atol) is on the block-Jacobi-scaled residual.
-static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, bool warm, int *iters, int *conv, double *rnorm_out, double *bnorm_out)
+static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, const GuessSpec gsp[3], int *iters, int *conv, double *rnorm_out, double *bnorm_out)
 {
     pb200_ctx *ctx = s->ctx;
     FoldSys &F = s->F;
@@ -961,16 +961,17 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
     // b^ and x^0
     kf_to_scaled_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, s->b, F.b); LAUNCH_CHECK(ctx);
     if (band) { kf_to_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->b, F.b); LAUNCH_CHECK(ctx); }
-    kf_dot<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.b, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
+    const bool cg = method == PB200_KRYLOV_CG;
+    static_assert(FS_RR0 == FS_BB + 1, "kf_resid publishes the pair (bb, rr0)");
+    const bool warm = gsp[0].m > 0;
     if (warm) {
-        kf_guess_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, s->x, F.x); LAUNCH_CHECK(ctx);
-        if (band) { kf_guess_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->x, F.x); LAUNCH_CHECK(ctx); }
+        kf_guess_dense<<<grid, FCH, 0, ctx->stream>>>(F.d, I, gsp[0], gsp[1], F.x); LAUNCH_CHECK(ctx);
+        if (band) { kf_guess_band<<<gb, 128, 0, ctx->stream>>>(F.d, gsp[0], gsp[1], gsp[2], F.x); LAUNCH_CHECK(ctx); }
         if ((rc = fold_apply(s, F.x, F.v, F.v, 0))) return rc;
-        kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, F.r, ctx->d_partials, res + FS_RR0, ctx->d_counter); LAUNCH_CHECK(ctx);
+        kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, 1, F.r, F.p, F.r0, cg ? 0 : 1, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
     } else {
         kf_zero<<<grid, FCH, 0, ctx->stream>>>(I, F.x); LAUNCH_CHECK(ctx);
-        kf_zero<<<grid, FCH, 0, ctx->stream>>>(I, F.v); LAUNCH_CHECK(ctx);
-        kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, F.r, ctx->d_partials, res + FS_RR0, ctx->d_counter); LAUNCH_CHECK(ctx);
+        kf_resid<<<grid, FCH, 0, ctx->stream>>>(I, F.b, F.v, 0, F.r, F.p, F.r0, cg ? 0 : 1, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
     }
     if ((rc = allreduce_results(ctx, FS_BB, 2))) return rc;
     // No host look at ||b||, ||r0|| here: the device-side stopping test (fold_done) needs neither, and a converged start simply turns
@@ -982,12 +983,10 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
         // (rho, rr) pair 0 = (rr0, rr0)
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(res + FS_PAIR0 + 1, res + FS_RR0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        const bool cg = method == PB200_KRYLOV_CG;
         const bool prec = cg && F.d.has_w && F.prec;   // F.prec is the same on every rank
         const int gE = band_wgrid(F.d.nE);
         const StopCrit nostop = {0.0, 0.0, -1};
         if (cg) {
-            kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.p, F.p); LAUNCH_CHECK(ctx);
             if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
                 DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
                 LAUNCH_CHECK(ctx);
@@ -995,7 +994,6 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, b
                 kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx);
             }
         }
-        else { kf_copy2<<<grid, FCH, 0, ctx->stream>>>(I, F.r, F.r0, F.p); LAUNCH_CHECK(ctx); }
         // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
         // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
         auto enqueue = [&](int curp) -> int {   // one Krylov iteration reading pair `curp`, publishing pair curp ^ 1
@@ -1131,6 +1129,8 @@ static int build_masks(pb200_solver *s)
         cudaStream_t st = ctx->stream;
         if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { k_mark_known_rows<<<grid, RED_THREADS, 0, st>>>(gg, ma, mb, list, cnt, cap); }, &s->Kcell, &s->nK))) return rc;
     }
+    // the solution vector is only written where unknowns are active: clear what an earlier mask set may have left elsewhere
+    for (int f = 0; f < s->nf; ++f) CUDA_TRY(ctx, cudaMemsetAsync(s->x.f[f], 0, sizeof(double) * (size_t)g.nloc, ctx->stream));
     s->masks_dirty = false;
     s->diag_key.cV = -1;
     s->F.built = false;
@@ -1236,9 +1236,11 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
                                                                                               s->nf == 2 ? s->b.f[1] : nullptr)));
             LAUNCH_CHECK(ctx);
         }
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]);
-        LAUNCH_CHECK(ctx);
-        if (s->nf == 2) { k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[0], s->histG[0]), s->m1, MB_IFREE, s->x.f[1]); LAUNCH_CHECK(ctx); }
+        if (!use_fold) {   // (the folded path evaluates the guess itself, in scaled unknowns)
+            k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]);
+            LAUNCH_CHECK(ctx);
+            if (s->nf == 2) { k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[0], s->histG[0]), s->m1, MB_IFREE, s->x.f[1]); LAUNCH_CHECK(ctx); }
+        }
     } else {
         if (gsp[0].arr) { double *fl[1] = {s->gS[0]}; if ((rc = halo_exchange(ctx, g, fl, 1))) return rc; }
         DISPATCH_N(g.N, (k_rhs_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
@@ -1250,9 +1252,11 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
                                                                                               gsp[0], s->b.f[0], s->b.f[1], s->b.f[2])));
             LAUNCH_CHECK(ctx);
         }
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]); LAUNCH_CHECK(ctx);
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[1], s->histW[1]), s->m2, MB_FREE, s->x.f[1]); LAUNCH_CHECK(ctx);
-        k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[1], s->histG[1]), s->m2, MB_IFREE, s->x.f[2]); LAUNCH_CHECK(ctx);
+        if (!use_fold) {
+            k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[0], s->histW[0]), s->m1, MB_FREE, s->x.f[0]); LAUNCH_CHECK(ctx);
+            k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tw[1], s->histW[1]), s->m2, MB_FREE, s->x.f[1]); LAUNCH_CHECK(ctx);
+            k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[1], s->histG[1]), s->m2, MB_IFREE, s->x.f[2]); LAUNCH_CHECK(ctx);
+        }
     }
     if (use_fold) {
         // folded system (cached per coefficient set and mask set)
@@ -1277,7 +1281,11 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     int it = 0, converged = 0;
     double rnorm = 0.0, bnorm = 0.0;
     if (use_fold) {
-        if ((rc = fold_solve(s, method, o, o.warm_start && unsteady, &it, &converged, &rnorm, &bnorm))) return rc;
+        GuessSpec gsp[3];
+        gsp[0] = guess_spec(s->Tw[0], s->histW[0]);
+        gsp[1] = diph ? guess_spec(s->Tw[1], s->histW[1]) : gsp[0];
+        gsp[2] = diph ? guess_spec(s->Tg[1], s->histG[1]) : guess_spec(s->Tg[0], s->histG[0]);
+        if ((rc = fold_solve(s, method, o, gsp, &it, &converged, &rnorm, &bnorm))) return rc;
     } else {
     // bnorm
     k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->b, s->b, s->b, s->b, ctx->d_partials, res + SL_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
