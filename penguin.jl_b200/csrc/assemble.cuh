@@ -39,12 +39,12 @@ __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const 
                            SrcSpec g0, SrcSpec g1, double *__restrict__ bb, double *__restrict__ bi, int skip_known)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
-        int c[PB_MAXD];
-        cell_coords(g, t, c);
         const int64_t l = t + g.plane;
         const unsigned char mb = m[l];
         const bool wb = mb & MB_FREE, wi = bi && (mb & MB_IFREE);
         if (!wb && !wi) { bb[l] = 0.0; if (bi) bi[l] = 0.0; continue; }
+        int c[PB_MAXD] = {0, 0, 0};
+        if (sc.cn || !skip_known) cell_coords(g, t, c);
         const double D = D_at(p, l), V = p.V[l], Gm = p.Gam[l];
         double Rbk = 0.0, Rik = 0.0, Rbe = 0.0, Rie = 0.0;
         GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
@@ -56,7 +56,7 @@ __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const 
         }
         if (wb) {
             double v = sc.cV * V * Tw[l] + V * (sc.wf0 * src_at(f0, l) + sc.wf1 * src_at(f1, l)) - sc.ce * D * Rbe
-                       - (sc.cV * V * ufix[l] + sc.c * D * Rbk);
+                       - sc.c * D * Rbk;   // (ufix is zero on a free row)
             if (sc.sym) v /= D;
             bb[l] = v;
         } else bb[l] = 0.0;
@@ -82,12 +82,12 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
                            double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw, int skip_known)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
-        int c[PB_MAXD];
-        cell_coords(g, t, c);
         const int64_t l = t + g.plane;
         const unsigned char a = m1[l], b = m2[l];
         const bool w1 = a & MB_FREE, w2 = b & MB_FREE, ww = b & MB_IFREE;
         if (!w1 && !w2 && !ww) { b1[l] = 0.0; b2[l] = 0.0; bw[l] = 0.0; continue; }
+        int c[PB_MAXD] = {0, 0, 0};
+        if (sc.cn || !skip_known) cell_coords(g, t, c);   // (64-bit divisions: only when a stencil is evaluated; the BE fast path streams)
         GamSpec gk1 = {gj.arr, 1.0 / sp.a1, nullptr, 0.0, gj.arr ? 0.0 : gj.cst / sp.a1};
         GamSpec gk2 = {nullptr, 0.0, nullptr, 0.0, 0.0};
         double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0, Rbe1 = 0, Rie1 = 0, Rbe2 = 0, Rie2 = 0;
@@ -103,10 +103,10 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
         }
         const double V1 = p1.V[l], V2 = p2.V[l];
         b1[l] = w1 ? sc.cV * V1 * Tw1[l] + V1 * (sc.wf0 * src_at(f10, l) + sc.wf1 * src_at(f11, l)) - sc.ce * D_at(p1, l) * Rbe1
-                         - (sc.cV * V1 * ufix1[l] + sc.c * D_at(p1, l) * Rbk1)
+                         - sc.c * D_at(p1, l) * Rbk1       /* (ufix is zero on a free row) */
                    : 0.0;
         b2[l] = w2 ? sc.cV * V2 * Tw2[l] + V2 * (sc.wf0 * src_at(f20, l) + sc.wf1 * src_at(f21, l)) - sc.ce * D_at(p2, l) * Rbe2
-                         - (sc.cV * V2 * ufix2[l] + sc.c * D_at(p2, l) * Rbk2)
+                         - sc.c * D_at(p2, l) * Rbk2
                    : 0.0;
         bw[l] = ww ? p2.Gam[l] * src_at(hj, l) - (sp.b1 * Rik1 + sp.b2 * Rik2) : 0.0;
     }
