@@ -130,7 +130,8 @@ typedef struct {
 int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *desc, pb200_solver **s);
 /* border condition of one side (BC_border_mono!/diph!, src/solver.jl:417-580).  `values` (host, may be NULL =>
  * `value` everywhere) holds one entry per real cell of the side, the other dims x fastest.  May be called again
- * before any step (time-dependent border data).                                                              */
+ * before any step (time-dependent border data).  Dirichlet: x = value.  Periodic: supported when the row pins a value (both sides
+ * Periodic, or Periodic + Dirichlet).  Neumann: a real row in 1-D only (`value` = g), a no-op in >= 2-D like Robin (src/solver.jl:471-498). */
 int pb200_solver_set_border(pb200_solver *s, int side, int kind, double value, const double *values);
 /* state vector [T_omega; T_gamma] (2 nloc) or [T_omega1; T_gamma1; T_omega2; T_gamma2] (4 nloc) */
 int pb200_solver_set_state(pb200_solver *s, const double *x);

@@ -514,8 +514,10 @@ def _set_borders(s, mesh, bc_b, t):
             continue
         kind = _BCK.get(type(cond), 0)
         cst, arr = (0.0, None)
-        if kind == 1:
+        if kind == 1 or (kind == 2 and mesh.N == 1):                 # values matter for Dirichlet rows and for the 1-D Neumann row
             cst, arr = _border_values(mesh, key, cond, t)
+            if kind == 2 and arr is not None:
+                cst, arr = float(arr[0]), None
         L.check(L.lib().pb200_solver_set_border(s._h, side, kind, cst, _dp(arr)), s._ctx.h)
 
 

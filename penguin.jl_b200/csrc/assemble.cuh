@@ -204,7 +204,7 @@ __global__ void k_count(Grid g, const unsigned char *__restrict__ m1, const unsi
     double v[2] = {0.0, 0.0};
     for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
         const unsigned char a = m1[l], b = m2 ? m2[l] : 0;
-        v[0] += ((a & (MB_FREE | MB_FIXED)) ? 1.0 : 0.0) + ((b & (MB_FREE | MB_FIXED)) ? 1.0 : 0.0);
+        v[0] += ((a & (MB_FREE | MB_FIXED | MB_SLAVE)) ? 1.0 : 0.0) + ((b & (MB_FREE | MB_FIXED | MB_SLAVE)) ? 1.0 : 0.0);
         v[1] += ((a & (MB_IFREE | MB_IKNOWN)) ? 1.0 : 0.0) + ((b & MB_IFREE) ? 1.0 : 0.0);
     }
     block_reduce_publish<2>(v, partials, results, counter);

@@ -98,6 +98,8 @@ __device__ __forceinline__ void phase_diag(const PhaseDev &ph, const Grid &g, in
 #define MB_FIXED 2  // bulk unknown pinned by a border Dirichlet row
 #define MB_IFREE 4  // interface unknown solved for (mono Robin/Neumann: T_gamma ; diph: T_gamma2)
 #define MB_IKNOWN 8 // mono Dirichlet interface: T_gamma = g kept by the reference's trimming (Gamma != 0)
+#define MB_SLAVE 32 // 1-D Neumann border row (src/solver.jl:471-493): (x_row - x_adj) / dx = g, i.e. x_row = x_adj + g dx is eliminated: the value
+                    // follows its neighbour (k_slave_copy around every operator apply), g dx sits in ufix
 #define MB_KNBR 16  // the bulk row of this cell couples to an eliminated value (a known T_gamma through H, or a border-Dirichlet neighbour):
                     // only these rows need the "known part" of the right-hand side (assemble.cuh)
 
@@ -192,6 +194,7 @@ __device__ __forceinline__ bool row_couples_to_known(const PhaseDev &ph, const G
             if (!real) continue;
             double vv;
             k = k || (border_pinned(g, bd, cn, vv) == 1);
+            if (N == 1) { const int kn = border_key(g, cn); k = k || (kn >= 0 && bd.kind[kn] == PB200_BC_NEUMANN); }
         }
     }
     return k;
@@ -213,6 +216,11 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
         const int pin = real ? border_pinned(g, bd, c, bval) : 0;
         if (pin < 0) *err = 1;
         const bool dirichlet = pin == 1;   // the row pins the value (Dirichlet, or a Periodic row that resolves to a known value)
+        bool slave = false;                // 1-D Neumann border row
+        if (N == 1 && real && pin == 0) {
+            const int kn = border_key(g, c);
+            if (kn >= 0 && bd.kind[kn] == PB200_BC_NEUMANN) { slave = true; bval = bd.value[kn] * g.h[0]; }
+        }
         const bool unsteady = sp.time_type == PB200_UNSTEADY;
         double GG, HH;
         bool rowG, hrow1, hrow2 = false;
@@ -221,6 +229,7 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
         bool kept1 = (unsteady && p1.V[l] != 0.0) || rowG;
         if (sp.phase_type == PB200_MONO) {
             if (dirichlet) { b1 |= MB_FIXED; ufix1[l] = bval; }
+            else if (slave) { b1 |= MB_SLAVE; ufix1[l] = bval; }
             else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
             bool keptI = (sp.beta != 0.0 && hrow1) || (sp.alpha != 0.0 && p1.Gam[l] != 0.0);
             if (keptI) b1 |= (sp.beta != 0.0 ? MB_IFREE : MB_IKNOWN);
@@ -231,8 +240,9 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
             phase_diag<N>(p2, g, l, c, GG, HH, rowG2, hrow2);
             bool kept2 = (unsteady && p2.V[l] != 0.0) || rowG2;
             bool d1 = dirichlet && ct1[l] != 0.0, d2 = dirichlet && ct2[l] != 0.0;   // src/solver.jl:573-576
-            if (d1) { b1 |= MB_FIXED; ufix1[l] = bval; } else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
-            if (d2) { b2 |= MB_FIXED; ufix2[l] = bval; } else { if (kept2) b2 |= MB_FREE; ufix2[l] = 0.0; }
+            const bool s1 = slave && ct1[l] != 0.0, s2 = slave && ct2[l] != 0.0;
+            if (d1) { b1 |= MB_FIXED; ufix1[l] = bval; } else if (s1) { b1 |= MB_SLAVE; ufix1[l] = bval; } else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
+            if (d2) { b2 |= MB_FIXED; ufix2[l] = bval; } else if (s2) { b2 |= MB_SLAVE; ufix2[l] = bval; } else { if (kept2) b2 |= MB_FREE; ufix2[l] = 0.0; }
             bool keptI = (sp.b1 != 0.0 && hrow1) || (sp.b2 != 0.0 && hrow2);
             if (keptI) b2 |= MB_IFREE;   // T_gamma2 is the interface unknown; T_gamma1 = (g + a2 T_gamma2) / a1 everywhere
             if ((b1 & MB_FREE) && row_couples_to_known<N>(p1, g, l, c, bd)) b1 |= MB_KNBR;
@@ -392,5 +402,17 @@ __global__ void k_wdag(int64_t n, const double *__restrict__ W, double *__restri
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double w = W[i];
         Wd[i] = w != 0.0 ? 1.0 / w : 1.0;
+    }
+}
+
+// 1-D Neumann border rows: the eliminated unknown follows its neighbour (bottom cell <- cell 1, top cell <- cell n-2); restore != 0 puts the
+// zero back that Krylov vectors carry on non-free entries
+__global__ void k_slave_copy(Grid g, const unsigned char *__restrict__ m, double *__restrict__ u, int restore)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = t + g.plane;
+        if (!(m[l] & MB_SLAVE)) continue;
+        const int c0 = (int)t + g.k0;
+        u[l] = restore ? 0.0 : (c0 == 0 ? u[l + 1] : u[l - 1]);
     }
 }

@@ -459,10 +459,11 @@ extern "C" int pb200_solver_set_border(pb200_solver *s, int side, int kind, doub
     pb200_ctx *ctx = s->ctx;
     const int dim = (side == PB200_LEFT || side == PB200_RIGHT) ? 1 : (side == PB200_BOTTOM || side == PB200_TOP) ? 0 : 2;
     if (dim >= s->g.N) return PB200_OK;   // keys of absent dimensions never match a cell (src/solver.jl:379-409)
-    if (kind == PB200_BC_NEUMANN && s->g.N == 1) return set_err(ctx, PB200_EUNSUPPORTED, "1-D Neumann border rows are not supported by libpenguin_b200 yet");
+    if (kind == PB200_BC_NEUMANN && s->g.N == 1 && ctx->nranks > 1)
+        return set_err(ctx, PB200_EUNSUPPORTED, "1-D Neumann border rows are supported on one rank only");
     // Neumann (>= 2-D) and Robin borders are no-ops in the reference (src/solver.jl:471-498): record as NONE -- but the key is PRESENT,
-    // which is what a Periodic row on the opposite side tests (src/solver.jl:458)
-    if (kind != PB200_BC_DIRICHLET && kind != PB200_BC_PERIODIC) kind = PB200_BC_NONE;
+    // which is what a Periodic row on the opposite side tests (src/solver.jl:458).  In 1-D the Neumann row is real (src/solver.jl:471-493).
+    if (kind != PB200_BC_DIRICHLET && kind != PB200_BC_PERIODIC && !(kind == PB200_BC_NEUMANN && s->g.N == 1)) kind = PB200_BC_NONE;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     s->bd.present[side] = 1;
     s->bd.kind[side] = kind;
@@ -539,6 +540,11 @@ extern "C" int pb200_solver_wait_state(pb200_solver *s)
     return PB200_OK;
 }
 
+static bool has_slave_rows(const pb200_solver *s)
+{
+    return s->g.N == 1 && (s->bd.kind[PB200_BOTTOM] == PB200_BC_NEUMANN || s->bd.kind[PB200_TOP] == PB200_BC_NEUMANN);
+}
+
 // ---- operator application on Krylov vectors ------------------------------------------------------------------------
 static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const MVec &out)
 {
@@ -547,6 +553,11 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
     int rc;
     if ((rc = halo_exchange(ctx, g, in.f, s->nf))) return rc;
     const int grid = sgrid(ctx, g.nown);
+    const bool slaves = has_slave_rows(s);
+    if (slaves) {
+        k_slave_copy<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m1, in.f[0], 0); LAUNCH_CHECK(ctx);
+        if (s->sp.phase_type == PB200_DIPH) { k_slave_copy<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m2, in.f[1], 0); LAUNCH_CHECK(ctx); }
+    }
     prof_mark(ctx, PB_PROF_APPLY);
     ctx->apply_launches++;
     if (s->sp.phase_type == PB200_MONO) {
@@ -561,6 +572,10 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
     }
     LAUNCH_CHECK(ctx);
     prof_mark(ctx, PB_PROF_APPLY);
+    if (slaves) {   // Krylov vectors carry zeros on non-free entries
+        k_slave_copy<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m1, in.f[0], 1); LAUNCH_CHECK(ctx);
+        if (s->sp.phase_type == PB200_DIPH) { k_slave_copy<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m2, in.f[1], 1); LAUNCH_CHECK(ctx); }
+    }
     return PB200_OK;
 }
 
@@ -571,6 +586,7 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
 static bool fold_eligible(const pb200_solver *s)
 {
     const SysParams &sp = s->sp;
+    if (has_slave_rows(s)) return false;   // 1-D Neumann border rows: eliminated unknowns that follow a neighbour -- generic path only
     if (sp.phase_type == PB200_MONO) {
         if (sp.beta == 0.0) return true;                       // Dirichlet interface: T_gamma known, SPD bulk system
         return sp.beta > 0.0 && sp.alpha >= 0.0;               // Robin / Neumann rows symmetrise with positive factors
@@ -1389,6 +1405,10 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         s->n_prev = s->prev_dt == in->dt ? (s->n_prev < keep ? s->n_prev + 1 : keep) : 1;
         s->prev_dt = in->dt;
     } else s->n_prev = 0;
+    if (has_slave_rows(s)) {   // x_row = x_adj (+ g dx from ufix in k_store_bulk)
+        k_slave_copy<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m1, z.f[0], 0); LAUNCH_CHECK(ctx);
+        if (diph) { k_slave_copy<<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->m2, z.f[1], 0); LAUNCH_CHECK(ctx); }
+    }
     k_store_bulk<<<grid, RED_THREADS, 0, ctx->stream>>>(g, z.f[0], s->ufix1, s->Tw[0]); LAUNCH_CHECK(ctx);
     if (!diph) {
         const double *src = s->nf == 2 ? z.f[1] : s->gK;

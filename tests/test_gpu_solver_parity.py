@@ -349,3 +349,39 @@ def test_periodic_borders(pb, kw, which):
     sol = sg.x[:mo.n].reshape(nx + 1, nx + 1)
     if which == "x":       # the reference's own assertion (:41): opposite columns agree
         assert np.allclose(sol[1:nx - 1, 0], sol[1:nx - 1, nx - 1], atol=1e-8)
+
+
+@pytest.mark.parametrize("phase", ["mono", "diph"])
+def test_neumann_border_1d(pb, phase):
+    # src/solver.jl:471-493: in 1-D a Neumann border is a real row, (x_row - x_adj) / dx = g (in >= 2-D it is a warning no-op)
+    nx, lx = 60, 6.0
+    mo, mg = _meshes(pb, (nx,), (lx,))
+    dt = 0.4 * (lx / nx) ** 2
+    bo = po.BorderConditions({"bottom": po.Neumann(0.7), "top": po.Dirichlet(0.2)})
+    bg = pb.BorderConditions({"bottom": pb.Neumann(0.7), "top": pb.Dirichlet(0.2)})
+    n = mo.n
+    if phase == "mono":
+        f = lambda x, y, z, t: 1.0 + 0 * x
+        pho, phg = _phases(pb, mo, mg, geom.LevelSet.halfspace(0, 4.13, True), f, 1.0)
+        u0 = np.zeros(2 * n)
+        so = po.DiffusionUnsteadyMono(pho, bo, po.Robin(1.0, 0.5, 0.3), dt, u0, "BE")
+        po.solve_DiffusionUnsteadyMono(so, pho, dt, 3.5 * dt, bo, po.Robin(1.0, 0.5, 0.3), "CN")
+        sg = pb.DiffusionUnsteadyMono(phg, bg, pb.Robin(1.0, 0.5, 0.3), dt, u0, "BE")
+        pb.solve_DiffusionUnsteadyMono_(sg, phg, dt, 3.5 * dt, bg, pb.Robin(1.0, 0.5, 0.3), "CN", reltol=1e-13, maxiter=50000)
+    else:
+        f = lambda x, y, z, t: 0.0 * x
+        ls = geom.LevelSet.halfspace(0, 3.07, True)
+        p1o, p1g = _phases(pb, mo, mg, ls, f, 1.0)
+        p2o, p2g = _phases(pb, mo, mg, ls.flipped(), f, 2.0)
+        u0 = np.concatenate([np.zeros(2 * n), np.ones(2 * n)])
+        bo = po.BorderConditions({"bottom": po.Dirichlet(0.0), "top": po.Neumann(-0.4)})
+        bg = pb.BorderConditions({"bottom": pb.Dirichlet(0.0), "top": pb.Neumann(-0.4)})
+        ico = po.InterfaceConditions(po.ScalarJump(1.0, 0.5, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+        icg = pb.InterfaceConditions(pb.ScalarJump(1.0, 0.5, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
+        so = po.DiffusionUnsteadyDiph(p1o, p2o, bo, ico, dt, u0, "BE")
+        po.solve_DiffusionUnsteadyDiph(so, p1o, p2o, dt, 3.5 * dt, bo, ico, "BE")
+        sg = pb.DiffusionUnsteadyDiph(p1g, p2g, bg, icg, dt, u0, "BE")
+        pb.solve_DiffusionUnsteadyDiph_(sg, p1g, p2g, dt, 3.5 * dt, bg, icg, "BE", reltol=1e-13, maxiter=50000)
+    assert len(sg.states) == len(so.states)
+    for a, b in zip(sg.states, so.states):
+        assert rel_l2(a, b) < TOL
