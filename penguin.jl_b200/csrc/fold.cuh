@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
 
 // ---- band preconditioner -------------------------------------------------------------------------------------------------------
 // The spectrum of M^ is the bulk interval [1/(1+2N theta dt/h^2 ...)] plus a few low modes localised on neighbouring cut cells (their w
-// unknowns are coupled across faces; tools/krylov_experiment3.py).  They are removed by a low-degree Chebyshev polynomial of the band
+// unknowns are coupled across faces; tests/experiments/krylov_experiment3.py).  They are removed by a low-degree Chebyshev polynomial of the band
 // block M^_BB (all unknowns of the band cells) used as preconditioner on the band only: z = r outside the band, z_B = q(M^_BB) r_B.
 // out[c][bo] = ca x_c + cb (M^_BB x)_c for every OWNED band cell; publishes sum_c x_c out_c  (x read from an FVec)
 template <int N>

@@ -1,7 +1,7 @@
 """3-D diphasic heat at nx^3 on device-built capacities: per-step parity with the oracle and the extremes of the state (the cut-cell
 scheme does not bound the values of near-empty cut cells; this shows the device reproduces the oracle's extremes)."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import penguin_b200 as pb

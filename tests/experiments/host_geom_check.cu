@@ -3,7 +3,7 @@
 #include <cmath>
 #include <cstdlib>
 #define PB_HOST_GEOM 1
-#include "../penguin.jl_b200/csrc/geometry.cuh"
+#include "../../penguin.jl_b200/csrc/geometry.cuh"
 extern "C" void pgo_ball_box(int m, const double *c, double R, const double *lo, const double *hi, double *out);
 extern "C" void pgo_sphere_box(int m, const double *c, double R, const double *lo, const double *hi, double *out);
 static double urand() { return rand() / (double)RAND_MAX; }

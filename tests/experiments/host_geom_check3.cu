@@ -3,7 +3,7 @@
 #include <cstdlib>
 #include <vector>
 #define PB_HOST_GEOM 1
-#include "../penguin.jl_b200/csrc/geometry.cuh"
+#include "../../penguin.jl_b200/csrc/geometry.cuh"
 extern "C" int pgo_capacity(int N, const int *ncell, const double *x0, const double *L, int kind, int nb, const double *centers, const double *radii, int inside, int hd, double hc,
                  double *V, double *Gamma, double *ctype, double *A, double *B, double *W, double *Com, double *Cga);
 int main()

@@ -1,6 +1,6 @@
 """CPU experiment (design aid, not product): Krylov behaviour of the eliminated diphasic system [u1, u2, w]."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 from oracle import geom, penguin_oracle as po
 

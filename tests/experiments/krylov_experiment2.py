@@ -1,6 +1,6 @@
 """CPU experiment: per-cell block-Jacobi (u1_i, u2_i, w_i) on the symmetrised diphasic system."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 from oracle import geom, penguin_oracle as po
 

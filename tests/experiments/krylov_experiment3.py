@@ -1,6 +1,6 @@
 """Where do the small eigenvalues of the block-Jacobi-scaled diphasic system live?"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 from oracle import geom, penguin_oracle as po
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 128

@@ -1,6 +1,6 @@
 """CG on the block-Jacobi-scaled system with a polynomial (Chebyshev) preconditioner restricted to the interface band."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 from oracle import geom, penguin_oracle as po
 

@@ -1,5 +1,5 @@
 """Run under torchrun (one rank per GPU): slab-partitioned solve vs the oracle on the global problem.
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_parity.py"""
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_parity.py"""
 import os
 import sys
 

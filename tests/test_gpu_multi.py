@@ -14,7 +14,7 @@ def test_two_rank_parity():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tools", "multi_gpu_parity.py")]
+           "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_parity.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_PARITY_OK" in out.stdout
