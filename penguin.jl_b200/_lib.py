@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libpenguin_b200.so")
+SO = os.environ.get("PB200_LIB") or os.path.join(HERE, "libpenguin_b200.so")   # (PB200_LIB: kernel-variant experiments)
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

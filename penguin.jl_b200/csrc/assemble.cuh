@@ -36,10 +36,14 @@ __global__ void k_gamma_known(Grid g, StepCoef sc, const unsigned char *__restri
 template <int N>
 __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m, const double *__restrict__ Tw,
                            const double *__restrict__ Tg, const double *__restrict__ ufix, const double *__restrict__ gK, SrcSpec f0, SrcSpec f1,
-                           SrcSpec g0, SrcSpec g1, double *__restrict__ bb, double *__restrict__ bi, int skip_known)
+                           SrcSpec g0, SrcSpec g1, double *__restrict__ bb, double *__restrict__ bi, int skip_known,
+                           const long long *__restrict__ list = nullptr, int nlist = 0)
 {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t l = t + g.plane;
+    // list != nullptr: only the listed rows (the folded path's CN step evaluates the unfolded explicit part on the rows that couple to
+    // eliminated values and takes M^ x^n everywhere else, kf_rhs_dense)
+    const int64_t nwork = list ? (int64_t)nlist : g.nown;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwork; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = list ? (int64_t)list[w] : w + g.plane, t = l - g.plane;
         const unsigned char mb = m[l];
         const bool wb = mb & MB_FREE, wi = bi && (mb & MB_IFREE);
         if (!wb && !wi) { bb[l] = 0.0; if (bi) bi[l] = 0.0; continue; }
@@ -79,10 +83,12 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
                            const unsigned char *__restrict__ m2, const double *__restrict__ Tw1, const double *__restrict__ Tg1,
                            const double *__restrict__ Tw2, const double *__restrict__ Tg2, const double *__restrict__ ufix1,
                            const double *__restrict__ ufix2, SrcSpec f10, SrcSpec f11, SrcSpec f20, SrcSpec f21, SrcSpec gj, SrcSpec hj,
-                           double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw, int skip_known)
+                           double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw, int skip_known,
+                           const long long *__restrict__ list = nullptr, int nlist = 0)
 {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t l = t + g.plane;
+    const int64_t nwork = list ? (int64_t)nlist : g.nown;   // (list: see k_rhs_mono)
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwork; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = list ? (int64_t)list[w] : w + g.plane, t = l - g.plane;
         const unsigned char a = m1[l], b = m2[l];
         const bool w1 = a & MB_FREE, w2 = b & MB_FREE, ww = b & MB_IFREE;
         if (!w1 && !w2 && !ww) { b1[l] = 0.0; b2[l] = 0.0; bw[l] = 0.0; continue; }
@@ -118,7 +124,8 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
 // the heavy unfolded stencil evaluations run side by side instead of stalling the warps of the streaming kernel.
 template <int N>
 __global__ void k_rhs_known_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m, const long long *__restrict__ list, int n,
-                                 const double *__restrict__ ufix, const double *__restrict__ gK, double *__restrict__ bb, double *__restrict__ bi)
+                                 const double *__restrict__ ufix, const double *__restrict__ gK, double *__restrict__ bb, double *__restrict__ bi,
+                                 int set_ifc = 0, SrcSpec g0 = SrcSpec{nullptr, 0.0}, SrcSpec g1 = SrcSpec{nullptr, 0.0})
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int64_t l = list[i];
@@ -131,13 +138,21 @@ __global__ void k_rhs_known_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, 
         GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
         phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
         if (wb) { double v = sc.c * D_at(p, l) * Rbk; if (sc.sym) v /= D_at(p, l); bb[l] -= v; }
-        if (wi) { double v = sc.c2 * sp.beta * Rik; if (sc.sym) v *= sc.c / (sc.c2 * sp.beta); bi[l] -= v; }
+        if (wi) {
+            double v = sc.c2 * sp.beta * Rik;
+            if (sc.sym) v *= sc.c / (sc.c2 * sp.beta);
+            // set_ifc (steps without an explicit part, kf_rhs_dense wrote the bulk rows only): the interface row from scratch
+            const double base = set_ifc ? sc.c2 * p.Gam[l] * (sc.wg0 * src_at(g0, l) + sc.wg1 * src_at(g1, l)) - sc.c2 * sp.alpha * p.Gam[l] * (gK ? gK[l] : 0.0)
+                                        : bi[l];
+            bi[l] = base - v;
+        }
     }
 }
 template <int N>
 __global__ void k_rhs_known_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepCoef sc, const unsigned char *__restrict__ m1, const unsigned char *__restrict__ m2,
                                  const long long *__restrict__ list, int n, const double *__restrict__ ufix1, const double *__restrict__ ufix2, SrcSpec gj,
-                                 double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw)
+                                 double *__restrict__ b1, double *__restrict__ b2, double *__restrict__ bw, int set_ifc = 0,
+                                 SrcSpec hj = SrcSpec{nullptr, 0.0})
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int64_t l = list[i];
@@ -152,7 +167,7 @@ __global__ void k_rhs_known_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp,
         if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
         if (w1) b1[l] -= sc.c * D_at(p1, l) * Rbk1;
         if (w2) b2[l] -= sc.c * D_at(p2, l) * Rbk2;
-        if (ww) bw[l] -= sp.b1 * Rik1 + sp.b2 * Rik2;
+        if (ww) bw[l] = (set_ifc ? p2.Gam[l] * src_at(hj, l) : bw[l]) - (sp.b1 * Rik1 + sp.b2 * Rik2);
     }
 }
 // rows that need the known part: MB_KNBR bulk rows and every interface row

@@ -491,13 +491,21 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        // the record, flags and constants of the block's NEXT item are pulled into L1 while this one streams: the dependent chain
+        // record -> addresses -> data then costs an L1 hit per tile instead of an L2 / HBM round trip
+        if (threadIdx.x == 0 && it + (int)gridDim.x < I.n) {
+            const int nx = it + gridDim.x;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(I.rec + nx));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(I.uni + nx));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(I.ucoef + (size_t)nx * PB_MAXD));
+        }
         const TileRec R = I.rec[it];
+        const bool uni = (I.uni[it] & 1) != 0;
         if (R.f >= 2) continue;
         const int f = R.f;
         const double *__restrict__ xf = f == 0 ? x.f[0] : x.f[1];
         double *__restrict__ yf = f == 0 ? y.f[0] : y.f[1];
         const double *__restrict__ af = f == 0 ? aux.f[0] : aux.f[1];
-        const bool uni = (I.uni[it] & 1) != 0;
         if (N >= 2 && uni && R.full) {
             // interior tile of full cells: constant coefficients, every cell valid.  The thread owns FU cells that are consecutive along
             // the k direction (y in 2-D, z in 3-D): their k-neighbours are shared registers (FU + 2 loads for the column), the x-neighbours
@@ -903,6 +911,81 @@ __global__ void __launch_bounds__(FCH) kf_guess_dense(FoldDev fd, Items I, Guess
         }
     }
 }
+// Fused prologue of a step without an explicit operator part (BE, steady) on the folded path: one pass over the active tiles gives
+//   b   = cV V T^n + V (wf0 f(t_n) + wf1 f(t_n+1))   the bulk rows of b_*_unstead_diff / b_*_stead_diff (src/solver/diffusion.jl:45-58,146-161,
+//                                                     243-265,391-420) without their known part (k_rhs_known_* adds it on its row list),
+//   b^  = sc rowscale b                               (kf_to_scaled_dense),
+//   x^0 = guess / sc                                  (kf_guess_dense)
+// instead of three kernels over all cells of every phase (k_rhs_*, kf_to_scaled_dense, kf_guess_dense).
+struct RhsSrc { SrcSpec f0[2], f1[2]; const double *Tw[2]; const unsigned char *m[2]; };
+// Crank-Nicolson (vexp != null): the explicit operator part of a row that couples to no eliminated value is the folded operator applied
+// to the old state, V T - c (D G'W!(G T + H Tg)) = 2 V T - (A T)_i with (L^-1 S A T)_i = (M^ x^n)_i, x^n = L^T T^n on the free unknowns:
+// b^ = sc rowscale (2 V T^n + V (wf0 f^n + wf1 f^n+1)) - vexp, one folded apply instead of the unfolded stencil on every cell.  Rows that
+// do couple to eliminated values (the k_mark_known_rows list: band, border- and interface-adjacent rows) are evaluated unfolded by
+// k_rhs_* in list mode afterwards and refreshed by kf_to_scaled_list / kf_to_scaled_band; b is meaningful on those rows only.
+__global__ void __launch_bounds__(FCH, 4) kf_rhs_dense(FoldDev fd, Items I, StepCoef sc, RhsSrc S, GuessSpec g0, GuessSpec g1, MVec b, FVec bh, FVec xh, FVec vexp)
+{
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        if (R.f >= 2) continue;
+        // the field is one per tile: every per-field pointer is selected here (no dynamically indexed kernel parameters)
+        const bool f1 = R.f == 1;
+        const unsigned char *__restrict__ m = f1 ? S.m[1] : S.m[0];
+        const double *__restrict__ Vf = f1 ? fd.ph[1].V : fd.ph[0].V;
+        const double *__restrict__ Da = f1 ? fd.ph[1].Darr : fd.ph[0].Darr;
+        const double *__restrict__ Tw = f1 ? S.Tw[1] : S.Tw[0];
+        const double *__restrict__ scf = f1 ? fd.sc[1] : fd.sc[0];
+        const double *__restrict__ fa0 = f1 ? S.f0[1].arr : S.f0[0].arr, *__restrict__ fa1 = f1 ? S.f1[1].arr : S.f1[0].arr;
+        const double fc0 = f1 ? S.f0[1].cst : S.f0[0].cst, fc1 = f1 ? S.f1[1].cst : S.f1[0].cst;
+        const double sF = f1 ? fd.s[1] : fd.s[0], Dc = f1 ? fd.ph[1].Dc : fd.ph[0].Dc;
+        double *__restrict__ bo = f1 ? b.f[1] : b.f[0], *__restrict__ bho = f1 ? bh.f[1] : bh.f[0], *__restrict__ xo = f1 ? xh.f[1] : xh.f[0];
+        const double *__restrict__ ve = f1 ? vexp.f[1] : vexp.f[0];
+        const double cT = ve ? 2.0 * sc.cV : sc.cV;
+        long long idx[FU];
+        bool ok[FU];
+        double s[FU], v[FU], gs[FU], ex[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) ok[k] = tile_cell(I, R, k, idx[k]);
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            s[k] = 0.0; v[k] = 0.0; gs[k] = 0.0; ex[k] = 0.0;
+            if (ok[k]) {
+                const long long i = idx[k];
+                s[k] = scf[i];
+                if (ve) ex[k] = ve[i];
+                if (m[i] & MB_FREE) {
+                    const double V = Vf[i];
+                    v[k] = cT * V * Tw[i] + V * (sc.wf0 * (fa0 ? fa0[i] : fc0) + sc.wf1 * (fa1 ? fa1[i] : fc1));
+                }
+                if (s[k] != 0.0) {
+#pragma unroll
+                    for (int j = 0; j < PB_MAXHIST; ++j)
+                        if (j < g0.m) gs[k] += (f1 ? g1.c[j] : g0.c[j]) * (f1 ? g1.T[j] : g0.T[j])[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            if (ok[k]) {
+                const long long i = idx[k];
+                bo[i] = v[k];
+                bho[i] = s[k] != 0.0 ? s[k] * (sF / (fd.c * (Da ? Da[i] : Dc))) * v[k] - ex[k] : 0.0;   // = sc fold_rowscale b (- M^ x^n)
+                if (g0.m > 0) xo[i] = s[k] != 0.0 ? gs[k] / s[k] : 0.0;
+            }
+        }
+    }
+}
+// b^ of the listed rows again, after k_rhs_known_* has subtracted their known part from b (band rows: kf_to_scaled_band)
+__global__ void kf_to_scaled_list(FoldDev fd, const long long *__restrict__ list, int n, MVec b, FVec bh)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const long long l = list[k];
+        for (int f = 0; f < fd.nbulk; ++f) {
+            const double s = fd.sc[f][l];
+            if (s != 0.0) bh.f[f][l] = s * fold_rowscale(fd, f, l) * b.f[f][l];
+        }
+    }
+}
 __global__ void kf_guess_band(FoldDev fd, GuessSpec g0, GuessSpec g1, GuessSpec gw, FVec xh)
 {
     for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
@@ -961,7 +1044,9 @@ struct FoldSys {
     double graph_key[5] = {};
     int last_iters = 0;                     // iteration count of the previous solve (sizes the first chunk of the next one)
     long long cells_uniform = 0, cells_general = 0;   // cells of tiles applied with constant / streamed coefficients (this rank)
-    Items I;
+    Items I;                                // every item, index order (vector kernels)
+    Items IA;                               // bulk tiles in cost-class order (operator apply)
+    int *itemsA = nullptr; TileRec *recA = nullptr; unsigned char *uniA = nullptr; double *ucoefA = nullptr;
     FVec x, b, r, p, v, r0, s, t;
     bool have_bicg = false;
     long long wcap = 0;
@@ -979,6 +1064,8 @@ static void fold_free(FoldSys &F)
     if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
+    if (F.itemsA) cudaFree(F.itemsA); if (F.recA) cudaFree(F.recA); if (F.uniA) cudaFree(F.uniA); if (F.ucoefA) cudaFree(F.ucoefA);
+    F.itemsA = nullptr; F.recA = nullptr; F.uniA = nullptr; F.ucoefA = nullptr;
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t};
     for (FVec *a : vs) fold_free_vec(*a);
     F.built = false; F.have_bicg = false;

@@ -840,6 +840,47 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         double cnt[2];
         if ((rc = fetch_results(ctx, SL_TMP, 2, cnt))) return rc;
         F.cells_uniform = (long long)(cnt[0] + 0.5); F.cells_general = (long long)(cnt[1] + 0.5);
+        // Static load balance of the operator apply.  The item-loop kernels hand item i to block i mod grid.  For the apply kernel a
+        // tile with streamed coefficients or partial validity costs several times a constant-coefficient interior tile, and where those
+        // sit in index order decides how many of them one block draws (measured: 296 -> 248 us per apply at 384^3).  The apply therefore
+        // walks a SECOND list: slow tiles first, then the fast ones, each class in index order -- every block gets the same number of
+        // tiles of each class +-1 for any grid size, and the order is fixed, so its reduction stays deterministic.  The streaming vector
+        // kernels keep the index-ordered list: all tiles cost them the same, and neighbouring blocks on neighbouring tiles share DRAM
+        // pages (the class order cost them 25 % at 384^3).
+        F.IA = I;
+        if (F.nitems > 1 && !getenv("PB200_NO_REORDER")) {
+            const int n = F.nitems;
+            std::vector<int> hi(n), ho;
+            std::vector<unsigned char> hu(n);
+            std::vector<TileRec> hr(n);
+            CUDA_TRY(ctx, cudaMemcpy(hi.data(), F.items, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(hu.data(), F.uni, (size_t)n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(hr.data(), F.rec, sizeof(TileRec) * (size_t)n, cudaMemcpyDeviceToHost));
+            ho.reserve(n);
+            for (int cls = 0; cls < 2; ++cls)
+                for (int i = 0; i < n; ++i) {
+                    if (hr[i].f >= 2) continue;     // (w chunks are not the dense apply's business)
+                    const int c = ((hu[i] & 1) && hr[i].full) ? 1 : 0;
+                    if (c == cls) ho.push_back(hi[i]);
+                }
+            const int na = (int)ho.size();
+            if (na > 0) {
+                CUDA_TRY(ctx, cudaMalloc((void **)&F.itemsA, sizeof(int) * (size_t)na));
+                CUDA_TRY(ctx, cudaMalloc((void **)&F.recA, sizeof(TileRec) * (size_t)na));
+                CUDA_TRY(ctx, cudaMalloc((void **)&F.uniA, (size_t)na));
+                CUDA_TRY(ctx, cudaMalloc((void **)&F.ucoefA, sizeof(double) * PB_MAXD * (size_t)na));
+                CUDA_TRY(ctx, cudaMemcpy(F.itemsA, ho.data(), sizeof(int) * (size_t)na, cudaMemcpyHostToDevice));
+                Items &A = F.IA;
+                A.it = F.itemsA; A.n = na;
+                kf_tile_records<<<(na + 255) / 256, 256, 0, ctx->stream>>>(A, F.recA); LAUNCH_CHECK(ctx);
+                A.rec = F.recA; A.uni = F.uniA; A.ucoef = F.ucoefA;
+                int ga = na; if (ga > ctx->sm_count * 8) ga = ctx->sm_count * 8;
+                DISPATCH_N(g.N, (kf_tile_meta<N><<<ga, FCH, 0, ctx->stream>>>(g, d, A, F.uniA, F.ucoefA, getenv("PB200_EXACT_TILES") ? 0.0 : 1e-12, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
+                LAUNCH_CHECK(ctx);
+                double cnt2[2];
+                if ((rc = fetch_results(ctx, SL_TMP, 2, cnt2))) return rc;
+            }
+        }
     }
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v};
     for (FVec *v : vs) if ((rc = fold_alloc_vec(s, v))) return rc;
@@ -952,7 +993,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     double *slotD = res + (mode == 3 ? FS_TS_D : FS_SIG_D), *slotB = res + (mode == 3 ? FS_TS_B : FS_SIG_B);
     prof_mark(ctx, PB_PROF_APPLY);
     ctx->apply_launches++;
-#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.I, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop)))
+#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.IA, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop)))
     if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else FOLD_DENSE(3);
 #undef FOLD_DENSE
     LAUNCH_CHECK(ctx);
@@ -970,7 +1011,8 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
 
 // Krylov solve of the folded system.  In: s->b (reference rows, known parts eliminated), s->x (initial guess on the free sets).
 // Out: s->x.  The stopping test ||r^|| <= max(rtol ||b^||, atol) is on the block-Jacobi-scaled residual.
-static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, const GuessSpec gsp[3], int *iters, int *conv, double *rnorm_out, double *bnorm_out)
+static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, const GuessSpec gsp[3], bool dense_done, int *iters, int *conv, double *rnorm_out,
+                      double *bnorm_out)
 {
     pb200_ctx *ctx = s->ctx;
     FoldSys &F = s->F;
@@ -987,13 +1029,15 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
     const int gb = band_grid(F.d.nBown);
     const bool band = F.d.has_w && F.d.nBown > 0;
     // b^ and x^0
-    kf_to_scaled_dense<<<wave_grid(s, kf_to_scaled_dense), FCH, 0, ctx->stream>>>(F.d, I, s->b, F.b); LAUNCH_CHECK(ctx);
+    // (dense_done: kf_rhs_dense has written b^ and x^0 on the active tiles; only the rows whose known part came afterwards are refreshed)
+    if (!dense_done) { kf_to_scaled_dense<<<wave_grid(s, kf_to_scaled_dense), FCH, 0, ctx->stream>>>(F.d, I, s->b, F.b); LAUNCH_CHECK(ctx); }
+    else if (s->nK > 0) { kf_to_scaled_list<<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(F.d, s->Kcell, s->nK, s->b, F.b); LAUNCH_CHECK(ctx); }
     if (band) { kf_to_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->b, F.b); LAUNCH_CHECK(ctx); }
     const bool cg = method == PB200_KRYLOV_CG;
     static_assert(FS_RR0 == FS_BB + 1, "kf_resid publishes the pair (bb, rr0)");
     const bool warm = gsp[0].m > 0;
     if (warm) {
-        kf_guess_dense<<<wave_grid(s, kf_guess_dense), FCH, 0, ctx->stream>>>(F.d, I, gsp[0], gsp[1], F.x); LAUNCH_CHECK(ctx);
+        if (!dense_done) { kf_guess_dense<<<wave_grid(s, kf_guess_dense), FCH, 0, ctx->stream>>>(F.d, I, gsp[0], gsp[1], F.x); LAUNCH_CHECK(ctx); }
         if (band) { kf_guess_band<<<gb, 128, 0, ctx->stream>>>(F.d, gsp[0], gsp[1], gsp[2], F.x); LAUNCH_CHECK(ctx); }
         if ((rc = fold_apply(s, F.x, F.v, F.v, 0))) return rc;
         kf_resid<<<wave_grid(s, kf_resid), FCH, 0, ctx->stream>>>(I, F.b, F.v, 1, F.r, F.p, F.r0, cg ? 0 : 1, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
@@ -1246,6 +1290,37 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         }
         return gsx;
     };
+    // folded system (cached per coefficient set and mask set)
+    if (use_fold && (!s->F.built || s->F.key[0] != ac.cV || s->F.key[1] != ac.c || s->F.key[2] != ac.c2)) { if ((rc = fold_build(s, ac))) return rc; }
+    // steps without an explicit operator part on the folded path: b, b^ and the scaled initial guess come out of ONE pass over the active
+    // tiles (kf_rhs_dense) instead of k_rhs_* + kf_to_scaled_dense + kf_guess_dense over all cells
+    const bool fused_rhs = use_fold && !getenv("PB200_NO_FUSED_RHS") && (!cn || (sc.ce == sc.c && !getenv("PB200_NO_FUSED_CN")));
+    GuessSpec fgs[3];
+    if (use_fold) {
+        fgs[0] = guess_spec(s->Tw[0], s->histW[0]);
+        fgs[1] = diph ? guess_spec(s->Tw[1], s->histW[1]) : fgs[0];
+        fgs[2] = diph ? guess_spec(s->Tg[1], s->histG[1]) : guess_spec(s->Tg[0], s->histG[0]);
+    }
+    auto rhs_fused = [&]() -> int {
+        FoldSys &F = s->F;
+        RhsSrc S;
+        for (int ph = 0; ph < 2; ++ph) { S.f0[ph] = f[ph][0]; S.f1[ph] = f[ph][1]; S.Tw[ph] = s->Tw[ph]; }
+        S.m[0] = s->m1; S.m[1] = diph ? s->m2 : s->m1;
+        FVec vexp; for (int q = 0; q < 3; ++q) vexp.f[q] = nullptr;
+        if (cn) {
+            // Crank-Nicolson: explicit part = M^ x^n with x^n = L^T T^n (kf_rhs_dense); F.p and F.v are free until the solve starts
+            auto cur = [&](double *T) { GuessSpec q; q.m = 1; for (int j = 0; j < PB_MAXHIST; ++j) { q.T[j] = nullptr; q.c[j] = 0.0; } q.T[0] = T; q.c[0] = 1.0; return q; };
+            const GuessSpec c0 = cur(s->Tw[0]), c1 = diph ? cur(s->Tw[1]) : c0, cw = diph ? cur(s->Tg[1]) : cur(s->Tg[0]);
+            const bool band = F.d.has_w && F.d.nBown > 0;
+            kf_guess_dense<<<wave_grid(s, kf_guess_dense), FCH, 0, ctx->stream>>>(F.d, F.I, c0, c1, F.p); LAUNCH_CHECK(ctx);
+            if (band) { kf_guess_band<<<band_grid(F.d.nBown), 128, 0, ctx->stream>>>(F.d, c0, c1, cw, F.p); LAUNCH_CHECK(ctx); }
+            int rc2;
+            if ((rc2 = fold_apply(s, F.p, F.v, F.v, 0))) return rc2;
+            vexp = F.v;
+        }
+        kf_rhs_dense<<<wave_grid(s, kf_rhs_dense), FCH, 0, ctx->stream>>>(F.d, F.I, sc, S, fgs[0], fgs[1], s->b, F.b, F.x, vexp); LAUNCH_CHECK(ctx);
+        return PB200_OK;
+    };
     // ghost planes of the state (stencil inputs of the explicit part)
     {
         double *fl[4] = {s->Tw[0], s->Tg[0], s->Tw[1], s->Tg[1]};
@@ -1256,12 +1331,22 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         LAUNCH_CHECK(ctx);
         double *fl[1] = {s->gK};
         if ((rc = halo_exchange(ctx, g, fl, 1))) return rc;
-        DISPATCH_N(g.N, (k_rhs_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Tw[0], s->Tg[0], s->ufix1, s->gK, f[0][0],
-                                                                               f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr, 1)));
-        LAUNCH_CHECK(ctx);
-        if (s->nK > 0) {
+        if (fused_rhs) { if ((rc = rhs_fused())) return rc; }
+        else {
+            DISPATCH_N(g.N, (k_rhs_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Tw[0], s->Tg[0], s->ufix1, s->gK, f[0][0],
+                                                                                   f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr, 1)));
+            LAUNCH_CHECK(ctx);
+        }
+        if (fused_rhs && cn) {   // the listed rows in full: unfolded explicit part + known part
+            if (s->nK > 0) {
+                DISPATCH_N(g.N, (k_rhs_mono<N><<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Tw[0], s->Tg[0], s->ufix1, s->gK, f[0][0],
+                                                                                        f[0][1], gsp[0], gsp[1], s->b.f[0], s->nf == 2 ? s->b.f[1] : nullptr, 0,
+                                                                                        s->Kcell, s->nK)));
+                LAUNCH_CHECK(ctx);
+            }
+        } else if (s->nK > 0) {
             DISPATCH_N(g.N, (k_rhs_known_mono<N><<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(g, s->p1, s->sp, sc, s->m1, s->Kcell, s->nK, s->ufix1, s->gK, s->b.f[0],
-                                                                                              s->nf == 2 ? s->b.f[1] : nullptr)));
+                                                                                              s->nf == 2 ? s->b.f[1] : nullptr, fused_rhs ? 1 : 0, gsp[0], gsp[1])));
             LAUNCH_CHECK(ctx);
         }
         if (!use_fold) {   // (the folded path evaluates the guess itself, in scaled unknowns)
@@ -1271,13 +1356,23 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         }
     } else {
         if (gsp[0].arr) { double *fl[1] = {s->gS[0]}; if ((rc = halo_exchange(ctx, g, fl, 1))) return rc; }
-        DISPATCH_N(g.N, (k_rhs_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
-                                                                               s->Tg[1], s->ufix1, s->ufix2, f[0][0], f[0][1], f[1][0], f[1][1], gsp[0],
-                                                                               gsp[1], s->b.f[0], s->b.f[1], s->b.f[2], 1)));
-        LAUNCH_CHECK(ctx);
-        if (s->nK > 0) {
+        if (fused_rhs) { if ((rc = rhs_fused())) return rc; }
+        else {
+            DISPATCH_N(g.N, (k_rhs_diph<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
+                                                                                   s->Tg[1], s->ufix1, s->ufix2, f[0][0], f[0][1], f[1][0], f[1][1], gsp[0],
+                                                                                   gsp[1], s->b.f[0], s->b.f[1], s->b.f[2], 1)));
+            LAUNCH_CHECK(ctx);
+        }
+        if (fused_rhs && cn) {   // the listed rows in full: unfolded explicit part + known part
+            if (s->nK > 0) {
+                DISPATCH_N(g.N, (k_rhs_diph<N><<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Tw[0], s->Tg[0], s->Tw[1],
+                                                                                        s->Tg[1], s->ufix1, s->ufix2, f[0][0], f[0][1], f[1][0], f[1][1], gsp[0],
+                                                                                        gsp[1], s->b.f[0], s->b.f[1], s->b.f[2], 0, s->Kcell, s->nK)));
+                LAUNCH_CHECK(ctx);
+            }
+        } else if (s->nK > 0) {
             DISPATCH_N(g.N, (k_rhs_known_diph<N><<<(s->nK + 127) / 128, 128, 0, ctx->stream>>>(g, s->p1, s->p2, s->sp, sc, s->m1, s->m2, s->Kcell, s->nK, s->ufix1, s->ufix2,
-                                                                                              gsp[0], s->b.f[0], s->b.f[1], s->b.f[2])));
+                                                                                              gsp[0], s->b.f[0], s->b.f[1], s->b.f[2], fused_rhs ? 1 : 0, gsp[1])));
             LAUNCH_CHECK(ctx);
         }
         if (!use_fold) {
@@ -1287,8 +1382,6 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         }
     }
     if (use_fold) {
-        // folded system (cached per coefficient set and mask set)
-        if (!s->F.built || s->F.key[0] != ac.cV || s->F.key[1] != ac.c || s->F.key[2] != ac.c2) { if ((rc = fold_build(s, ac))) return rc; }
     } else if (memcmp(&ac, &s->diag_key, sizeof(ac)) != 0) {   // Jacobi diagonal (cached per coefficient set)
         if (!diph) {
             DISPATCH_N(g.N, (k_diag_mono<N><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->p1, s->sp, ac, s->m1, s->dinv.f[0], s->nf == 2 ? s->dinv.f[1] : nullptr)));
@@ -1309,11 +1402,7 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     int it = 0, converged = 0;
     double rnorm = 0.0, bnorm = 0.0;
     if (use_fold) {
-        GuessSpec gsp[3];
-        gsp[0] = guess_spec(s->Tw[0], s->histW[0]);
-        gsp[1] = diph ? guess_spec(s->Tw[1], s->histW[1]) : gsp[0];
-        gsp[2] = diph ? guess_spec(s->Tg[1], s->histG[1]) : guess_spec(s->Tg[0], s->histG[0]);
-        if ((rc = fold_solve(s, method, o, gsp, &it, &converged, &rnorm, &bnorm))) return rc;
+        if ((rc = fold_solve(s, method, o, fgs, fused_rhs, &it, &converged, &rnorm, &bnorm))) return rc;
     } else {
     // bnorm
     k_dots<1><<<grid, RED_THREADS, 0, ctx->stream>>>(g, s->nf, s->b, s->b, s->b, s->b, ctx->d_partials, res + SL_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
