@@ -199,6 +199,10 @@ typedef struct {
  * rows, solves the reduced system, stores the new state on the device (solve_system!, src/solver.jl:158-188:
  * removed DOFs are exactly 0).  opts / stats may be NULL.                                                      */
 int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const pb200_krylov_opts *opts, pb200_step_stats *stats);
+/* check_convergence (src/convergence.jl:59-93) without a host round trip of the state: volume-weighted L^p norms (p > 0, or INFINITY) of
+ * u_ana - T_omega of bulk field `phase` (0, or 1 for the second phase of a diphasic solver), u_ana[n] evaluated by the caller at C_omega;
+ * out = {all fluid cells (full + cut), full, cut, empty}, classes by capacity.cell_types.  relative != 0: relative_lp_norm.                */
+int pb200_solver_error_norms(pb200_solver *s, int phase, const double *u_ana, double p, int relative, double out[4]);
 int pb200_solver_destroy(pb200_solver *s);
 
 #ifdef __cplusplus

@@ -145,9 +145,11 @@ def nobody_capacity(mesh):
 # --------------------------------------------------------------------------------------------
 def delta_m(n):
     """Backward difference with the reference's quirk: ``D[n, n] = 0`` (operators.jl:9)."""
-    D = sp.diags([np.ones(n), -np.ones(n - 1)], [0, -1], format="lil")
-    D[n - 1, n - 1] = 0.0
-    return D.tocsr()
+    D = sp.diags([np.ones(n), -np.ones(n - 1)], [0, -1], format="csr")
+    # Julia's `D[n, n] = 0.0` on a SparseMatrixCSC keeps the entry STORED with value zero (it matters only for NaN propagation,
+    # solve_darcy_velocity: NaN * stored 0.0 = NaN) -- recalled SparseArrays behaviour, see SURVEY Appendix B
+    D.data[D.indptr[n - 1]:D.indptr[n]][D.indices[D.indptr[n - 1]:D.indptr[n]] == n - 1] = 0.0
+    return D
 
 
 def lift(op1d_list):
@@ -659,7 +661,7 @@ def n_solves(dt, Tend):
 # --------------------------------------------------------------------------------------------
 # check_convergence (src/convergence.jl:4-93) -- used only to pin the oracle on the reference's asserts
 # --------------------------------------------------------------------------------------------
-def check_convergence(u_analytical, x, cap, p=2):
+def check_convergence(u_analytical, x, cap, p=2, relative=False):
     C = cap.C_omega
     u_ana = np.asarray(u_analytical(*[C[:, d] for d in range(cap.N)]), float) * np.ones(len(C))
     u_num = x[:len(x) // 2] if len(x) == 2 * len(C) else x
@@ -668,6 +670,43 @@ def check_convergence(u_analytical, x, cap, p=2):
 
     def lp(mask):
         if p == np.inf:
-            return float(np.max(np.abs(err[mask]), initial=0.0))
-        return float((np.sum(np.abs(err[mask]) ** p * cap.V[mask]) / np.sum(cap.V)) ** (1.0 / p))
+            if not relative:
+                return float(np.max(np.abs(err[mask]), initial=0.0))
+            # errors[idx] / u_ana[idx] on two Julia vectors is err * pinv(u_ana), a matrix (src/convergence.jl:19)
+            with np.errstate(all="ignore"):
+                return float(np.max(np.abs(err[mask]), initial=0.0) * np.max(np.abs(u_ana[mask]), initial=0.0) / np.sum(u_ana[mask] ** 2))
+        with np.errstate(all="ignore"):
+            e = np.abs(err[mask] / u_ana[mask]) if relative else np.abs(err[mask])
+            return float((np.sum(e ** p * cap.V[mask]) / np.sum(cap.V)) ** (1.0 / p))
     return lp((ct == 1) | (ct == -1)), lp(ct == 1), lp(ct == -1), lp(ct == 0)
+
+
+# --------------------------------------------------------------------------------------------
+# Darcy (src/solver/darcy.jl:1-40): steady diffusion system + u = -grad p with NaN-masked pressures
+# --------------------------------------------------------------------------------------------
+def solve_darcy_velocity(x, op, cap):
+    """u = -grad(op, p) with p_omega = NaN on empty cells and p_gamma = NaN on empty and full cells (darcy.jl:26-40).
+    NaN propagation follows Julia's STRUCTURAL sparsity (recalled SparseArrays behaviour, SURVEY Appendix B: `spdiagm`, `D[n, n] = 0.0`,
+    `kron`, `*` and `-` all keep numerically zero entries stored, and NaN * stored 0.0 = NaN), whereas SciPy prunes zeros while it builds
+    G and H.  The values therefore come from the pruned operators applied to the NaN-free pressures, and an entry is NaN exactly when
+    a structurally present coefficient of its row -- (i, i) and (i, i - 1) of the lifted backward difference, both in G and in H --
+    meets a NaN."""
+    n = len(x) // 2
+    po, pg = np.array(x[:n], float), np.array(x[n:], float)
+    ct = cap.cell_types
+    bad_o = ct == 0
+    bad_g = (ct == 0) | (ct == 1)
+    po[bad_o] = 0.0
+    pg[bad_g] = 0.0
+    u = -grad(op, np.concatenate([po, pg]))
+    bad = (bad_o | bad_g).astype(float)
+    dims = cap.mesh.dims
+    N = len(dims)
+    for d in range(N):
+        ops = []
+        for i in range(N):
+            m = dims[i] + 1
+            ops.append(sp.diags([np.ones(m), np.ones(m - 1)], [0, -1], format="csr") if i == d else sp.identity(m, format="csr"))
+        P = lift(ops)
+        u[d * n:(d + 1) * n][(P @ bad) > 0] = np.nan
+    return u

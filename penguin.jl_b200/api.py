@@ -26,6 +26,7 @@ __all__ = [
     "BorderConditions", "InterfaceConditions", "Solver", "DiffusionSteadyMono", "solve_DiffusionSteadyMono_",
     "DiffusionSteadyDiph", "solve_DiffusionSteadyDiph_", "DiffusionUnsteadyMono", "solve_DiffusionUnsteadyMono_",
     "DiffusionUnsteadyDiph", "solve_DiffusionUnsteadyDiph_", "Steady", "Unsteady", "Monophasic", "Diphasic", "Diffusion",
+    "DarcyFlow", "solve_DarcyFlow_", "DarcyFlowUnsteady", "solve_DarcyFlowUnsteady_", "solve_darcy_velocity", "check_convergence",
 ]
 
 Steady, Unsteady = "Steady", "Unsteady"
@@ -687,3 +688,62 @@ def solve_DiffusionUnsteadyDiph_(s, phase1, phase2, Δt, Tₑ, bc_b, ic, scheme,
         if k % states_stride == 0:
             s.states.append(s.x)
     return s
+
+
+# ---- Darcy (src/solver/darcy.jl:1-89): the diffusion systems under another name + the velocity u = -∇p ---------------------------
+def DarcyFlow(phase, bc_b, bc_i):
+    """src/solver/darcy.jl:1-15 -- the steady monophasic diffusion system (A_mono_stead_diff / b_mono_stead_diff + border rows)."""
+    return DiffusionSteadyMono(phase, bc_b, bc_i)
+
+
+def solve_DarcyFlow_(s, method="cg", algorithm=None, **kw):
+    """src/solver/darcy.jl:17-24"""
+    solve_DiffusionSteadyMono_(s, method=method, algorithm=algorithm, **kw)
+    s.states.append(s.x)
+    return s
+
+
+def solve_darcy_velocity(solver, Fluide, state_i=1):
+    """src/solver/darcy.jl:26-40: ``u = -∇(operator, p)`` of a stored state (1-based ``state_i`` as in the reference), with the
+    pressures of cells that do not carry them set to NaN first: p_ω on empty cells, p_γ on empty and on full cells."""
+    ct = Fluide.capacity.cell_types
+    st = np.array(solver.states[state_i - 1], float)
+    n = st.size // 2
+    pω, pγ = st[:n].copy(), st[n:].copy()
+    pω[ct == 0] = np.nan
+    pγ[ct == 0] = np.nan
+    pγ[ct == 1] = np.nan
+    return -grad(Fluide.operator, np.concatenate([pω, pγ]))
+
+
+def DarcyFlowUnsteady(phase, bc_b, bc_i, Δt, Tᵢ, scheme):
+    """src/solver/darcy.jl:45-58"""
+    return DiffusionUnsteadyMono(phase, bc_b, bc_i, Δt, Tᵢ, scheme)
+
+
+def solve_DarcyFlowUnsteady_(s, phase, Δt, Tₑ, bc_b, bc_i, scheme, method="cg", algorithm=None, **kw):
+    """src/solver/darcy.jl:60-89 (the time loop of solve_DiffusionUnsteadyMono! under another name)"""
+    return solve_DiffusionUnsteadyMono_(s, phase, Δt, Tₑ, bc_b, bc_i, scheme, method=method, algorithm=algorithm, **kw)
+
+
+# ---- check_convergence (src/convergence.jl:4-93) ------------------------------------------------------------------------------
+def check_convergence(u_analytical, solver, capacity, p=2, relative=False, phase=0, verbose=False):
+    """Volume-weighted error norms between ``u_analytical`` (evaluated on the host at ``capacity.C_ω``, as the reference does)
+    and the bulk field of the solver's CURRENT device state, reduced on the device in one pass (no host copy of the state).
+    Returns ``(u_ana, u_num, global_err, full_err, cut_err, empty_err)`` like the reference; ``u_num`` is ``None`` unless the
+    solver's host copy ``solver.x`` exists (it is not downloaded for this).  ``phase`` (extension): 1 = second bulk field of a
+    diphasic solver (the reference handles monophasic solvers only: ``solver.x[1:end÷2]``, src/convergence.jl:73)."""
+    Cω = capacity.C_ω
+    N = capacity.N
+    u_ana = np.ascontiguousarray(np.asarray(u_analytical(*[Cω[:, d] for d in range(N)]), float) * np.ones(Cω.shape[0]))
+    out = (C.c_double * 4)()
+    L.check(L.lib().pb200_solver_error_norms(solver._h, int(phase), _dp(u_ana), float(p), 1 if relative else 0,
+                                             C.cast(out, L.dp)), solver._ctx.h)
+    g, fu, cu, em = (float(v) for v in out)
+    if verbose:
+        print(f"All cells L{p} norm        = {g}\nFull cells L{p} norm   = {fu}\nCut cells L{p} norm    = {cu}\nEmpty cells L{p} norm  = {em}")
+    u_num = None
+    if solver.x is not None:
+        n = Cω.shape[0]
+        u_num = np.asarray(solver.x)[2 * phase * n:(2 * phase + 1) * n]
+    return u_ana, u_num, g, fu, cu, em

@@ -224,3 +224,40 @@ __global__ void k_count(Grid g, const unsigned char *__restrict__ m1, const unsi
     }
     block_reduce_publish<2>(v, partials, results, counter);
 }
+
+
+// check_convergence (src/convergence.jl:4-93): volume-weighted error norms of u_ana - T_omega by cell class (full / cut / empty), ONE fused
+// reduction on the device state.  Classes by capacity.cell_types (1, -1, 0).  sums[c] = sum_class |e|^p V (finite p; e = err or err / u_ana),
+// or sum_class u_ana^2 (p = Inf, relative); sums[3] = sum(V) over every cell; mx[c] = max_class |err|, mx[3 + c] = max_class |u_ana| (bit
+// patterns of non-negative doubles order like unsigned integers, so atomicMax keeps the result independent of the block order).
+__global__ void k_err_norms(Grid g, const double *__restrict__ ct, const double *__restrict__ V, const double *__restrict__ ua,
+                            const double *__restrict__ Tw, double p, int relative, int is_inf, unsigned long long *__restrict__ mx,
+                            double *partials, double *results, unsigned *counter)
+{
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    double me[3] = {0.0, 0.0, 0.0}, mu[3] = {0.0, 0.0, 0.0};
+    for (int64_t l = g.plane + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < g.plane + g.nown; l += (int64_t)gridDim.x * blockDim.x) {
+        const double c = ct[l], Vi = V[l], u = ua[l], e = u - Tw[l];
+        v[3] += Vi;
+        const int cls = c == 1.0 ? 0 : (c == -1.0 ? 1 : (c == 0.0 ? 2 : -1));
+        if (cls < 0) continue;
+        double add = 0.0;
+        if (!is_inf) add = pow(fabs(relative ? e / u : e), p) * Vi;
+        else if (relative) add = u * u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k == cls) { v[k] += add; me[k] = fmax(me[k], fabs(e)); mu[k] = fmax(mu[k], fabs(u)); }
+    }
+    if (is_inf) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { me[k] = fmax(me[k], __shfl_xor_sync(0xffffffffu, me[k], o)); mu[k] = fmax(mu[k], __shfl_xor_sync(0xffffffffu, mu[k], o)); }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(mx + k, (unsigned long long)__double_as_longlong(me[k]));
+                atomicMax(mx + 3 + k, (unsigned long long)__double_as_longlong(mu[k]));
+            }
+        }
+    }
+    block_reduce_publish<4>(v, partials, results, counter);
+}

@@ -511,6 +511,46 @@ extern "C" int pb200_solver_get_state(pb200_solver *s, double *x)
     return PB200_OK;
 }
 
+// check_convergence (src/convergence.jl:59-93) on the device state: out[0..3] = norms over all fluid (full + cut), full, cut, empty cells
+extern "C" int pb200_solver_error_norms(pb200_solver *s, int phase, const double *u_ana, double p, int relative, double out[4])
+{
+    if (!s || !u_ana || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    const int np = s->sp.phase_type == PB200_DIPH ? 2 : 1;
+    if (phase < 0 || phase >= np) return set_err(ctx, PB200_EINVAL, "phase index out of range");
+    const bool is_inf = std::isinf(p);
+    if (!is_inf && !(p > 0.0)) return set_err(ctx, PB200_EINVAL, "the norm order p must be positive");
+    if (is_inf && ctx->nranks > 1) return set_err(ctx, PB200_EUNSUPPORTED, "L-infinity error norms are rank-local: not available on a slab-partitioned grid");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const pb200_capacity *cap = (phase == 0 ? s->o1 : s->o2)->cap;
+    double *ua = nullptr;
+    unsigned long long *mx = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ua, g.nloc))) return rc;
+    if ((rc = upload_owned(ctx, g, ua, u_ana))) return rc;
+    CUDA_TRY(ctx, cudaMalloc((void **)&mx, sizeof(unsigned long long) * 6));
+    CUDA_TRY(ctx, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * 6, ctx->stream));
+    k_err_norms<<<sgrid(ctx, g.nown), RED_THREADS, 0, ctx->stream>>>(g, cap->ct, cap->V, ua, s->Tw[phase], p, relative ? 1 : 0, is_inf ? 1 : 0, mx, ctx->d_partials,
+                                                                    ctx->d_results + SL_TMP, ctx->d_counter);
+    LAUNCH_CHECK(ctx);
+    if ((rc = allreduce_results(ctx, SL_TMP, 4))) return rc;
+    double sums[4], hm[6];
+    if ((rc = fetch_results(ctx, SL_TMP, 4, sums))) return rc;
+    CUDA_TRY(ctx, cudaMemcpy(hm, mx, sizeof(hm), cudaMemcpyDeviceToHost));   // (bit patterns of doubles)
+    cudaFree(mx);
+    dev_free(ua);
+    auto cls = [&](int a, int b) -> double {   // class a (and b): the reference's lp_norm / relative_lp_norm
+        if (!is_inf) { const double S = sums[a] + (b >= 0 ? sums[b] : 0.0); return pow(S / sums[3], 1.0 / p); }
+        const double me = b >= 0 ? fmax(hm[a], hm[b]) : hm[a], mu = b >= 0 ? fmax(hm[3 + a], hm[3 + b]) : hm[3 + a];
+        if (!relative) return me;
+        // errors[idx] / u_ana[idx] on two Julia VECTORS is err * pinv(u_ana) (a matrix): max |err_i u_j| / sum u^2 (src/convergence.jl:19)
+        return me * mu / (sums[a] + (b >= 0 ? sums[b] : 0.0));
+    };
+    out[0] = cls(0, 1); out[1] = cls(0, -1); out[2] = cls(1, -1); out[3] = cls(2, -1);
+    return PB200_OK;
+}
+
 extern "C" int pb200_solver_get_state_async(pb200_solver *s, double *x)
 {
     if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
