@@ -981,18 +981,18 @@ __global__ void __launch_bounds__(FCH, 4) kf_rhs_dense(FoldDev fd, Items I, Step
         for (int k = 0; k < FU; ++k) {
             s[k] = 0.0; v[k] = 0.0; gs[k] = 0.0; ex[k] = 0.0;
             if (ok[k]) {
+                // every load of the cell is issued unconditionally (one round trip): the mask and the scale only select afterwards
                 const long long i = idx[k];
                 s[k] = scf[i];
+                const bool fr = (m[i] & MB_FREE) != 0;
+                const double V = Vf[i], T = Tw[i], q0 = fa0 ? fa0[i] : fc0, q1 = fa1 ? fa1[i] : fc1;
                 if (ve) ex[k] = ve[i];
-                if (m[i] & MB_FREE) {
-                    const double V = Vf[i];
-                    v[k] = cT * V * Tw[i] + V * (sc.wf0 * (fa0 ? fa0[i] : fc0) + sc.wf1 * (fa1 ? fa1[i] : fc1));
-                }
-                if (s[k] != 0.0) {
+                double gsum = 0.0;
 #pragma unroll
-                    for (int j = 0; j < PB_MAXHIST; ++j)
-                        if (j < g0.m) gs[k] += (f1 ? g1.c[j] : g0.c[j]) * (f1 ? g1.T[j] : g0.T[j])[i];
-                }
+                for (int j = 0; j < PB_MAXHIST; ++j)
+                    if (j < g0.m) gsum += (f1 ? g1.c[j] : g0.c[j]) * (f1 ? g1.T[j] : g0.T[j])[i];
+                v[k] = fr ? cT * V * T + V * (sc.wf0 * q0 + sc.wf1 * q1) : 0.0;
+                gs[k] = s[k] != 0.0 ? gsum : 0.0;
             }
         }
 #pragma unroll
