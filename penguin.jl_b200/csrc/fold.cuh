@@ -59,7 +59,7 @@ struct FVec { double *f[3]; };   // f[0], f[1]: dense bulk fields; f[2]: compact
 // unknown are listed; each carries a precomputed record so that no index arithmetic beyond shifts happens in the kernels.
 #define FU 4
 #ifndef PB_APPLY_GP
-#define PB_APPLY_GP(N) ((N) == 3 ? 2 : 4)   // cells of a general tile in flight per thread in kf_apply_dense
+#define PB_APPLY_GP(N) 2   // cells of a general tile in flight per thread in kf_apply_dense (4: more registers, no gain measured)
 #endif
 #define FTILE (FCH * FU)
 struct __align__(16) TileRec {
@@ -142,11 +142,15 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
 }
 
 // result slots of the folded Krylov loops (dense-part and band-part partial sums are adjacent: one allreduce covers both)
-// (rho, rr, rho_band) triples live in two ping-pong groups {0,1,2} and {3,4,5}: one allreduce of 3 doubles publishes a new triple
-enum { FS_PAIR0 = 0, FS_PAIR1 = 3, FS_SIG_D = 6, FS_SIG_B = 7, FS_TS_D = 8, FS_TT_D = 9, FS_TS_B = 10, FS_TT_B = 11, FS_BB = 12, FS_RR0 = 13, FS_ITERS = 14, FS_TMP = 15 };
-#define FS_TRIPLE(p) (3 * (p))
-// rho of the triple at slot sl: with the band preconditioner rho = (r, r) + (r_B, z_B - r_B), the second part in slot sl + 2
-__device__ __forceinline__ double rho_at(const double *res, int sl) { return res[sl] + res[sl + 2]; }
+// (rho, rr, rho_band, rho_poly_band) groups live in two ping-pong sets {0..3} and {4..7}: one allreduce of 4 doubles publishes a new group
+enum { FS_PAIR0 = 0, FS_PAIR1 = 4, FS_SIG_D = 8, FS_SIG_B = 9, FS_TS_D = 10, FS_TT_D = 11, FS_TS_B = 12, FS_TT_B = 13, FS_BB = 14, FS_RR0 = 15, FS_ITERS = 16, FS_TMP = 17 };
+#define FS_TRIPLE(p) (4 * (p))
+#define FS_NGROUP 4
+// rho of the group at slot sl = (r, z) with z = q(M^) r + (q_B(M^_BB) - 1) r_B:
+//   [sl]     (r, q(M^) r), dense part of the last polynomial step -- (r, r) without the polynomial preconditioner (q = 1),
+//   [sl + 2] (r_B, z_B - r_B), the band preconditioner's part (kf_band_poly),
+//   [sl + 3] the band kernel's share of (r, q(M^) r) (0 without the polynomial);           [sl + 1] is ||r||^2 (stopping test)
+__device__ __forceinline__ double rho_at(const double *res, int sl) { return res[sl] + res[sl + 2] + res[sl + 3]; }
 
 // device-side stopping test: the Krylov kernels of an iteration turn into no-ops once ||r||^2 (slot `sl_rr`) is below the
 // tolerance, so the host may queue several iterations between two looks at the residual without doing extra work
@@ -486,10 +490,12 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
 
 // ---- operator ---------------------------------------------------------------------------------------------------------------
 // dense part: y = x + sum_d off_d[l] x[l-s] + off_d[l+s] x[l+s] on the active chunks of each bulk field.
-// MODE 0: no dot; 1: publish (x, y); 2: publish (aux, y); 3: publish (y, x), (y, y)
+// MODE 0: no dot; 1: publish (x, y); 2: publish (aux, y); 3: publish (y, x), (y, y);
+// MODE 4: one step of the polynomial preconditioner, y = pc.r aux + pc.z x + pc.A (M^ x), publish (aux, y)   (aux = the residual)
+struct PolyCoef { double r, z, A; };
 template <int N, int MODE>
-__global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items I, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
-                                                      const double *res, StopCrit stop)
+__global__ void __launch_bounds__(FCH, 4) kf_apply_dense(Grid g, FoldDev fd, Items I, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
+                                                      const double *res, StopCrit stop, PolyCoef pc)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
@@ -525,7 +531,7 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
 #pragma unroll
                 for (int k = 0; k < FU; ++k) { yn[k][0] = p0[k * ks - I.ld0]; yn[k][1] = p0[k * ks + I.ld0]; }
             }
-            if (MODE == 2) {
+            if (MODE == 2 || MODE == 4) {
 #pragma unroll
                 for (int k = 0; k < FU; ++k) avv[k] = af[l0 + k * ks];
             }
@@ -548,9 +554,10 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
             for (int k = 0; k < FU; ++k) {
                 double acc = col[k + 1] + cx * (lf[k] + rt[k]) + ck * (col[k] + col[k + 2]);
                 if (N == 3) acc += cy * (yn[k][0] + yn[k][1]);
+                if (MODE == 4) acc = pc.r * avv[k] + pc.z * col[k + 1] + pc.A * acc;
                 yf[l0 + k * ks] = acc;
                 if (MODE == 1) v[0] += col[k + 1] * acc;
-                if (MODE == 2) v[0] += avv[k] * acc;
+                if (MODE == 2 || MODE == 4) v[0] += avv[k] * acc;
                 if (MODE == 3) { v[0] += acc * col[k + 1]; v[1] += acc * acc; }
             }
             continue;
@@ -580,7 +587,7 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
 #pragma unroll
             for (int j = 0; j < GP; ++j) {
                 xl[j] = xf[l[j]];
-                av[j] = MODE == 2 ? af[l[j]] : 0.0;
+                av[j] = (MODE == 2 || MODE == 4) ? af[l[j]] : 0.0;
 #pragma unroll
                 for (int d = 0; d < N; ++d) {
                     const long long s = g.stride[d];
@@ -596,16 +603,17 @@ __global__ void __launch_bounds__(FCH) kf_apply_dense(Grid g, FoldDev fd, Items 
                 double acc = xl[j];
 #pragma unroll
                 for (int d = 0; d < N; ++d) acc += cm[j][d] * xm[j][d] + cp[j][d] * xp[j][d];
+                if (MODE == 4) acc = pc.r * av[j] + pc.z * xl[j] + pc.A * acc;
                 if (ok[j]) {
                     yf[l[j]] = acc;
                     if (MODE == 1) v[0] += xl[j] * acc;
-                    if (MODE == 2) v[0] += av[j] * acc;
+                    if (MODE == 2 || MODE == 4) v[0] += av[j] * acc;
                     if (MODE == 3) { v[0] += acc * xl[j]; v[1] += acc * acc; }
                 }
             }
         }
     }
-    if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
+    if (MODE == 1 || MODE == 2 || MODE == 4) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
 }
 
@@ -665,7 +673,7 @@ __device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int 
 // band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here
 template <int N, int MODE>
 __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
-                                                     const double *res, StopCrit stop)
+                                                     const double *res, StopCrit stop, PolyCoef pc)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
@@ -683,19 +691,24 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
         band_rows<N, false>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
         if (lane == 0 && live) {
             const double y0p = y.f[0][l], y1p = two ? y.f[1][l] : 0.0;
+            if (MODE == 4) { a0 *= pc.A; a1 *= pc.A; }   // the dense kernel has written pc.r aux + pc.z x + pc.A (dense part of M^ x)
             y.f[0][l] = y0p + a0;
             if (two) y.f[1][l] = y1p + a1;
             double yw = 0.0;
-            if (bo >= 0) { yw = xw + a2; y.f[2][bo] = yw; }
+            if (bo >= 0) {
+                yw = xw + a2;
+                if (MODE == 4) yw = pc.r * aux.f[2][bo] + pc.z * xw + pc.A * yw;
+                y.f[2][bo] = yw;
+            }
             if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
-            if (MODE == 2) v[0] += aux.f[0][l] * a0 + (two ? aux.f[1][l] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
+            if (MODE == 2 || MODE == 4) v[0] += aux.f[0][l] * a0 + (two ? aux.f[1][l] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
             if (MODE == 3) {
                 v[0] += x0 * a0 + x1 * a1 + xw * yw;
                 v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
             }
         }
     }
-    if (MODE == 1 || MODE == 2) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
+    if (MODE == 1 || MODE == 2 || MODE == 4) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
 }
 
@@ -763,6 +776,15 @@ __global__ void kf_band_seed(FoldDev fd, double *out)
                     if (long long i = 0; tile_cell((I), R__, k__, i))
 
 __global__ void __launch_bounds__(FCH) kf_zero(Items I, FVec a) { FV_LOOP(I) a.f[f][i] = 0.0; }
+// deterministic pseudo-random start vector in (-1, 1) (power iteration for the top of the spectrum of M^)
+__global__ void __launch_bounds__(FCH) kf_seed(Items I, FVec a)
+{
+    FV_LOOP(I) {
+        unsigned long long h = (unsigned long long)(i * 3 + f + 1) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
+        a.f[f][i] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
 __global__ void __launch_bounds__(FCH) kf_copy2(Items I, FVec a, FVec b, FVec c) { FV_LOOP(I) { const double v = a.f[f][i]; b.f[f][i] = v; c.f[f][i] = v; } }
 // r = b - q ; publishes (r, r)
 // first residual of a solve, one pass: r = b - q (q == nullptr fields: r = b), copies of r into p (and r0), publishes ((b, b), (r, r))
@@ -822,7 +844,7 @@ __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho,
                                                const int *__restrict__ bord, int nB, StopCrit stop_old, StopCrit stop)
 {
     if (fold_done(res, stop_old)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; res[sl_new + 3] = res[sl_rho + 3]; }
         return;
     }
     // x += alpha p_old belongs to this iteration even when it is the one that converged; the new direction is only needed otherwise
@@ -1078,8 +1100,10 @@ struct FoldSys {
     Items I;                                // every item, index order (vector kernels)
     Items IA;                               // bulk tiles in cost-class order (operator apply)
     int *itemsA = nullptr; TileRec *recA = nullptr; unsigned char *uniA = nullptr; double *ucoefA = nullptr;
-    FVec x, b, r, p, v, r0, s, t;
-    bool have_bicg = false;
+    FVec x, b, r, p, v, r0, s, t, z;
+    bool have_bicg = false, have_z = false;
+    int poly_m = 0;                         // degree of the polynomial preconditioner q(M^) (0: none)
+    double poly_lo = 0.0, poly_hi = 0.0;    // Chebyshev interval of the bulk spectrum
     long long wcap = 0;
     double key[8] = {};   // coefficient set the system was built for
 };
@@ -1097,9 +1121,9 @@ static void fold_free(FoldSys &F)
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
     if (F.itemsA) cudaFree(F.itemsA); if (F.recA) cudaFree(F.recA); if (F.uniA) cudaFree(F.uniA); if (F.ucoefA) cudaFree(F.ucoefA);
     F.itemsA = nullptr; F.recA = nullptr; F.uniA = nullptr; F.ucoefA = nullptr;
-    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t};
+    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t, &F.z};
     for (FVec *a : vs) fold_free_vec(*a);
-    F.built = false; F.have_bicg = false;
+    F.built = false; F.have_bicg = false; F.have_z = false;
 }
 
 static const int PB_NCCL_UINT8 = 1;

@@ -8,6 +8,9 @@
 #include "p2p.cuh"
 #include "fold.cuh"
 
+#ifndef PB200_POLY_DEFAULT
+#define PB200_POLY_DEFAULT 1   // degree of the polynomial preconditioner of the folded CG when PB200_POLY is not set
+#endif
 #define DISPATCH_N(N_, ...)                  \
     do {                                     \
         if ((N_) == 1) { constexpr int N = 1; __VA_ARGS__; } \
@@ -1021,7 +1024,10 @@ static int fold_halo(pb200_solver *s, const FVec &x)
 }
 
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
-static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode, StopCrit stop = StopCrit{0.0, 0.0, -1})
+// mode 4 (one step of the polynomial preconditioner, y = pc.r aux + pc.z x + pc.A M^ x): the partial sums of (aux, y) go to the
+// caller's slots (dense part, band part) and are reduced over the ranks by the caller together with the rest of their group
+static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec &aux, int mode, StopCrit stop = StopCrit{0.0, 0.0, -1},
+                      PolyCoef pc = PolyCoef{0.0, 0.0, 0.0}, int slotD4 = FS_TMP, int slotB4 = FS_TMP + 1)
 {
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
@@ -1030,22 +1036,117 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     if ((rc = fold_halo(s, x))) return rc;
     double *res = ctx->d_results;
     const int grid = fold_grid(s);
-    double *slotD = res + (mode == 3 ? FS_TS_D : FS_SIG_D), *slotB = res + (mode == 3 ? FS_TS_B : FS_SIG_B);
+    double *slotD = res + (mode == 4 ? slotD4 : (mode == 3 ? FS_TS_D : FS_SIG_D)), *slotB = res + (mode == 4 ? slotB4 : (mode == 3 ? FS_TS_B : FS_SIG_B));
     prof_mark(ctx, PB_PROF_APPLY);
     ctx->apply_launches++;
-#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.IA, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop)))
-    if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else FOLD_DENSE(3);
+#define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.IA, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop, pc)))
+    if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else if (mode == 3) FOLD_DENSE(3); else FOLD_DENSE(4);
 #undef FOLD_DENSE
     LAUNCH_CHECK(ctx);
     prof_mark(ctx, PB_PROF_APPLY);
     if (F.d.has_w) {   // also on a rank without band cells: the kernel must refresh its partial-sum slots (to 0) before the in-place reduction
         const int gb = band_wgrid(F.d.nE);
-#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 256, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop)))
-        if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else FOLD_BAND(3);
+#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 256, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop, pc)))
+        if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else if (mode == 3) FOLD_BAND(3); else FOLD_BAND(4);
 #undef FOLD_BAND
         LAUNCH_CHECK(ctx);
     }
-    if (mode != 0 && (rc = allreduce_results(ctx, mode == 3 ? FS_TS_D : FS_SIG_D, mode == 3 ? 4 : 2))) return rc;
+    if (mode != 0 && mode != 4 && (rc = allreduce_results(ctx, mode == 3 ? FS_TS_D : FS_SIG_D, mode == 3 ? 4 : 2))) return rc;
+    return PB200_OK;
+}
+
+// Polynomial preconditioner of the CG on the folded system: z = q_m(M^) r, q_m = the Chebyshev polynomial of degree m for the interval
+// [lo, hi] of the BULK spectrum (the few low interface modes below it are the band preconditioner's business: z = q_m(M^) r + (q_B(M^_BB) - 1)
+// r_B, an SPD sum).  Why: a CG iteration moves 80 B per unknown around one 16 B operator apply; a polynomial step is the apply with an axpby
+// epilogue (kf_apply_* MODE 4: 24-32 B), so the same error reduction costs ~30 % fewer bytes and (m + 1) times fewer reductions
+// (tests/experiments/krylov_experiment5.py: 35 -> 14 outer iterations at m = 2).  Three-term recurrence with z_1 = r / theta never stored:
+//   step 1:  z_2 = ((1 + rho_1 rho_0) / theta + 2 rho_1 / delta) r - (2 rho_1 / (delta theta)) M^ r
+//   step 2:  z_3 = (1 + rho_2 rho_1) z_2 + (2 rho_2 / delta - rho_2 rho_1 / theta) r - (2 rho_2 / delta) M^ z_2
+static void poly_coefs(double lo, double hi, PolyCoef c[2])
+{
+    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+    const double rho0 = 1.0 / sigma, rho1 = 1.0 / (2.0 * sigma - rho0), rho2 = 1.0 / (2.0 * sigma - rho1);
+    c[0].r = (1.0 + rho1 * rho0) / theta + 2.0 * rho1 / delta; c[0].z = 0.0; c[0].A = -2.0 * rho1 / (delta * theta);
+    c[1].r = 2.0 * rho2 / delta - rho2 * rho1 / theta; c[1].z = 1.0 + rho2 * rho1; c[1].A = -2.0 * rho2 / delta;
+}
+// z = q_m(M^) r into `out` (m = 1: one step; m = 2: through F.z), (r, z) published into res[slot] (dense) and res[slot + 3] (band part)
+static int fold_poly(pb200_solver *s, const FVec &r, const FVec &out, int slot, StopCrit stop)
+{
+    FoldSys &F = s->F;
+    PolyCoef c[2];
+    poly_coefs(F.poly_lo, F.poly_hi, c);
+    int rc;
+    if (F.poly_m == 1) return fold_apply(s, r, out, r, 4, stop, c[0], slot, slot + 3);
+    if ((rc = fold_apply(s, r, F.z, r, 4, stop, c[0], FS_TMP, FS_TMP + 1))) return rc;
+    return fold_apply(s, F.z, out, r, 4, stop, c[1], slot, slot + 3);
+}
+
+// set-up of the polynomial preconditioner, after fold_build (collective: every rank calls it)
+static int fold_poly_setup(pb200_solver *s)
+{
+    pb200_ctx *ctx = s->ctx;
+    const Grid &g = s->g;
+    FoldSys &F = s->F;
+    int rc;
+    // polynomial preconditioner (fold_poly): Chebyshev interval = bulk spectrum [1 - R, max(1 + R, lambda_max(M^))], R = 2 sum_d |c_d| of the
+    // constant-coefficient interior stencil (its eigenvalues are 1 + 2 sum_d c_d cos k_d); lambda_max by a power iteration on M^ (collective)
+    F.poly_m = 0;
+    {
+        const char *e = getenv("PB200_POLY");
+        int m = e ? atoi(e) : PB200_POLY_DEFAULT;
+        if (m > 2) m = 2;
+        // Only without interface unknowns (monophasic problems with a Dirichlet interface).  With the band preconditioner the additive
+        // combination q(M^) + (q_B(M^_BB) - 1) is NOT positive definite in general: for band modes at the upper end of the spectrum
+        // q_B - 1 ~ -0.9 outweighs q ~ 0.3 (measured at 2048^2 diphasic: ~230 iterations per step instead of 8).  The symmetric product
+        // B q(M^) B is the SPD way to combine the two (tests/experiments: same outer counts); not built yet.
+        if (F.d.has_w && !getenv("PB200_POLY_FORCE")) m = 0;
+        if (m > 0) {
+            double R = 0.0, cnt = 0.0;
+            if (F.nitems > 0) {
+                std::vector<unsigned char> hu(F.nitems);
+                std::vector<double> hc((size_t)F.nitems * PB_MAXD);
+                std::vector<TileRec> hr(F.nitems);
+                CUDA_TRY(ctx, cudaMemcpy(hu.data(), F.uni, (size_t)F.nitems, cudaMemcpyDeviceToHost));
+                CUDA_TRY(ctx, cudaMemcpy(hc.data(), F.ucoef, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+                CUDA_TRY(ctx, cudaMemcpy(hr.data(), F.rec, sizeof(TileRec) * (size_t)F.nitems, cudaMemcpyDeviceToHost));
+                for (int i = 0; i < F.nitems; ++i)
+                    if (hr[i].f < 2 && (hu[i] & 1) && hr[i].full) {
+                        double r = 0.0;
+                        for (int dd = 0; dd < g.N; ++dd) r += 2.0 * fabs(hc[(size_t)i * PB_MAXD + dd]);
+                        if (r > R) R = r;
+                        cnt = 1.0;
+                    }
+            }
+            // the same numbers on every rank: mean of the ranks that hold interior tiles (they agree on uniform grids)
+            double h2[2] = {cnt > 0.0 ? R : 0.0, cnt};
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_results + SL_TMP, h2, sizeof(h2), cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = allreduce_results(ctx, SL_TMP, 2))) return rc;
+            if ((rc = fetch_results(ctx, SL_TMP, 2, h2))) return rc;
+            if (h2[1] > 0.5 && h2[0] / h2[1] < 0.95) {
+                R = h2[0] / h2[1];
+                // power iteration, no normalisation (lambda_max < ~2: 1.8^32 is harmless in fp64): lambda ~ (y, y) / (y, x), y = M^ x
+                const int gz = wave_grid(s, kf_seed);
+                kf_seed<<<gz, FCH, 0, ctx->stream>>>(F.I, F.p); LAUNCH_CHECK(ctx);
+                double lam = 1.0 + R;
+                FVec *a = &F.p, *b = &F.v;
+                for (int it = 0; it < 32; ++it) {
+                    if ((rc = fold_apply(s, *a, *b, *b, 3))) return rc;
+                    std::swap(a, b);
+                }
+                double t4[4];
+                if ((rc = fetch_results(ctx, FS_TS_D, 4, t4))) return rc;   // FS_TS_D, FS_TT_D, FS_TS_B, FS_TT_B of the last apply
+                const double yx = t4[0] + t4[2], yy = t4[1] + t4[3];
+                if (yx > 0.0 && yy > 0.0 && yy / yx > lam) lam = yy / yx;
+                kf_zero<<<gz, FCH, 0, ctx->stream>>>(F.I, F.p); LAUNCH_CHECK(ctx);
+                kf_zero<<<gz, FCH, 0, ctx->stream>>>(F.I, F.v); LAUNCH_CHECK(ctx);
+                F.poly_lo = 1.0 - R;
+                F.poly_hi = 1.03 * lam;
+                F.poly_m = m;
+                if (!F.have_z) { if ((rc = fold_alloc_vec(s, &F.z))) return rc; F.have_z = true; }
+                if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] polynomial preconditioner: degree %d on [%.4f, %.4f] (R = %.4f, lambda_max ~ %.4f)\n", m, F.poly_lo, F.poly_hi, R, lam);
+            }
+        }
+    }
     return PB200_OK;
 }
 
@@ -1098,6 +1199,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         const bool prec = cg && F.d.has_w && F.prec;   // F.prec is the same on every rank
         const int gE = band_wgrid(F.d.nE);
         const StopCrit nostop = {0.0, 0.0, -1};
+        const bool poly = cg && F.poly_m > 0;
+        if (poly && (rc = fold_poly(s, F.r, F.p, FS_PAIR0, nostop))) return rc;   // p0 = q(M^) r0 (kf_resid had set p0 = r0)
         if (cg) {
             if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
                 DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
@@ -1105,6 +1208,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 if ((rc = allreduce_results(ctx, FS_PAIR0 + 2, 1))) return rc;
                 kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx);
             }
+            if (poly && ((rc = allreduce_results(ctx, FS_PAIR0, 1)) || (rc = allreduce_results(ctx, FS_PAIR0 + 3, 1)))) return rc;   // (slots 1, 2 are global already)
         }
         // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
         // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
@@ -1118,14 +1222,16 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 prof_mark(ctx, PB_PROF_UPDATE);
                 kf_cg_update<<<wave_grid(s, kf_cg_update), FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
                 prof_mark(ctx, PB_PROF_UPDATE);
-                if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 2))) return rc2;
-                if (prec) {   // z = r + (q(M^_BB) - 1) r_B on the band: rho_new = (r, r) + (r_B, dz_B)
+                // z = q(M^) r (polynomial preconditioner, into F.v: free until the next apply) -- rho_new = (r, q(M^) r) replaces (r, r)
+                if (poly && (rc2 = fold_poly(s, F.r, F.v, FS_TRIPLE(nxt), st))) return rc2;
+                if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 2))) return rc2;
+                if (prec) {   // z += (q(M^_BB) - 1) r_B on the band: rho_new += (r_B, dz_B)
                     DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
                     LAUNCH_CHECK(ctx);
-                    if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 3))) return rc2;
+                    if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 3))) return rc2;
                 }
                 prof_mark(ctx, PB_PROF_PUPD);
-                kf_cg_p<<<wave_grid(s, kf_cg_p), FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.r, F.p, F.x, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
+                kf_cg_p<<<wave_grid(s, kf_cg_p), FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), poly ? F.v : F.r, F.p, F.x, prec ? F.dz : nullptr, F.bord, F.d.nB, st, stn); LAUNCH_CHECK(ctx);
                 prof_mark(ctx, PB_PROF_PUPD);
             } else {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.r0, 2, st))) return rc2;
@@ -1147,7 +1253,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
         const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
         const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
-        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen, o.rtol, o.atol, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
+        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen + 1024.0 * F.poly_m, o.rtol + F.poly_lo, o.atol + F.poly_hi, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
         if (use_graph && memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
             for (auto &kv : F.graphs) cudaGraphExecDestroy(kv.second.exec);
             F.graphs.clear();
@@ -1181,8 +1287,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 for (int q = 0; q < chunk; ++q) { if ((rc = enqueue(cur))) return rc; cur ^= 1; }
             }
             queued += chunk;
-            double all[16];
-            if ((rc = fetch_results(ctx, 0, 16, all))) return rc;   // one look: rr, iteration count, ||b||^2
+            double all[FS_TMP + 1];
+            if ((rc = fetch_results(ctx, 0, FS_TMP + 1, all))) return rc;   // one look: rr, iteration count, ||b||^2
             if ((rc = p2p_check(ctx))) return rc;
             bnorm = sqrt(all[FS_BB]);
             tol = fmax(o.rtol * bnorm, o.atol);
@@ -1331,7 +1437,7 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         return gsx;
     };
     // folded system (cached per coefficient set and mask set)
-    if (use_fold && (!s->F.built || s->F.key[0] != ac.cV || s->F.key[1] != ac.c || s->F.key[2] != ac.c2)) { if ((rc = fold_build(s, ac))) return rc; }
+    if (use_fold && (!s->F.built || s->F.key[0] != ac.cV || s->F.key[1] != ac.c || s->F.key[2] != ac.c2)) { if ((rc = fold_build(s, ac)) || (rc = fold_poly_setup(s))) return rc; }
     // steps without an explicit operator part on the folded path: b, b^ and the scaled initial guess come out of ONE pass over the active
     // tiles (kf_rhs_dense) instead of k_rhs_* + kf_to_scaled_dense + kf_guess_dense over all cells
     const bool fused_rhs = use_fold && !getenv("PB200_NO_FUSED_RHS") && (!cn || (sc.ce == sc.c && !getenv("PB200_NO_FUSED_CN")));

@@ -24,7 +24,8 @@ def main():
         return obj[0]
     pb.init_distributed(rank, world, local, bcast)
     worst = 0.0
-    for case in ("diph2d", "mono3d"):
+    # mono3d_dcn: Dirichlet interface (no interface unknowns -> polynomial preconditioner) and CN (explicit part = one folded apply)
+    for case in ("diph2d", "mono3d", "mono3d_dcn"):
         if case == "diph2d":
             dims, L = (40, 36), (8.0, 7.2)
             body = pb.Balls([[4.03, 3.67]], [2.0])   # no tangency to a grid line
@@ -53,8 +54,10 @@ def main():
             keys = ("left", "right", "top", "bottom", "forward", "backward")
             bc = pb.BorderConditions({k: pb.Dirichlet(1.0) for k in keys})
             u0 = np.concatenate([cut(np.zeros(n)), cut(np.zeros(n))])
-            s = pb.DiffusionUnsteadyMono(p1, bc, pb.Robin(1.0, 0.5, 0.3), dt, u0, "BE")
-            pb.solve_DiffusionUnsteadyMono_(s, p1, dt, 2.5 * dt, bc, pb.Robin(1.0, 0.5, 0.3), "BE", reltol=1e-13)
+            bci = pb.Dirichlet(0.7) if case == "mono3d_dcn" else pb.Robin(1.0, 0.5, 0.3)
+            sch = "CN" if case == "mono3d_dcn" else "BE"
+            s = pb.DiffusionUnsteadyMono(p1, bc, bci, dt, u0, "BE")
+            pb.solve_DiffusionUnsteadyMono_(s, p1, dt, 2.5 * dt, bc, bci, sch, reltol=1e-13)
             nblk = 2
         nloc = c1.nloc
         if rank == 0:
@@ -97,8 +100,9 @@ def main():
             else:
                 q1 = po.Phase(o1, po.DiffusionOps(o1), f, 1.0)
                 bco = po.BorderConditions({k: po.Dirichlet(1.0) for k in keys})
-                so = po.DiffusionUnsteadyMono(q1, bco, po.Robin(1.0, 0.5, 0.3), dt, np.zeros(2 * n), "BE")
-                po.solve_DiffusionUnsteadyMono(so, q1, dt, 2.5 * dt, bco, po.Robin(1.0, 0.5, 0.3), "BE")
+                bcio = po.Dirichlet(0.7) if case == "mono3d_dcn" else po.Robin(1.0, 0.5, 0.3)
+                so = po.DiffusionUnsteadyMono(q1, bco, bcio, dt, np.zeros(2 * n), "BE")
+                po.solve_DiffusionUnsteadyMono(so, q1, dt, 2.5 * dt, bco, bcio, sch)
             assert len(so.states) == len(gathered[0])
             for k, ref in enumerate(so.states):
                 # each rank's state is [blk0_local; blk1_local; ...]: reassemble block by block
