@@ -1095,10 +1095,12 @@ static int fold_poly_setup(pb200_solver *s)
         const char *e = getenv("PB200_POLY");
         int m = e ? atoi(e) : PB200_POLY_DEFAULT;
         if (m > 2) m = 2;
-        // Only without interface unknowns (monophasic problems with a Dirichlet interface).  With the band preconditioner the additive
-        // combination q(M^) + (q_B(M^_BB) - 1) is NOT positive definite in general: for band modes at the upper end of the spectrum
-        // q_B - 1 ~ -0.9 outweighs q ~ 0.3 (measured at 2048^2 diphasic: ~230 iterations per step instead of 8).  The symmetric product
-        // B q(M^) B is the SPD way to combine the two (tests/experiments: same outer counts); not built yet.
+        // Only without interface unknowns (monophasic problems with a Dirichlet interface).  Measured on the diphasic configs[1] system
+        // (2048^2, extrapolated initial guess; iterations per step): band preconditioner alone 8.35 (what runs), no preconditioner 27.6,
+        // polynomial alone 12.8, the sum q(M^) + (q_B(M^_BB) - 1) ~230 -- it is not positive definite: for band modes at the upper end of
+        // the spectrum q_B - 1 ~ -0.9 outweighs q ~ 0.3 --, the symmetric product B q(M^) B 32 -- q_B^2 crushes those same modes
+        // (lambda q_B^2 q ~ 0.01 against ~2-4 elsewhere).  The residual left by the extrapolated guess lives on the interface band, which
+        // is why the O(band) preconditioner does more there than the bulk polynomial; combining them needs a deflation-type coupling.
         if (F.d.has_w && !getenv("PB200_POLY_FORCE")) m = 0;
         if (m > 0) {
             double R = 0.0, cnt = 0.0;
