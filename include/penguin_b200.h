@@ -203,6 +203,9 @@ int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const pb200_kryl
  * u_ana - T_omega of bulk field `phase` (0, or 1 for the second phase of a diphasic solver), u_ana[n] evaluated by the caller at C_omega;
  * out = {all fluid cells (full + cut), full, cut, empty}, classes by capacity.cell_types.  relative != 0: relative_lp_norm.                */
 int pb200_solver_error_norms(pb200_solver *s, int phase, const double *u_ana, double p, int relative, double out[4]);
+/* Host-only helper (no device needed): coefficients of the polynomial preconditioner z = q(M^) r of the folded CG for the
+ * Chebyshev interval [lo, hi]: step 1  z2 = out[0] r + out[2] M^ r ;  step 2  z3 = out[3] r + out[4] z2 + out[5] M^ z2  (out[1] = 0).       */
+int pb200_poly_coefs(double lo, double hi, double out[6]);
 int pb200_solver_destroy(pb200_solver *s);
 
 #ifdef __cplusplus

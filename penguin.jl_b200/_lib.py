@@ -67,6 +67,7 @@ SYMBOLS = {
     "pb200_solver_get_state": ([C.c_void_p, dp], C.c_int),
     "pb200_solver_get_state_async": ([C.c_void_p, dp], C.c_int),
     "pb200_solver_error_norms": ([C.c_void_p, C.c_int, dp, C.c_double, C.c_int, dp], C.c_int),
+    "pb200_poly_coefs": ([C.c_double, C.c_double, dp], C.c_int),
     "pb200_solver_wait_state": ([C.c_void_p], C.c_int),
     "pb200_solver_step": ([C.c_void_p, C.POINTER(StepIn), C.POINTER(KrylovOpts), C.POINTER(StepStats)], C.c_int),
     "pb200_solver_destroy": ([C.c_void_p], C.c_int),

@@ -1069,6 +1069,15 @@ static void poly_coefs(double lo, double hi, PolyCoef c[2])
     c[0].r = (1.0 + rho1 * rho0) / theta + 2.0 * rho1 / delta; c[0].z = 0.0; c[0].A = -2.0 * rho1 / (delta * theta);
     c[1].r = 2.0 * rho2 / delta - rho2 * rho1 / theta; c[1].z = 1.0 + rho2 * rho1; c[1].A = -2.0 * rho2 / delta;
 }
+// host-only: the coefficients of the two polynomial steps, out = {r1, z1, A1, r2, z2, A2} (unit-tested against a NumPy Chebyshev iteration)
+extern "C" int pb200_poly_coefs(double lo, double hi, double out[6])
+{
+    if (!out || !(lo > 0.0) || !(hi > lo)) return set_err(nullptr, PB200_EINVAL, "need 0 < lo < hi");
+    PolyCoef c[2];
+    poly_coefs(lo, hi, c);
+    out[0] = c[0].r; out[1] = c[0].z; out[2] = c[0].A; out[3] = c[1].r; out[4] = c[1].z; out[5] = c[1].A;
+    return PB200_OK;
+}
 // z = q_m(M^) r into `out` (m = 1: one step; m = 2: through F.z), (r, z) published into res[slot] (dense) and res[slot + 3] (band part)
 static int fold_poly(pb200_solver *s, const FVec &r, const FVec &out, int slot, StopCrit stop)
 {

@@ -59,3 +59,39 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "from oracle" not in src and "libgeom_oracle" not in src, f
                 assert not re.search(r'#include\s+"[^"]*oracle', src), f
+
+
+def test_polynomial_preconditioner_coefficients():
+    """pb200_poly_coefs (host-only) against a NumPy Chebyshev iteration: z_{m+1} = q_m(A) r for A z = r, z_0 = 0 on [lo, hi]."""
+    import ctypes
+    import numpy as np
+    from penguin_b200 import _lib
+    lo, hi = 1.0 / 3.0, 1.95
+    out = (ctypes.c_double * 6)()
+    assert _lib.lib().pb200_poly_coefs(lo, hi, ctypes.cast(out, _lib.dp)) == 0
+    c = list(out)
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rng.standard_normal((40, 40)))
+    A = Q @ np.diag(np.linspace(0.2, 1.9, 40)) @ Q.T
+    r = rng.standard_normal(40)
+
+    def cheb(m):                      # residual form of the Chebyshev iteration, m matvecs
+        theta, delta = (hi + lo) / 2, (hi - lo) / 2
+        sigma = theta / delta
+        rho = 1 / sigma
+        z, res, d = np.zeros(40), r.copy(), r / theta
+        for _ in range(m):
+            z = z + d
+            res = res - A @ d
+            rho_n = 1 / (2 * sigma - rho)
+            d = rho_n * rho * d + 2 * rho_n / delta * res
+            rho = rho_n
+        return z + d
+    z2 = c[0] * r + c[2] * (A @ r)
+    z3 = c[3] * r + c[4] * z2 + c[5] * (A @ z2)
+    assert c[1] == 0.0
+    assert np.allclose(z2, cheb(1), rtol=1e-12, atol=1e-13) and np.allclose(z3, cheb(2), rtol=1e-12, atol=1e-13)
+    # q(A) is positive definite on the whole spectrum, also below lo (the interface modes) and up to hi
+    lam = np.linspace(0.01, hi, 200)
+    assert np.all(c[0] + c[2] * lam > 0)
+    assert _lib.lib().pb200_poly_coefs(1.0, 0.5, ctypes.cast(out, _lib.dp)) != 0
