@@ -1110,7 +1110,7 @@ static int fold_poly_setup(pb200_solver *s)
         // the spectrum q_B - 1 ~ -0.9 outweighs q ~ 0.3 --, the symmetric product B q(M^) B 32 -- q_B^2 crushes those same modes
         // (lambda q_B^2 q ~ 0.01 against ~2-4 elsewhere).  The residual left by the extrapolated guess lives on the interface band, which
         // is why the O(band) preconditioner does more there than the bulk polynomial; combining them needs a deflation-type coupling.
-        if (F.d.has_w && !getenv("PB200_POLY_FORCE")) m = 0;
+        if (F.d.has_w) m = 0;
         if (m > 0) {
             double R = 0.0, cnt = 0.0;
             if (F.nitems > 0) {
