@@ -78,3 +78,20 @@ def test_check_convergence_on_device(pb, p, relative):
             assert np.isnan(g) or np.isinf(g)
         else:
             assert abs(g - w) <= 1e-9 * max(abs(w), 1e-300) + 1e-13, (g, w)
+
+
+def test_reference_darcy_test_jl(pb):
+    # test/solver/darcy_test.jl:4-26,56-76 through the device library: circle (0.5, 0.5) r 0.5 in [0, 2]^2, pure Neumann(0) interface,
+    # Dirichlet 10 / 20 on :left / :right; the reference's asserts (max p_omega = 20 +- 1e-2, |u| < 1e2) and parity with the oracle
+    f = (lambda x, y, z: 0.0 * x)
+    mo, pho, phg = _problem(pb, (20, 20), (2.0, 2.0), geom.LevelSet.ball((0.5, 0.5), 0.5), f, (lambda x, y, z: 1.0 + 0.0 * x))
+    bcb = pb.BorderConditions({"left": pb.Dirichlet(10.0), "right": pb.Dirichlet(20.0)})
+    so = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(pho, to_oracle_borders(pb, bcb), po.Neumann(0.0)))
+    sg = pb.solve_DarcyFlow_(pb.DarcyFlow(phg, bcb, pb.Neumann(0.0)), reltol=1e-13, maxiter=50000)
+    assert abs(sg.x[:mo.n].max() - 20.0) < 1e-2
+    assert rel_l2(sg.x, so.x) < 1e-9
+    ug = pb.solve_darcy_velocity(sg, phg)
+    uo = po.solve_darcy_velocity(so.x, pho.operator, pho.capacity)
+    assert np.array_equal(np.isnan(ug), np.isnan(uo))
+    ok = ~np.isnan(ug)
+    assert np.abs(ug[ok]).max() < 1e2 and rel_l2(ug[ok], uo[ok]) < 1e-8

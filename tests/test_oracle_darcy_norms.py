@@ -61,3 +61,42 @@ def test_check_convergence_norms():
     assert po.check_convergence(u, np.concatenate([num, np.zeros_like(num)]), cap, 2)[0] == g
     rel = po.check_convergence(u, num, cap, 1, relative=True)
     assert np.isclose(rel[1], (np.abs(0.5 / ua[ct == 1]) * V[ct == 1]).sum() / tot)
+
+
+# ---- the reference's own asserts for this stage (test/solver/darcy_test.jl) ------------------------------------------------------
+def _darcy_reference_case():
+    mesh = po.Mesh((20, 20), (2.0, 2.0))
+    cap = geom.capacity(mesh, geom.LevelSet.ball((0.5, 0.5), 0.5))       # LS < 0 inside the circle: darcy_test.jl:10
+    op = po.DiffusionOps(cap)
+    bcb = po.BorderConditions({"left": po.Dirichlet(10.0), "right": po.Dirichlet(20.0)})
+    return mesh, cap, op, bcb
+
+
+def test_reference_darcy_steady_assert():
+    # darcy_test.jl:4-26: maximum(uo) ~ 20 +- 1e-2
+    mesh, cap, op, bcb = _darcy_reference_case()
+    ph = po.Phase(cap, op, (lambda x, y, z: 0.0 * x), (lambda x, y, z: 1.0 + 0.0 * x))
+    s = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(ph, bcb, po.Neumann(0.0)))
+    assert abs(s.x[:mesh.n].max() - 20.0) < 1e-2
+
+
+def test_reference_darcy_unsteady_assert():
+    # darcy_test.jl:28-54: BE, dt = 0.1 (lx/nx)^2, Tend = 0.2 (shortened: the assert holds from the first state on, border rows carry 20)
+    mesh, cap, op, bcb = _darcy_reference_case()
+    ph = po.Phase(cap, op, (lambda x, y, z, t: 0.0 * x), (lambda x, y, z: 1.0 + 0.0 * x))
+    dt = 0.1 * (2.0 / 20) ** 2
+    u0 = np.full(2 * mesh.n, 10.0)
+    s = po.DiffusionUnsteadyMono(ph, bcb, po.Neumann(0.0), dt, u0, "BE")
+    po.solve_DiffusionUnsteadyMono(s, ph, dt, 0.2, bcb, po.Neumann(0.0), "BE", max_steps=12)
+    assert len(s.states) == 13
+    assert abs(s.states[-1][:mesh.n].max() - 20.0) < 1e-2
+
+
+def test_reference_darcy_velocity_assert():
+    # darcy_test.jl:56-76: the non-NaN velocities stay below 1e2
+    mesh, cap, op, bcb = _darcy_reference_case()
+    ph = po.Phase(cap, op, (lambda x, y, z: 0.0 * x), (lambda x, y, z: 1.0 + 0.0 * x))
+    s = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(ph, bcb, po.Neumann(0.0)))
+    u = po.solve_darcy_velocity(s.x, op, cap)
+    ok = ~np.isnan(u)
+    assert 0 < ok.sum() < u.size and np.abs(u[ok]).max() < 1e2
