@@ -138,9 +138,15 @@ __host__ __device__ __noinline__ void disc_rect(double X0, double Y0, double rho
             if (c > 0.0) {
                 double s = c / (2.0 * rho);
                 if (s > 1.0) s = 1.0;
+                // half angle p of the arc from its chord: tan p = (c / 2) / d, d = crs / c = signed distance of the disc centre from the
+                // chord (negative: major arc), cos p = d / rho.  (asin(c / 2 rho) and sqrt(1 - s^2) lose up to eight digits when the chord
+                // is close to a diameter -- a disc centre on or near an edge line, e.g. every z-section of a sphere centred on a grid
+                // plane: tests/host_harness/geom_primitives.cu, half-ball volume off by 2e-10 relative.)
                 const double crs = (x0 - X0) * (y1 - Y0) - (x1 - X0) * (y0 - Y0);
-                double p = asin(s), cp = sqrt(fmax(1.0 - s * s, 0.0));
-                if (crs < 0.0) { p = PB_PI - p; cp = -cp; }   // major arc
+                const double d = crs / c;
+                const double p = atan2(0.5 * c, d);
+                double cp = d / rho;
+                cp = cp > 1.0 ? 1.0 : (cp < -1.0 ? -1.0 : cp);
                 const double nxh = dy / c, nyh = -dx / c;      // unit vector from the chord mid-point towards the arc
                 const double Mx = 0.5 * (x0 + x1), My = 0.5 * (y0 + y1);
                 const double sa = r2 * seg_area_f(p, s, cp);
