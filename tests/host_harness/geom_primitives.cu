@@ -87,11 +87,26 @@ static int run3d(int n)
     return bad + badc;
 }
 
+// the reference's darcy_test.jl geometry: circle centre (0.5, 0.5) r 0.5 on an h = 0.1 grid -- tangent to x = 0 at the grid node (0, 0.5)
+static void run_tangent()
+{
+    const double h = 0.1;
+    for (int j = 3; j <= 6; ++j)
+        for (int i = 0; i <= 1; ++i) {
+            const double lox = i * h, hix = (i + 1) * h, loy = j * h, hiy = (j + 1) * h;
+            const double mx = 0.5 * (lox + hix), my = 0.5 * (loy + hiy);
+            double o[6];
+            disc_rect(0.5 - mx, 0.5 - my, 0.5, 0.5 * (hix - lox), 0.5 * (hiy - loy), o);
+            printf("TANGENT %d %d %.17g %.17g %.17g %.17g %.17g %.17g\n", i, j, lox, hix, loy, hiy, o[0], 0.5 * o[3]);
+        }
+}
+
 int main(int argc, char **argv)
 {
     srand(1);
     const int n2 = argc > 1 ? atoi(argv[1]) : 200000, n3 = argc > 2 ? atoi(argv[2]) : 4000;
     run2d(n2);
     run3d(n3);
+    run_tangent();
     return 0;
 }

@@ -76,3 +76,19 @@ def test_ball_box_vs_oracle_and_closed_forms(harness_output):
         # ball of radius 0.37 with k coordinates of its centre ON the box boundary: 1 / 2^k of the ball, volume and surface
         # (k = 1 was off by 2e-10 with the asin-based arc angle: every z-section has its centre on an edge line)
         assert abs(float(v) - float(vex)) <= 1e-14 and abs(float(s) - float(sex)) <= 1e-13, (k, v, vex, s, sex)
+
+
+def test_tangency_at_a_grid_node(harness_output):
+    # test/solver/darcy_test.jl:10 -- circle (0.5, 0.5) r 0.5 on the h = 0.1 grid touches x = 0 exactly at a cell corner
+    mp = pytest.importorskip("mpmath")
+    rows = [ln.split() for ln in harness_output if ln.startswith("TANGENT")]
+    assert len(rows) == 8
+    for _, i, j, lox, hix, loy, hiy, area, arc in rows:
+        lox, hix, loy, hiy, area, arc = map(float, (lox, hix, loy, hiy, area, arc))
+        mx, my = 0.5 * (lox + hix), 0.5 * (loy + hiy)
+        ex = float(_exact_area(0.5 - mx, 0.5 - my, 0.5, 0.5 * (hix - lox), 0.5 * (hiy - loy)))
+        assert abs(area - ex) <= 1e-15, (i, j, area, ex)
+        if i == "1":
+            assert area == pytest.approx(0.01, abs=1e-17) and arc == 0.0          # second column: full cells, no interface
+        else:
+            assert 0.0 < area < 0.01 and arc > 0.1                                  # first column: cut cells
