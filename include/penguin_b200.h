@@ -155,6 +155,17 @@ typedef struct {
     const double *g_arr[2];
 } pb200_step_in;
 
+/* kernel classes of pb200_step_stats.kernel_ms / kernel_launches */
+#define PB200_K_APPLY 0      /* operator apply on the bulk tiles (+ fused search-direction update on the fused path) */
+#define PB200_K_UPDATE 1     /* residual update with fused dot products                                               */
+#define PB200_K_PUPD 2       /* solution / search-direction update (unfused path)                                     */
+#define PB200_K_BAND_APPLY 3 /* interface-band part of the operator                                                   */
+#define PB200_K_BAND_PREC 4  /* interface-band preconditioner                                                         */
+#define PB200_K_EXCHANGE 5   /* halo exchange + scalar reductions between ranks                                       */
+#define PB200_K_PROLOGUE 6   /* per-step right-hand side, scaling, initial guess, first residual                      */
+#define PB200_K_EPILOGUE 7   /* back-transform and state write-back                                                   */
+#define PB200_K_NCLASS 8
+
 #define PB200_KRYLOV_AUTO 0 /* CG on the folded (symmetrised) path and for mono; BiCGSTAB for diph on the generic path */
 #define PB200_KRYLOV_CG 1
 #define PB200_KRYLOV_BICGSTAB 2
@@ -189,10 +200,12 @@ typedef struct {
     /* folded path, this rank: cells of the tiles the apply kernel processes with per-tile constant coefficients (no coefficient
      * arrays read) and with streamed coefficient arrays -- the census behind bench.py's algorithmic-byte count */
     int64_t apply_cells_uniform, apply_cells_general;
-    /* profiling enabled: summed device time / launch count per hot kernel -- [0] operator apply (dense part), [1] x,r update with
-     * fused dots, [2] search-direction update */
-    double kernel_ms[3];
-    int64_t kernel_launches[3];
+    /* profiling enabled: summed device time / launch count per kernel class of the Krylov loop (PB200_K_* below) */
+    double kernel_ms[8];
+    int64_t kernel_launches[8];
+    /* cells of the tiles that take the apply kernel's staged interior branch (every cell valid AND constant coefficients) -- the parity
+     * tests assert this is > 0 so that the branch the benchmark runs is the branch they compare with the oracle */
+    int64_t apply_cells_fast;
 } pb200_step_stats;
 
 /* one solve: builds b from the device-resident state (b_*_unstead_diff / b_*_stead_diff), applies the border

@@ -585,7 +585,9 @@ def _step(s, scheme, dt, t, bc_i, ic, opts, mono_border_t=True):
     L.check(L.lib().pb200_solver_get_state(s._h, _dp(x)), s._ctx.h)
     s.x = x
     s.ch.append(dict(iters=st.iters, converged=bool(st.converged), rnorm=st.rnorm, bnorm=st.bnorm, solve_ms=st.solve_ms,
-                     setup_ms=st.setup_ms, dof_bulk=st.dof_bulk, dof_ifc=st.dof_ifc, launches=st.launches))
+                     setup_ms=st.setup_ms, dof_bulk=st.dof_bulk, dof_ifc=st.dof_ifc, launches=st.launches,
+                     apply_cells_uniform=st.apply_cells_uniform, apply_cells_general=st.apply_cells_general,
+                     apply_cells_fast=st.apply_cells_fast))
     return st
 
 

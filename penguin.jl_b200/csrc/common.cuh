@@ -48,10 +48,15 @@ struct pb200_ctx {
 };
 
 // event bracket around one launch (no-op unless profiling): prof_mark(ctx, tag); kernel<<<>>>; prof_mark(ctx, tag);
-#define PB_PROF_APPLY 0    // operator apply, dense part
-#define PB_PROF_UPDATE 1   // x, r update + dots (CG) / x, r update (BiCGSTAB)
-#define PB_PROF_PUPD 2     // search-direction update
-#define PB_PROF_NTAG 3
+#define PB_PROF_APPLY PB200_K_APPLY
+#define PB_PROF_UPDATE PB200_K_UPDATE
+#define PB_PROF_PUPD PB200_K_PUPD
+#define PB_PROF_BAPPLY PB200_K_BAND_APPLY
+#define PB_PROF_BPREC PB200_K_BAND_PREC
+#define PB_PROF_XCHG PB200_K_EXCHANGE
+#define PB_PROF_PROLOGUE PB200_K_PROLOGUE
+#define PB_PROF_EPILOGUE PB200_K_EPILOGUE
+#define PB_PROF_NTAG PB200_K_NCLASS
 static inline void prof_mark(pb200_ctx *ctx, int tag)
 {
     if (!ctx->profile) return;

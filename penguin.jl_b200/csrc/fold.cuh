@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
 {
     __shared__ double smn[PB_MAXD][FCH / 32], smx[PB_MAXD][FCH / 32];
     __shared__ int s_uni;
-    double cnt[2] = {0.0, 0.0};
+    double cnt[3] = {0.0, 0.0, 0.0};   // cells of constant-coefficient tiles, of streamed-coefficient tiles, of the staged interior branch
     for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
         const TileRec R = I.rec[it];
         if (R.f >= 2) { if (threadIdx.x == 0) uni[it] = 0; continue; }   // uniform over the block
@@ -483,9 +483,10 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
         }
         __syncthreads();
         cnt[s_uni ? 0 : 1] += (double)nok;
+        if (s_uni && R.full) cnt[2] += (double)nok;
         __syncthreads();
     }
-    block_reduce_publish<2>(cnt, partials, results, counter);
+    block_reduce_publish<3>(cnt, partials, results, counter);
 }
 
 // ---- operator ---------------------------------------------------------------------------------------------------------------
@@ -1097,6 +1098,7 @@ struct FoldSys {
     double graph_key[5] = {};
     int last_iters = 0;                     // iteration count of the previous solve (sizes the first chunk of the next one)
     long long cells_uniform = 0, cells_general = 0;   // cells of tiles applied with constant / streamed coefficients (this rank)
+    long long cells_fast = 0;                         // cells of full tiles with constant coefficients (the apply kernel's staged interior branch)
     Items I;                                // every item, index order (vector kernels)
     Items IA;                               // bulk tiles in cost-class order (operator apply)
     int *itemsA = nullptr; TileRec *recA = nullptr; unsigned char *uniA = nullptr; double *ucoefA = nullptr;

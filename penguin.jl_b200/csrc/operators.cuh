@@ -252,6 +252,27 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
     }
 }
 
+// Border VALUES changed, kinds did not (time-dependent Dirichlet data, src/solver/diffusion.jl:291-293 calls BC_border_mono! every step):
+// only the pinned values are refreshed -- the masks, the folded system and the captured graphs stay valid.
+__global__ void k_refresh_ufix(Grid g, BorderDev bd, const unsigned char *__restrict__ m1, const unsigned char *__restrict__ m2, double *__restrict__ ufix1,
+                               double *__restrict__ ufix2)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = t + g.plane;
+        const unsigned char a = m1[l], b = m2 ? m2[l] : 0;
+        if (!((a | b) & (MB_FIXED | MB_SLAVE))) continue;
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        double bval = 0.0;
+        if (border_pinned(g, bd, c, bval) != 1) {   // 1-D Neumann row
+            const int kn = border_key(g, c);
+            bval = kn >= 0 ? bd.value[kn] * g.h[0] : 0.0;
+        }
+        if (a & (MB_FIXED | MB_SLAVE)) ufix1[l] = bval;
+        if (b & (MB_FIXED | MB_SLAVE)) ufix2[l] = bval;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // general block-row kernels
 // ------------------------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ struct P2PHeader {                                   // at offset 0 of every mai
     unsigned long long flag_halo[2];                 // [0] written by my LOWER neighbour, [1] by my UPPER neighbour
     unsigned long long flag_red[P2P_MAXR];           // written by peer r
     unsigned long long seq_halo, seq_red;            // my own sequence counters (advanced by my kernels)
-    unsigned int done[2];                            // block counters of the halo kernel (per direction)
+    unsigned int done[2];                            // block counters of the halo kernel: [0] blocks that have packed, [1] blocks that have left
     int err;                                         // set when a spin timed out
     int pad;
     double red[2][P2P_MAXR][P2P_REDK];               // [parity][source rank][k]
@@ -122,8 +122,10 @@ __global__ void k_p2p_halo(char *mbox, size_t zone_doubles, HaloDirArgs lo, Halo
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned t = atomicAdd(&me->done[0], 1u);
-        if (t == 2 * gridDim.x - 1) { me->done[0] = 0; me->seq_halo = seq; }   // last block out: re-arm and advance
+        // a SEPARATE counter for the way out: a fast block may leave before a slow one has packed, so one shared counter would let a
+        // leaving block take the ticket that releases the flags (or never reach it)
+        const unsigned t = atomicAdd(&me->done[1], 1u);
+        if (t == gridDim.x - 1) { me->done[0] = 0; me->done[1] = 0; __threadfence(); me->seq_halo = seq; }   // last block out: re-arm and advance
     }
 }
 
@@ -177,12 +179,14 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     // the zone size must be the same everywhere and so must the decision to (re)build: take the maximum of the requests first
     double want = (double)zone_doubles;
     double *d_tmp = nullptr;
+    unsigned char *d_h = nullptr;
+    struct Guard { double *&a; unsigned char *&b; ~Guard() { if (a) cudaFree(a); if (b) cudaFree(b); } } guard{d_tmp, d_h};   // also on the error returns
     CUDA_TRY(ctx, cudaMalloc((void **)&d_tmp, sizeof(double)));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_tmp, &want, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NCCL_TRY(ctx, g_nccl.AllReduce(d_tmp, d_tmp, 1, PB_NCCL_FLOAT64, PB_NCCL_MAX, ctx->comm, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&want, d_tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->p2p && ctx->p2p->on && (double)ctx->p2p->zone_doubles >= want) { cudaFree(d_tmp); return PB200_OK; }
+    if (ctx->p2p && ctx->p2p->on && (double)ctx->p2p->zone_doubles >= want) return PB200_OK;
     // generous first allocation (>= 1 Mi doubles per zone, twice the request) so that later, larger problems rarely force a re-mapping
     zone_doubles = (size_t)(2.0 * want) + 64;
     if (zone_doubles < (1u << 20)) zone_doubles = 1u << 20;
@@ -201,7 +205,6 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     cudaGetLastError();
     // all-gather the handles (64 bytes each) and the ok flags through NCCL
     const size_t HS = sizeof(cudaIpcMemHandle_t) + 8;
-    unsigned char *d_h = nullptr;
     std::vector<unsigned char> h_all(HS * P->n, 0);
     CUDA_TRY(ctx, cudaMalloc((void **)&d_h, HS * P->n));
     memcpy(h_all.data() + HS * P->rank, &mine, sizeof(mine));
@@ -227,7 +230,6 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     NCCL_TRY(ctx, g_nccl.AllReduce(d_tmp, d_tmp, 1, PB_NCCL_FLOAT64, PB_NCCL_SUM, ctx->comm, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&okd, d_tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_tmp); cudaFree(d_h);
     P->on = okd > P->n - 0.5;
     if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] rank %d: peer-memory exchange %s (zone %zu doubles)\n", ctx->rank, P->on ? "ON" : "off (NCCL)", zone_doubles);
     return PB200_OK;
@@ -253,6 +255,11 @@ static int p2p_check(pb200_ctx *ctx)
     int err = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&err, P->mbox + offsetof(P2PHeader, err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (err) return set_err(ctx, PB200_ENCCL, "peer-memory exchange timed out waiting for a neighbour rank");
+    if (err) {
+        // report once: the flag is cleared so that a later solve (after the caller has dealt with the stalled rank) is not failed by it
+        cudaMemsetAsync(P->mbox + offsetof(P2PHeader, err), 0, sizeof(int), ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        return set_err(ctx, PB200_ENCCL, "peer-memory exchange timed out waiting for a neighbour rank");
+    }
     return PB200_OK;
 }

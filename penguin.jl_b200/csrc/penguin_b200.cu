@@ -135,7 +135,8 @@ static int cap_alloc(pb200_ctx *ctx, pb200_capacity *c)
         if ((rc = dev_alloc(ctx, &c->B[d], g.nloc))) return rc;
         if ((rc = dev_alloc(ctx, &c->W[d], g.nloc))) return rc;
         if ((rc = dev_alloc(ctx, &c->Co[d], g.nloc))) return rc;
-        if ((rc = dev_alloc(ctx, &c->Cg[d], g.nloc))) return rc;
+        // C_gamma only when asked for (compute_centroids / imported): N fields per phase that the solve never reads (6.5 GB per phase at 512^3)
+        if (c->has_cg && (rc = dev_alloc(ctx, &c->Cg[d], g.nloc))) return rc;
     }
     return PB200_OK;
 }
@@ -146,6 +147,7 @@ static int cap_halo(pb200_capacity *c)
     return halo_exchange(c->ctx, c->g, f.data(), (int)f.size());
 }
 
+extern "C" int pb200_capacity_destroy(pb200_capacity *c);
 extern "C" int pb200_capacity_import(pb200_ctx *ctx, int ndim, const int *n, const double *x0, const double *L, const double *V, const double *Gamma,
                                      const double *cell_types, const double *A, const double *B, const double *W, const double *C_omega,
                                      const double *C_gamma, pb200_capacity **out)
@@ -154,21 +156,26 @@ extern "C" int pb200_capacity_import(pb200_ctx *ctx, int ndim, const int *n, con
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_capacity *c = new pb200_capacity();
     c->ctx = ctx;
-    int rc = make_grid(ctx, ndim, n, x0, L, &c->g);
-    if (!rc) rc = cap_alloc(ctx, c);
-    if (rc) { delete c; return rc; }
-    const Grid &g = c->g;
-    if ((rc = upload_owned(ctx, g, c->V, V)) || (rc = upload_owned(ctx, g, c->Gam, Gamma)) || (rc = upload_owned(ctx, g, c->ct, cell_types))) return rc;
-    for (int d = 0; d < g.N; ++d) {
-        if ((rc = upload_owned(ctx, g, c->A[d], A ? A + (int64_t)d * g.nown : nullptr))) return rc;
-        if ((rc = upload_owned(ctx, g, c->B[d], B ? B + (int64_t)d * g.nown : nullptr))) return rc;
-        if ((rc = upload_owned(ctx, g, c->W[d], W ? W + (int64_t)d * g.nown : nullptr))) return rc;
-        if ((rc = upload_owned(ctx, g, c->Co[d], C_omega ? C_omega + (int64_t)d * g.nown : nullptr))) return rc;
-        if ((rc = upload_owned(ctx, g, c->Cg[d], C_gamma ? C_gamma + (int64_t)d * g.nown : nullptr))) return rc;
-    }
     c->has_cg = C_gamma != nullptr;
-    if ((rc = cap_halo(c))) return rc;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // every failure below leaves through ONE path that releases the partial object (pb200_capacity_destroy frees what exists)
+    auto body = [&]() -> int {
+        int rc = make_grid(ctx, ndim, n, x0, L, &c->g);
+        if (rc || (rc = cap_alloc(ctx, c))) return rc;
+        const Grid &g = c->g;
+        if ((rc = upload_owned(ctx, g, c->V, V)) || (rc = upload_owned(ctx, g, c->Gam, Gamma)) || (rc = upload_owned(ctx, g, c->ct, cell_types))) return rc;
+        for (int d = 0; d < g.N; ++d) {
+            if ((rc = upload_owned(ctx, g, c->A[d], A ? A + (int64_t)d * g.nown : nullptr))) return rc;
+            if ((rc = upload_owned(ctx, g, c->B[d], B ? B + (int64_t)d * g.nown : nullptr))) return rc;
+            if ((rc = upload_owned(ctx, g, c->W[d], W ? W + (int64_t)d * g.nown : nullptr))) return rc;
+            if ((rc = upload_owned(ctx, g, c->Co[d], C_omega ? C_omega + (int64_t)d * g.nown : nullptr))) return rc;
+            if (c->Cg[d] && (rc = upload_owned(ctx, g, c->Cg[d], C_gamma ? C_gamma + (int64_t)d * g.nown : nullptr))) return rc;
+        }
+        if ((rc = cap_halo(c))) return rc;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return PB200_OK;
+    };
+    const int rc = body();
+    if (rc) { const std::string msg = ctx->err; pb200_capacity_destroy(c); return set_err(ctx, rc, msg); }
     *out = c;
     return PB200_OK;
 }
@@ -180,17 +187,20 @@ extern "C" int pb200_capacity_create(pb200_ctx *ctx, int ndim, const int *n, con
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_capacity *c = new pb200_capacity();
     c->ctx = ctx;
-    int rc = make_grid(ctx, ndim, n, x0, L, &c->g);
-    if (!rc) rc = cap_alloc(ctx, c);
-    if (rc) { delete c; return rc; }
-    GeomOut go;
-    go.V = c->V; go.Gam = c->Gam; go.ct = c->ct;
-    for (int d = 0; d < PB_MAXD; ++d) { go.A[d] = c->A[d]; go.B[d] = c->B[d]; go.W[d] = c->W[d]; go.Co[d] = c->Co[d]; go.Cg[d] = c->Cg[d]; }
-    rc = geometry_build(ctx, c->g, ls, compute_centroids, go);
-    if (rc) return rc;
     c->has_cg = compute_centroids != 0;
-    if ((rc = cap_halo(c))) return rc;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    auto body = [&]() -> int {
+        int rc = make_grid(ctx, ndim, n, x0, L, &c->g);
+        if (rc || (rc = cap_alloc(ctx, c))) return rc;
+        GeomOut go;
+        go.V = c->V; go.Gam = c->Gam; go.ct = c->ct;
+        for (int d = 0; d < PB_MAXD; ++d) { go.A[d] = c->A[d]; go.B[d] = c->B[d]; go.W[d] = c->W[d]; go.Co[d] = c->Co[d]; go.Cg[d] = c->Cg[d]; }
+        if ((rc = geometry_build(ctx, c->g, ls, compute_centroids, go))) return rc;
+        if ((rc = cap_halo(c))) return rc;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return PB200_OK;
+    };
+    const int rc = body();
+    if (rc) { const std::string msg = ctx->err; pb200_capacity_destroy(c); return set_err(ctx, rc, msg); }
     *out = c;
     return PB200_OK;
 }
@@ -209,7 +219,8 @@ extern "C" int pb200_capacity_export(pb200_capacity *c, double *V, double *Gamma
         if ((rc = download_owned(ctx, g, B ? B + (int64_t)d * g.nown : nullptr, c->B[d]))) return rc;
         if ((rc = download_owned(ctx, g, W ? W + (int64_t)d * g.nown : nullptr, c->W[d]))) return rc;
         if ((rc = download_owned(ctx, g, C_omega ? C_omega + (int64_t)d * g.nown : nullptr, c->Co[d]))) return rc;
-        if ((rc = download_owned(ctx, g, C_gamma ? C_gamma + (int64_t)d * g.nown : nullptr, c->Cg[d]))) return rc;
+        if (C_gamma && !c->Cg[d]) memset(C_gamma + (int64_t)d * g.nown, 0, sizeof(double) * (size_t)g.nown);   // not computed (compute_centroids = 0)
+        else if ((rc = download_owned(ctx, g, C_gamma ? C_gamma + (int64_t)d * g.nown : nullptr, c->Cg[d]))) return rc;
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
@@ -347,6 +358,7 @@ struct pb200_solver {
     BorderDev bd;
     double *bvals[6] = {};
     bool masks_dirty = true;
+    bool values_dirty = false;           // border values changed, kinds did not: refresh ufix only
     unsigned char *m1 = nullptr, *m2 = nullptr;
     double *ufix1 = nullptr, *ufix2 = nullptr;
     double *Tw[2] = {}, *Tg[2] = {};
@@ -381,6 +393,7 @@ static int solver_vec(pb200_solver *s, MVec *v)
     return PB200_OK;
 }
 
+extern "C" int pb200_solver_destroy(pb200_solver *s);
 extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, pb200_solver **out)
 {
     if (!ctx || !d || !out || !d->ops1) return set_err(ctx, PB200_EINVAL, "NULL argument");
@@ -390,6 +403,7 @@ extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, p
     s->ctx = ctx;
     s->g = d->ops1->cap->g;
     const Grid &g = s->g;
+    auto body = [&]() -> int {   // every failure leaves through pb200_solver_destroy on the partial object (below)
     s->o1 = d->ops1; s->o2 = d->ops2;
     s->sp.phase_type = d->phase_type; s->sp.time_type = d->time_type; s->sp.ifc_kind = d->ifc_kind;
     s->sp.alpha = d->alpha; s->sp.beta = d->beta;
@@ -426,6 +440,10 @@ extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, p
     MVec *vs[] = {&s->x, &s->b, &s->r, &s->r0, &s->p, &s->ph, &s->v, &s->s, &s->sh, &s->t, &s->dinv};
     for (MVec *v : vs) if ((rc = solver_vec(s, v))) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+    };
+    const int rcb = body();
+    if (rcb) { const std::string msg = ctx->err; pb200_solver_destroy(s); return set_err(ctx, rcb, msg); }
     *out = s;
     return PB200_OK;
 }
@@ -468,17 +486,23 @@ extern "C" int pb200_solver_set_border(pb200_solver *s, int side, int kind, doub
     // which is what a Periodic row on the opposite side tests (src/solver.jl:458).  In 1-D the Neumann row is real (src/solver.jl:471-493).
     if (kind != PB200_BC_DIRICHLET && kind != PB200_BC_PERIODIC && !(kind == PB200_BC_NEUMANN && s->g.N == 1)) kind = PB200_BC_NONE;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // The reference's time loop calls BC_border_mono! every step (src/solver/diffusion.jl:291-293).  Masks, folded system and captured
+    // graphs depend on WHICH rows are pinned (kind / presence per side), not on the pinned values: a call that only changes values
+    // refreshes ufix with one light kernel at the next step; a call that changes nothing costs nothing.
+    const bool same_kind = s->bd.present[side] == 1 && s->bd.kind[side] == kind;
+    const bool had_arr = s->bd.values[side] != nullptr, has_arr = values && kind == PB200_BC_DIRICHLET;
+    if (!same_kind) s->masks_dirty = true;
+    else if (has_arr || had_arr || s->bd.value[side] != value) s->values_dirty = true;
     s->bd.present[side] = 1;
     s->bd.kind[side] = kind;
     s->bd.value[side] = value;
-    if (values && kind == PB200_BC_DIRICHLET) {
+    if (has_arr) {
         int64_t n = side_cells(s->g, side);
         if (!s->bvals[side]) CUDA_TRY(ctx, cudaMalloc((void **)&s->bvals[side], sizeof(double) * (size_t)n));
         CUDA_TRY(ctx, cudaMemcpyAsync(s->bvals[side], values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         s->bd.values[side] = s->bvals[side];
     } else s->bd.values[side] = nullptr;
-    s->masks_dirty = true;
     return PB200_OK;
 }
 
@@ -880,9 +904,9 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         int gm = F.nitems; if (gm > ctx->sm_count * 8) gm = ctx->sm_count * 8; if (gm < 1) gm = 1;
         DISPATCH_N(g.N, (kf_tile_meta<N><<<gm, FCH, 0, ctx->stream>>>(g, d, I, F.uni, F.ucoef, getenv("PB200_EXACT_TILES") ? 0.0 : 1e-12, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
         LAUNCH_CHECK(ctx);
-        double cnt[2];
-        if ((rc = fetch_results(ctx, SL_TMP, 2, cnt))) return rc;
-        F.cells_uniform = (long long)(cnt[0] + 0.5); F.cells_general = (long long)(cnt[1] + 0.5);
+        double cnt[3];
+        if ((rc = fetch_results(ctx, SL_TMP, 3, cnt))) return rc;
+        F.cells_uniform = (long long)(cnt[0] + 0.5); F.cells_general = (long long)(cnt[1] + 0.5); F.cells_fast = (long long)(cnt[2] + 0.5);
         // Static load balance of the operator apply.  The item-loop kernels hand item i to block i mod grid.  For the apply kernel a
         // tile with streamed coefficients or partial validity costs several times a constant-coefficient interior tile, and where those
         // sit in index order decides how many of them one block draws (measured: 296 -> 248 us per apply at 384^3).  The apply therefore
@@ -1405,7 +1429,14 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     (void)nonconstD;
     int rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (s->masks_dirty && (rc = build_masks(s))) return rc;
+    if (s->masks_dirty) { if ((rc = build_masks(s))) return rc; }
+    else if (s->values_dirty) {
+        k_refresh_ufix<<<sgrid(ctx, g.nown), RED_THREADS, 0, ctx->stream>>>(g, s->bd, s->m1, s->sp.phase_type == PB200_DIPH ? s->m2 : nullptr, s->ufix1, s->ufix2);
+        LAUNCH_CHECK(ctx);
+        double *fl[2] = {s->ufix1, s->ufix2};
+        if ((rc = halo_exchange(ctx, g, fl, 2))) return rc;
+    }
+    s->values_dirty = false;
 
     StepCoef sc;
     if (unsteady) {
@@ -1678,6 +1709,7 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         stats->apply_launches = ctx->apply_launches - applies0;
         stats->apply_cells_uniform = use_fold ? s->F.cells_uniform : 0;
         stats->apply_cells_general = use_fold ? s->F.cells_general : 0;
+        stats->apply_cells_fast = use_fold ? s->F.cells_fast : 0;
     }
     if (!converged) return set_err(ctx, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
     return PB200_OK;
