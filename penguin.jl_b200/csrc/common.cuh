@@ -35,6 +35,12 @@ struct pb200_ctx {
     unsigned *d_counter = nullptr;
     double *h_results = nullptr;   // pinned mirror
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // second stream of the fused Krylov iteration (fold2.cuh): ghost-class tiles + halo exchange run beside the interior class; kernels
+    // on it that reduce use their own scratch (they are concurrent with reducing kernels of the main stream)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    double *d_partials2 = nullptr;
+    unsigned *d_counter2 = nullptr;
     // peer-memory exchange (p2p.cuh): every rank's mailbox is mapped into every other rank with CUDA IPC; halos and the Krylov
     // scalar reductions are then plain kernels that store into the peers' mailboxes over NVLink and spin on sequence flags
     struct P2PState *p2p = nullptr;

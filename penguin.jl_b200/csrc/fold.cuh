@@ -18,6 +18,7 @@
 // phases of a diphasic problem are complementary, so streaming both dense would double the traffic); w lives in a compact
 // array over the band cells, sorted by cell index (ghost-plane entries form a prefix / suffix, so its halo is two contiguous ranges).
 #pragma once
+#include <cuda.h>
 #include <map>
 
 #include <thrust/execution_policy.h>
@@ -48,7 +49,14 @@ struct FoldDev {
     int *EB;         // [nE]
     int *EnbrB;      // [nE][2N]   (AoS: one warp works on one band cell)
     double *Eblk;    // [nE][(1+2N)*9]  block 0: self, 1+2d: lower neighbour in d, 2+2d: upper; each 3x3 row-major
+    // Krylov vectors (FVec bulk fields) live in a RE-PITCHED copy of the local grid: x rows padded from ld0 (the reference's odd n+1) to P0,
+    // a multiple of 32 doubles, so that every 32-cell tile row is 256-byte aligned and the arrays can be described to TMA (global
+    // strides must be multiples of 16 bytes).  They never cross the ABI; capacities, masks, states keep the reference pitch.
+    long long ld0, dP;           // reference pitch, P0 - ld0
+    long long sq[PB_MAXD];       // strides of the re-pitched layout (1, P0, P0 * ld1)
 };
+// re-pitched index of local cell l
+__device__ __forceinline__ long long fd_q(const FoldDev &fd, long long l) { return fd.dP ? l + (l / fd.ld0) * fd.dP : l; }
 
 struct FVec { double *f[3]; };   // f[0], f[1]: dense bulk fields; f[2]: compact w
 
@@ -64,11 +72,15 @@ struct FVec { double *f[3]; };   // f[0], f[1]: dense bulk fields; f[2]: compact
 #define FTILE (FCH * FU)
 struct __align__(16) TileRec {
     long long base;        // local linear index of the tile origin (w items: first entry)
+    long long baseq;       // the same cell in the re-pitched layout of the Krylov vectors (w items: = base)
+    int ox, oy, oz;        // tile origin in local array coordinates (TMA box coordinates)
     short nx;              // valid extent along x (w items: valid entries)
     signed char f;         // field: 0, 1 bulk, 2 w
     signed char ylo, yhi;  // valid range of the tile-relative y coordinate
     signed char zlo, zhi;  // valid range of the tile-relative z coordinate
     signed char full;      // 1: every cell of the tile is valid (interior tile)
+    signed char ghost;     // 1: the tile + halo box touches a ghost plane whose data comes from a neighbour rank
+    signed char pad_;
 };
 struct Items {
     const int *it; int n;
@@ -77,25 +89,34 @@ struct Items {
     int kx, ky, kz;                // tile-relative coordinate advance per k: (256,0,0) 1-D, (0,1,0) 2-D, (0,0,1) 3-D
     int tym;                       // thread row ty covers tile rows ty * tym + ky * k  (2-D: FU consecutive rows per thread; else 1)
     long long ustride;             // linear index advance per k
+    long long P0, ustrideq;        // x pitch and per-k advance of the re-pitched Krylov vectors
     long long ld0, ld1, ld2;       // local array extents
     int T0, T1, T2, nt0, nt1;      // tile extents and tiles per direction (build-time only)
     int sd, lz;                    // slab dimension and its local extent (first / last plane of it are ghosts)
+    int glo, ghi;                  // a neighbour rank exists below / above (its data fills that ghost plane)
     int wlo, whi;
     const unsigned char *uni;      // [n] bit 0: the tile's coefficients are constants (ucoef); bit 1: the tile holds band cells (kf_tile_meta)
     const double *ucoef;           // [n][PB_MAXD]
 };
-// cell k (0..FU-1) of this thread inside tile R: linear index and validity
-__device__ __forceinline__ bool tile_cell(const Items &I, const TileRec &R, int k, long long &idx)
+// cell k (0..FU-1) of this thread inside tile R: linear index (reference pitch), index in the re-pitched Krylov vectors, validity
+__device__ __forceinline__ bool tile_cell(const Items &I, const TileRec &R, int k, long long &idx, long long &q)
 {
     if (R.f >= 2) {   // compact w: 1-D layout
         const int xr = (int)threadIdx.x + FCH * k;
         idx = R.base + xr;
+        q = idx;
         return xr < R.nx;
     }
     const int tx = (int)threadIdx.x & ((1 << I.shx) - 1), ty = (int)threadIdx.x >> I.shx;
     const int xr = tx + I.kx * k, yr = ty * I.tym + I.ky * k, zr = I.kz * k;
     idx = R.base + tx + (long long)(ty * I.tym) * I.ld0 + (long long)k * I.ustride;
+    q = R.baseq + tx + (long long)(ty * I.tym) * I.P0 + (long long)k * I.ustrideq;
     return xr < R.nx && yr >= R.ylo && yr < R.yhi && zr >= R.zlo && zr < R.zhi;
+}
+__device__ __forceinline__ bool tile_cell(const Items &I, const TileRec &R, int k, long long &idx)
+{
+    long long q;
+    return tile_cell(I, R, k, idx, q);
 }
 __device__ __forceinline__ long long tile_of_cell(const Items &I, long long l)
 {
@@ -110,9 +131,10 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
         const int f = (int)(v >> 30);
         const long long ord = (long long)(v & 0x3fffffffu);
         TileRec R;
-        R.f = (signed char)f; R.full = 0;
+        R.f = (signed char)f; R.full = 0; R.ghost = 0; R.pad_ = 0; R.ox = R.oy = R.oz = 0;
         if (f >= 2) {
             R.base = (long long)I.wlo + ord * FTILE;
+            R.baseq = R.base;
             const long long left = (long long)I.whi - R.base;
             R.nx = (short)(left < FTILE ? left : FTILE);
             R.ylo = 0; R.yhi = 1; R.zlo = 0; R.zhi = 1;
@@ -131,9 +153,17 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
                 lo[d] = (int)a; hi[d] = (int)b;
             }
             R.base = o[0] + I.ld0 * (o[1] + I.ld1 * o[2]);
+            R.baseq = o[0] + I.P0 * (o[1] + I.ld1 * o[2]);
+            R.ox = (int)o[0]; R.oy = (int)o[1]; R.oz = (int)o[2];
             // x validity is [0, nx): the slab dimension is x only for 1-D grids, where the lower ghost is excluded by shifting the base
-            if (I.sd == 0) { R.base += lo[0]; R.nx = (short)(hi[0] - lo[0]); }
+            if (I.sd == 0) { R.base += lo[0]; R.baseq += lo[0]; R.nx = (short)(hi[0] - lo[0]); }
             else R.nx = (short)hi[0];
+            // does the box (tile + one halo cell) reach a ghost plane of the slab dimension that a neighbour rank fills?
+            if (I.sd > 0) {
+                const long long osd = o[I.sd];
+                const int Tsd = T[I.sd];
+                if ((I.glo && osd - 1 <= 0) || (I.ghi && osd + Tsd >= I.lz - 1)) R.ghost = 1;
+            }
             R.ylo = (signed char)lo[1]; R.yhi = (signed char)hi[1]; R.zlo = (signed char)lo[2]; R.zhi = (signed char)hi[2];
             R.full = (lo[0] == 0 && hi[0] == T[0] && lo[1] == 0 && hi[1] == T[1] && lo[2] == 0 && hi[2] == T[2]) ? 1 : 0;
         }
@@ -143,7 +173,10 @@ __global__ void kf_tile_records(Items I, TileRec *rec)
 
 // result slots of the folded Krylov loops (dense-part and band-part partial sums are adjacent: one allreduce covers both)
 // (rho, rr, rho_band, rho_poly_band) groups live in two ping-pong sets {0..3} and {4..7}: one allreduce of 4 doubles publishes a new group
-enum { FS_PAIR0 = 0, FS_PAIR1 = 4, FS_SIG_D = 8, FS_SIG_B = 9, FS_TS_D = 10, FS_TT_D = 11, FS_TS_B = 12, FS_TT_B = 13, FS_BB = 14, FS_RR0 = 15, FS_ITERS = 16, FS_TMP = 17 };
+// FS_SIG_G: (p, v) partial of the ghost-class tiles (fold2.cuh); FS_ALPHA / FS_XPEND: alpha_k and "x += alpha_k p_k still pending" of the fused iteration
+enum { FS_PAIR0 = 0, FS_PAIR1 = 4, FS_SIG_D = 8, FS_SIG_B = 9, FS_SIG_G = 10, FS_TS_D = 11, FS_TT_D = 12, FS_TS_B = 13, FS_TT_B = 14, FS_BB = 15, FS_RR0 = 16, FS_ITERS = 17,
+       FS_TMP = 18 /* and 19 */, FS_ALPHA = 20, FS_XPEND = 21 };
+static_assert(FS_XPEND < RED_SLOTS, "result slots");
 #define FS_TRIPLE(p) (4 * (p))
 #define FS_NGROUP 4
 // rho of the group at slot sl = (r, z) with z = q(M^) r + (q_B(M^_BB) - 1) r_B:
@@ -522,15 +555,15 @@ __global__ void __launch_bounds__(FCH, 4) kf_apply_dense(Grid g, FoldDev fd, Ite
             // come from the adjacent lanes (a warp is one 32-cell row; only lanes 0 and 31 load the halo), y-neighbours are loaded in 3-D.
             const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
             const int lane = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
-            const long long ks = I.ustride;
-            const long long l0 = R.base + lane + (long long)(ty * I.tym) * I.ld0;
+            const long long ks = I.ustrideq;                       // (Krylov vectors: re-pitched layout)
+            const long long l0 = R.baseq + lane + (long long)(ty * I.tym) * I.P0;
             const double *__restrict__ p0 = xf + l0;
             double col[FU + 2], yn[FU][2], avv[FU];
 #pragma unroll
             for (int k = -1; k <= FU; ++k) col[k + 1] = p0[k * ks];
             if (N == 3) {
 #pragma unroll
-                for (int k = 0; k < FU; ++k) { yn[k][0] = p0[k * ks - I.ld0]; yn[k][1] = p0[k * ks + I.ld0]; }
+                for (int k = 0; k < FU; ++k) { yn[k][0] = p0[k * ks - I.P0]; yn[k][1] = p0[k * ks + I.P0]; }
             }
             if (MODE == 2 || MODE == 4) {
 #pragma unroll
@@ -571,32 +604,34 @@ __global__ void __launch_bounds__(FCH, 4) kf_apply_dense(Grid g, FoldDev fd, Ite
         const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
         constexpr int GP = PB_APPLY_GP(N);
         const long long lsafe = R.base + (long long)R.ylo * I.ld0 + (long long)R.zlo * I.ld0 * I.ld1;
+        const long long qsafe = R.baseq + (long long)R.ylo * I.P0 + (long long)R.zlo * I.P0 * I.ld1;
         const double *__restrict__ of0 = f == 0 ? fd.off[0][0] : fd.off[1][0];
         const double *__restrict__ of1 = f == 0 ? fd.off[0][N > 1 ? 1 : 0] : fd.off[1][N > 1 ? 1 : 0];
         const double *__restrict__ of2 = f == 0 ? fd.off[0][N > 2 ? 2 : 0] : fd.off[1][N > 2 ? 2 : 0];
 #pragma unroll 1
         for (int k0 = 0; k0 < FU; k0 += GP) {
-            long long l[GP];
+            long long l[GP], lq[GP];
             bool ok[GP];
             double xl[GP], av[GP], cm[GP][N], cp[GP][N], xm[GP][N], xp[GP][N];
 #pragma unroll
             for (int j = 0; j < GP; ++j) {
-                long long t;
-                ok[j] = tile_cell(I, R, k0 + j, t);
+                long long t, tq;
+                ok[j] = tile_cell(I, R, k0 + j, t, tq);
                 l[j] = ok[j] ? t : lsafe;
+                lq[j] = ok[j] ? tq : qsafe;
             }
 #pragma unroll
             for (int j = 0; j < GP; ++j) {
-                xl[j] = xf[l[j]];
-                av[j] = (MODE == 2 || MODE == 4) ? af[l[j]] : 0.0;
+                xl[j] = xf[lq[j]];
+                av[j] = (MODE == 2 || MODE == 4) ? af[lq[j]] : 0.0;
 #pragma unroll
                 for (int d = 0; d < N; ++d) {
-                    const long long s = g.stride[d];
+                    const long long s = g.stride[d], sq = fd.sq[d];
                     const double *__restrict__ of = d == 0 ? of0 : (d == 1 ? of1 : of2);
                     if (uni) { cm[j][d] = uc[d]; cp[j][d] = uc[d]; }
                     else { cm[j][d] = of[l[j]]; cp[j][d] = of[l[j] + s]; }
-                    xm[j][d] = xf[l[j] - s];
-                    xp[j][d] = xf[l[j] + s];
+                    xm[j][d] = xf[lq[j] - sq];
+                    xp[j][d] = xf[lq[j] + sq];
                 }
             }
 #pragma unroll
@@ -606,7 +641,7 @@ __global__ void __launch_bounds__(FCH, 4) kf_apply_dense(Grid g, FoldDev fd, Ite
                 for (int d = 0; d < N; ++d) acc += cm[j][d] * xm[j][d] + cp[j][d] * xp[j][d];
                 if (MODE == 4) acc = pc.r * av[j] + pc.z * xl[j] + pc.A * acc;
                 if (ok[j]) {
-                    yf[l[j]] = acc;
+                    yf[lq[j]] = acc;
                     if (MODE == 1) v[0] += xl[j] * acc;
                     if (MODE == 2 || MODE == 4) v[0] += av[j] * acc;
                     if (MODE == 3) { v[0] += acc * xl[j]; v[1] += acc * acc; }
@@ -634,11 +669,11 @@ __device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int 
     double xv = 0.0;
     if (lane < NX) {
         const int k = lane / 3, c = lane - 3 * k;
-        long long ln = l;
+        long long ln = fd_q(fd, l);   // (index into the re-pitched Krylov vectors)
         int nb = bo;
         if (k > 0) {
             const int kk = k - 1, d = kk >> 1;
-            ln = (kk & 1) ? l + g.stride[d] : l - g.stride[d];
+            ln = (kk & 1) ? ln + fd.sq[d] : ln - fd.sq[d];
             nb = fd.EnbrB[(size_t)e * (2 * N) + kk];
         }
         // BAND_ONLY: the preconditioner block is the band block of THIS rank (neighbours in the ghost planes are left out), so that
@@ -691,10 +726,11 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
         long long l; int bo;
         band_rows<N, false>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
         if (lane == 0 && live) {
-            const double y0p = y.f[0][l], y1p = two ? y.f[1][l] : 0.0;
+            const long long lq = fd_q(fd, l);
+            const double y0p = y.f[0][lq], y1p = two ? y.f[1][lq] : 0.0;
             if (MODE == 4) { a0 *= pc.A; a1 *= pc.A; }   // the dense kernel has written pc.r aux + pc.z x + pc.A (dense part of M^ x)
-            y.f[0][l] = y0p + a0;
-            if (two) y.f[1][l] = y1p + a1;
+            y.f[0][lq] = y0p + a0;
+            if (two) y.f[1][lq] = y1p + a1;
             double yw = 0.0;
             if (bo >= 0) {
                 yw = xw + a2;
@@ -702,7 +738,7 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
                 y.f[2][bo] = yw;
             }
             if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
-            if (MODE == 2 || MODE == 4) v[0] += aux.f[0][l] * a0 + (two ? aux.f[1][l] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
+            if (MODE == 2 || MODE == 4) v[0] += aux.f[0][lq] * a0 + (two ? aux.f[1][lq] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
             if (MODE == 3) {
                 v[0] += x0 * a0 + x1 * a1 + xw * yw;
                 v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
@@ -751,8 +787,9 @@ __global__ void kf_band_put(FoldDev fd, FVec x, const double *in, double scale, 
     for (int k = fd.nBlo + blockIdx.x * blockDim.x + threadIdx.x; k < fd.nBlo + fd.nBown; k += gridDim.x * blockDim.x) {
         const long long l = fd.Bcell[k];
         const double v0 = scale * in[(size_t)0 * fd.nB + k], v1 = scale * in[(size_t)1 * fd.nB + k], v2 = scale * in[(size_t)2 * fd.nB + k];
-        if (add) { x.f[0][l] += v0; if (fd.nbulk > 1) x.f[1][l] += v1; x.f[2][k] += v2; }
-        else { x.f[0][l] = v0; if (fd.nbulk > 1) x.f[1][l] = v1; x.f[2][k] = v2; }
+        const long long lq = fd_q(fd, l);
+        if (add) { x.f[0][lq] += v0; if (fd.nbulk > 1) x.f[1][lq] += v1; x.f[2][k] += v2; }
+        else { x.f[0][lq] = v0; if (fd.nbulk > 1) x.f[1][lq] = v1; x.f[2][k] = v2; }
     }
 }
 // deterministic pseudo-random start vector on the band (power iteration)
@@ -774,31 +811,34 @@ __global__ void kf_band_seed(FoldDev fd, double *out)
         if (const TileRec R__ = (I).rec[it__]; true)                \
             if (const int f = R__.f; true)                          \
                 _Pragma("unroll") for (int k__ = 0; k__ < FU; ++k__) \
-                    if (long long i = 0; tile_cell((I), R__, k__, i))
+                    if (long long i = 0, q = 0; tile_cell((I), R__, k__, i, q))
 
-__global__ void __launch_bounds__(FCH) kf_zero(Items I, FVec a) { FV_LOOP(I) a.f[f][i] = 0.0; }
+// (FV_LOOP: i = index in reference-pitch arrays (capacities, masks, states, MVec), q = index in the re-pitched Krylov vectors (FVec))
+__global__ void __launch_bounds__(FCH) kf_zero(Items I, FVec a) { FV_LOOP(I) { (void)i; a.f[f][q] = 0.0; } }
 // deterministic pseudo-random start vector in (-1, 1) (power iteration for the top of the spectrum of M^)
 __global__ void __launch_bounds__(FCH) kf_seed(Items I, FVec a)
 {
     FV_LOOP(I) {
         unsigned long long h = (unsigned long long)(i * 3 + f + 1) * 0x9E3779B97F4A7C15ull;
         h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
-        a.f[f][i] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        a.f[f][q] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
     }
 }
-__global__ void __launch_bounds__(FCH) kf_copy2(Items I, FVec a, FVec b, FVec c) { FV_LOOP(I) { const double v = a.f[f][i]; b.f[f][i] = v; c.f[f][i] = v; } }
+__global__ void __launch_bounds__(FCH) kf_copy2(Items I, FVec a, FVec b, FVec c) { FV_LOOP(I) { (void)i; const double v = a.f[f][q]; b.f[f][q] = v; c.f[f][q] = v; } }
 // r = b - q ; publishes (r, r)
 // first residual of a solve, one pass: r = b - q (q == nullptr fields: r = b), copies of r into p (and r0), publishes ((b, b), (r, r))
-__global__ void __launch_bounds__(FCH) kf_resid(Items I, FVec b, FVec q, int have_q, FVec r, FVec p, FVec r0, int have_r0, double *partials, double *results,
+// pzero: p = 0 instead of r (the fused CG iteration forms its first direction itself: p_0 = z_0 + beta_0 * 0)
+__global__ void __launch_bounds__(FCH) kf_resid(Items I, FVec b, FVec qv, int have_q, FVec r, FVec p, FVec r0, int have_r0, int pzero, double *partials, double *results,
                                                 unsigned *counter)
 {
     double v[2] = {0.0, 0.0};
     FV_LOOP(I) {
-        const double bv = b.f[f][i];
-        const double x = have_q ? bv - q.f[f][i] : bv;
-        r.f[f][i] = x;
-        p.f[f][i] = x;
-        if (have_r0) r0.f[f][i] = x;
+        (void)i;
+        const double bv = b.f[f][q];
+        const double x = have_q ? bv - qv.f[f][q] : bv;
+        r.f[f][q] = x;
+        p.f[f][q] = pzero ? 0.0 : x;
+        if (have_r0) r0.f[f][q] = x;
         v[0] += bv * bv;
         v[1] += x * x;
     }
@@ -807,7 +847,7 @@ __global__ void __launch_bounds__(FCH) kf_resid(Items I, FVec b, FVec q, int hav
 __global__ void __launch_bounds__(FCH) kf_dot(Items I, FVec a, FVec b, double *partials, double *results, unsigned *counter)
 {
     double v[1] = {0.0};
-    FV_LOOP(I) v[0] += a.f[f][i] * b.f[f][i];
+    FV_LOOP(I) { (void)i; v[0] += a.f[f][q] * b.f[f][q]; }
     block_reduce_publish<1>(v, partials, results, counter);
 }
 // CG: r -= alpha q ; publishes (rho_new, rr) = ((r, r), (r, r)).  (x += alpha p is done by kf_cg_p, which reads p anyway.)
@@ -822,17 +862,17 @@ __global__ void __launch_bounds__(FCH) kf_cg_update(Items I, double *res, int sl
         const int f = R.f;
         const double *__restrict__ qf = f == 0 ? q.f[0] : (f == 1 ? q.f[1] : q.f[2]);
         double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
-        long long i[FU]; bool ok[FU]; double qv[FU], rv[FU];
+        long long i[FU], iq[FU]; bool ok[FU]; double qv[FU], rv[FU];
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
-            ok[k] = tile_cell(I, R, k, i[k]);
-            if (ok[k]) { qv[k] = qf[i[k]]; rv[k] = rf[i[k]]; }
+            ok[k] = tile_cell(I, R, k, i[k], iq[k]);
+            if (ok[k]) { qv[k] = qf[iq[k]]; rv[k] = rf[iq[k]]; }
         }
 #pragma unroll
         for (int k = 0; k < FU; ++k)
             if (ok[k]) {
                 const double rn = rv[k] - alpha * qv[k];
-                rf[i[k]] = rn;
+                rf[iq[k]] = rn;
                 v[0] += rn * rn;
             }
     }
@@ -859,11 +899,11 @@ __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho,
         double *__restrict__ pf = f == 0 ? p.f[0] : (f == 1 ? p.f[1] : p.f[2]);
         double *__restrict__ xf = f == 0 ? x.f[0] : (f == 1 ? x.f[1] : x.f[2]);
         const bool band_tile = dz != nullptr && (f == 2 || (I.uni[it] & 2));
-        long long i[FU]; bool ok[FU]; double pv[FU], rv[FU], xv[FU];
+        long long i[FU], iq[FU]; bool ok[FU]; double pv[FU], rv[FU], xv[FU];
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
-            ok[k] = tile_cell(I, R, k, i[k]);
-            if (ok[k]) { pv[k] = pf[i[k]]; xv[k] = xf[i[k]]; rv[k] = last ? 0.0 : rf[i[k]]; }
+            ok[k] = tile_cell(I, R, k, i[k], iq[k]);
+            if (ok[k]) { pv[k] = pf[iq[k]]; xv[k] = xf[iq[k]]; rv[k] = last ? 0.0 : rf[iq[k]]; }
         }
         if (band_tile && !last) {
 #pragma unroll
@@ -876,8 +916,8 @@ __global__ void __launch_bounds__(FCH) kf_cg_p(Items I, double *res, int sl_rho,
 #pragma unroll
         for (int k = 0; k < FU; ++k)
             if (ok[k]) {
-                xf[i[k]] = xv[k] + alpha * pv[k];
-                if (!last) pf[i[k]] = rv[k] + beta * pv[k];
+                xf[iq[k]] = xv[k] + alpha * pv[k];
+                if (!last) pf[iq[k]] = rv[k] + beta * pv[k];
             }
     }
 }
@@ -886,7 +926,7 @@ __global__ void __launch_bounds__(FCH) kf_bicg_s(Items I, const double *res, int
 {
     if (fold_done(res, stop)) return;
     const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
-    FV_LOOP(I) s.f[f][i] = r.f[f][i] - alpha * v.f[f][i];
+    FV_LOOP(I) { (void)i; s.f[f][q] = r.f[f][q] - alpha * v.f[f][q]; }
 }
 __global__ void __launch_bounds__(FCH) kf_bicg_xr(Items I, double *res, int sl_rho, int sl_new, FVec p, FVec s, FVec t, FVec r0, FVec x, FVec r, double *partials,
                                                   unsigned *counter, StopCrit stop)
@@ -897,11 +937,12 @@ __global__ void __launch_bounds__(FCH) kf_bicg_xr(Items I, double *res, int sl_r
     const double omega = safe_div(res[FS_TS_D] + res[FS_TS_B], res[FS_TT_D] + res[FS_TT_B]);
     double v[2] = {0.0, 0.0};
     FV_LOOP(I) {
-        const double sv = s.f[f][i];
-        x.f[f][i] += alpha * p.f[f][i] + omega * sv;
-        const double rn = sv - omega * t.f[f][i];
-        r.f[f][i] = rn;
-        v[0] += r0.f[f][i] * rn;
+        (void)i;
+        const double sv = s.f[f][q];
+        x.f[f][q] += alpha * p.f[f][q] + omega * sv;
+        const double rn = sv - omega * t.f[f][q];
+        r.f[f][q] = rn;
+        v[0] += r0.f[f][q] * rn;
         v[1] += rn * rn;
     }
     block_reduce_publish<2>(v, partials, res + sl_new, counter);
@@ -912,7 +953,7 @@ __global__ void __launch_bounds__(FCH) kf_bicg_p(Items I, const double *res, int
     const double alpha = safe_div(res[sl_rho], res[FS_SIG_D] + res[FS_SIG_B]);
     const double omega = safe_div(res[FS_TS_D] + res[FS_TS_B], res[FS_TT_D] + res[FS_TT_B]);
     const double beta = safe_div(res[sl_new], res[sl_rho]) * safe_div(alpha, omega);
-    FV_LOOP(I) p.f[f][i] = r.f[f][i] + beta * (p.f[f][i] - omega * v.f[f][i]);
+    FV_LOOP(I) { (void)i; p.f[f][q] = r.f[f][q] + beta * (p.f[f][q] - omega * v.f[f][q]); }
 }
 
 // iteration skipped by the stopping test: copy the (rho, rr) pair forward
@@ -930,7 +971,7 @@ __device__ __forceinline__ double fold_rowscale(const FoldDev &fd, int p, long l
 // b^ = L^-1 (rowscale . b): dense part (band cells get 0 here, the band kernel overwrites them)
 __global__ void __launch_bounds__(FCH) kf_to_scaled_dense(FoldDev fd, Items I, MVec b, FVec bh)
 {
-    FV_LOOP(I) { if (f < 2) bh.f[f][i] = fd.sc[f][i] * fold_rowscale(fd, f, i) * b.f[f][i]; }
+    FV_LOOP(I) { if (f < 2) bh.f[f][q] = fd.sc[f][i] * fold_rowscale(fd, f, i) * b.f[f][i]; }
 }
 __global__ void kf_to_scaled_band(FoldDev fd, MVec b, FVec bh)
 {
@@ -942,8 +983,9 @@ __global__ void kf_to_scaled_band(FoldDev fd, MVec b, FVec bh)
         const double v0 = I5[0] != 0.0 ? fold_rowscale(fd, 0, l) * b.f[0][l] : 0.0;
         const double v1 = (fd.nbulk > 1 && I5[1] != 0.0) ? fold_rowscale(fd, 1, l) * b.f[1][l] : 0.0;
         const double vw = fd.wrow * b.f[fd.nbulk][l];
-        bh.f[0][l] = I5[0] * v0;
-        if (fd.nbulk > 1) bh.f[1][l] = I5[1] * v1;
+        const long long lq = fd_q(fd, l);
+        bh.f[0][lq] = I5[0] * v0;
+        if (fd.nbulk > 1) bh.f[1][lq] = I5[1] * v1;
         bh.f[2][k] = I5[2] * v0 + I5[3] * v1 + I5[4] * vw;
     }
 }
@@ -961,7 +1003,7 @@ __global__ void __launch_bounds__(FCH) kf_guess_dense(FoldDev fd, Items I, Guess
     FV_LOOP(I) {
         if (f < 2) {
             const double s = fd.sc[f][i];     // non-zero exactly on the free, non-band unknowns
-            xh.f[f][i] = s != 0.0 ? guess_at(f == 0 ? g0 : g1, i) / s : 0.0;
+            xh.f[f][q] = s != 0.0 ? guess_at(f == 0 ? g0 : g1, i) / s : 0.0;
         }
     }
 }
@@ -995,11 +1037,11 @@ __global__ void __launch_bounds__(FCH, 4) kf_rhs_dense(FoldDev fd, Items I, Step
         double *__restrict__ bo = f1 ? b.f[1] : b.f[0], *__restrict__ bho = f1 ? bh.f[1] : bh.f[0], *__restrict__ xo = f1 ? xh.f[1] : xh.f[0];
         const double *__restrict__ ve = f1 ? vexp.f[1] : vexp.f[0];
         const double cT = ve ? 2.0 * sc.cV : sc.cV;
-        long long idx[FU];
+        long long idx[FU], idq[FU];
         bool ok[FU];
         double s[FU], v[FU], gs[FU], ex[FU];
 #pragma unroll
-        for (int k = 0; k < FU; ++k) ok[k] = tile_cell(I, R, k, idx[k]);
+        for (int k = 0; k < FU; ++k) ok[k] = tile_cell(I, R, k, idx[k], idq[k]);
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             s[k] = 0.0; v[k] = 0.0; gs[k] = 0.0; ex[k] = 0.0;
@@ -1009,7 +1051,7 @@ __global__ void __launch_bounds__(FCH, 4) kf_rhs_dense(FoldDev fd, Items I, Step
                 s[k] = scf[i];
                 const bool fr = (m[i] & MB_FREE) != 0;
                 const double V = Vf[i], T = Tw[i], q0 = fa0 ? fa0[i] : fc0, q1 = fa1 ? fa1[i] : fc1;
-                if (ve) ex[k] = ve[i];
+                if (ve) ex[k] = ve[idq[k]];
                 double gsum = 0.0;
 #pragma unroll
                 for (int j = 0; j < PB_MAXHIST; ++j)
@@ -1021,10 +1063,10 @@ __global__ void __launch_bounds__(FCH, 4) kf_rhs_dense(FoldDev fd, Items I, Step
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             if (ok[k]) {
-                const long long i = idx[k];
+                const long long i = idx[k], iq = idq[k];
                 bo[i] = v[k];
-                bho[i] = s[k] != 0.0 ? s[k] * (sF / (fd.c * (Da ? Da[i] : Dc))) * v[k] - ex[k] : 0.0;   // = sc fold_rowscale b (- M^ x^n)
-                if (g0.m > 0) xo[i] = s[k] != 0.0 ? gs[k] / s[k] : 0.0;
+                bho[iq] = s[k] != 0.0 ? s[k] * (sF / (fd.c * (Da ? Da[i] : Dc))) * v[k] - ex[k] : 0.0;   // = sc fold_rowscale b (- M^ x^n)
+                if (g0.m > 0) xo[iq] = s[k] != 0.0 ? gs[k] / s[k] : 0.0;
             }
         }
     }
@@ -1036,7 +1078,7 @@ __global__ void kf_to_scaled_list(FoldDev fd, const long long *__restrict__ list
         const long long l = list[k];
         for (int f = 0; f < fd.nbulk; ++f) {
             const double s = fd.sc[f][l];
-            if (s != 0.0) bh.f[f][l] = s * fold_rowscale(fd, f, l) * b.f[f][l];
+            if (s != 0.0) bh.f[f][fd_q(fd, l)] = s * fold_rowscale(fd, f, l) * b.f[f][l];
         }
     }
 }
@@ -1050,15 +1092,16 @@ __global__ void kf_guess_band(FoldDev fd, GuessSpec g0, GuessSpec g1, GuessSpec 
         const double l00 = I5[0] != 0.0 ? 1.0 / I5[0] : 0.0, l11 = I5[1] != 0.0 ? 1.0 / I5[1] : 0.0, l22 = 1.0 / I5[4];
         const double l20 = -I5[2] * l00 * l22, l21 = -I5[3] * l11 * l22;
         const double x0 = I5[0] != 0.0 ? guess_at(g0, l) : 0.0, x1 = (fd.nbulk > 1 && I5[1] != 0.0) ? guess_at(g1, l) : 0.0, xw = guess_at(gw, l);
-        xh.f[0][l] = l00 * x0 + l20 * xw;
-        if (fd.nbulk > 1) xh.f[1][l] = l11 * x1 + l21 * xw;
+        const long long lq = fd_q(fd, l);
+        xh.f[0][lq] = l00 * x0 + l20 * xw;
+        if (fd.nbulk > 1) xh.f[1][lq] = l11 * x1 + l21 * xw;
         xh.f[2][k] = l22 * xw;
     }
 }
 // x = L^-T x^
 __global__ void __launch_bounds__(FCH) kf_from_scaled_dense(FoldDev fd, Items I, FVec xh, MVec x)
 {
-    FV_LOOP(I) { if (f < 2) x.f[f][i] = fd.sc[f][i] * xh.f[f][i]; }
+    FV_LOOP(I) { if (f < 2) x.f[f][i] = fd.sc[f][i] * xh.f[f][q]; }
 }
 __global__ void kf_from_scaled_band(FoldDev fd, FVec xh, MVec x)
 {
@@ -1068,8 +1111,9 @@ __global__ void kf_from_scaled_band(FoldDev fd, FVec xh, MVec x)
 #pragma unroll
         for (int q = 0; q < 5; ++q) I5[q] = fd.Linv[(size_t)q * fd.nB + k];
         const double hw = xh.f[2][k];
-        x.f[0][l] = I5[0] * xh.f[0][l] + I5[2] * hw;
-        if (fd.nbulk > 1) x.f[1][l] = I5[1] * xh.f[1][l] + I5[3] * hw;
+        const long long lq = fd_q(fd, l);
+        x.f[0][l] = I5[0] * xh.f[0][lq] + I5[2] * hw;
+        if (fd.nbulk > 1) x.f[1][l] = I5[1] * xh.f[1][lq] + I5[3] * hw;
         x.f[fd.nbulk][l] = I5[4] * hw;
     }
 }
@@ -1101,12 +1145,19 @@ struct FoldSys {
     long long cells_fast = 0;                         // cells of full tiles with constant coefficients (the apply kernel's staged interior branch)
     Items I;                                // every item, index order (vector kernels)
     Items IA;                               // bulk tiles in cost-class order (operator apply)
-    int *itemsA = nullptr; TileRec *recA = nullptr; unsigned char *uniA = nullptr; double *ucoefA = nullptr;
+    Items IAi, IAg;                         // ... split into the interior class and the ghost class (box reaches a neighbour rank's ghost plane)
+    Items IG1;                              // ghost-class tiles + compact interface unknowns: pointwise p / x update of the fused iteration
+    std::vector<void *> list_mem;           // device arrays behind the sub-lists
     FVec x, b, r, p, v, r0, s, t, z;
+    FVec p2 = {}, zz = {};                  // fused iteration: second search-direction buffer, preconditioned residual (polynomial)
+    bool have_p2 = false, have_zz = false;
+    bool tma_ok = false;                    // the Krylov vectors are describable to TMA (fold2.cuh)
+    std::map<const double *, CUtensorMap> tmaps;
     bool have_bicg = false, have_z = false;
     int poly_m = 0;                         // degree of the polynomial preconditioner q(M^) (0: none)
     double poly_lo = 0.0, poly_hi = 0.0;    // Chebyshev interval of the bulk spectrum
     long long wcap = 0;
+    long long P0 = 0, nlocq = 0, planeq = 0;   // x pitch, size and slab-plane size of the re-pitched Krylov vectors
     double key[8] = {};   // coefficient set the system was built for
 };
 
@@ -1121,11 +1172,12 @@ static void fold_free(FoldSys &F)
     if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
-    if (F.itemsA) cudaFree(F.itemsA); if (F.recA) cudaFree(F.recA); if (F.uniA) cudaFree(F.uniA); if (F.ucoefA) cudaFree(F.ucoefA);
-    F.itemsA = nullptr; F.recA = nullptr; F.uniA = nullptr; F.ucoefA = nullptr;
-    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t, &F.z};
+    for (void *m : F.list_mem) cudaFree(m);
+    F.list_mem.clear();
+    F.tmaps.clear();
+    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t, &F.z, &F.p2, &F.zz};
     for (FVec *a : vs) fold_free_vec(*a);
-    F.built = false; F.have_bicg = false; F.have_z = false;
+    F.built = false; F.have_bicg = false; F.have_z = false; F.have_p2 = false; F.have_zz = false; F.tma_ok = false;
 }
 
 static const int PB_NCCL_UINT8 = 1;

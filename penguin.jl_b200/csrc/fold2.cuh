@@ -1,0 +1,309 @@
+// fold2.cuh -- TMA-staged operator apply of the folded system and the fused CG iteration built on it.
+//
+// What it replaces: kf_apply_dense (fold.cuh: tile in registers + warp shuffles, neighbours re-loaded per thread) and kf_cg_p.
+// Reference rows behind the operator: /root/reference/src/solver/diffusion.jl:212-241, 334-389 (see fold.cuh for the algebra).
+//
+// Staging.  The Krylov vectors live in a re-pitched copy of the local grid (x pitch = multiple of 32 doubles), which makes them
+// describable to the Tensor Memory Accelerator: one `cp.async.bulk.tensor` (SASS: UTMALDG) brings a tile PLUS its one-cell halo --
+// a 34 x 34 (2-D) or 34 x 10 x 6 (3-D) box of doubles -- into shared memory and signals an mbarrier; out-of-range coordinates (boxes
+// hanging over the array) are zero-filled by the hardware.  A block walks its tile list with TWO stages: the box of tile i+1 is in
+// flight while tile i is computed, so the dependent chain record -> address -> data that bounded the register kernel (one round trip
+// per tile, 20 us launches at 2048^2) is gone, and every neighbour value is read once from L2 instead of up to 3 times.
+//
+// Fusion (MODE 5).  The CG search-direction update needs no pass of its own: p_k = z_k + beta_k p_{k-1} is formed IN SHARED MEMORY on the
+// tile + halo from the staged boxes of z and p_{k-1} (recomputing the halo ring is 13 % more flops and no extra DRAM traffic), the
+// solution update x += alpha_{k-1} p_{k-1} rides along on the tile's own cells, and v = M^ p_k with the partial sum of (p_k, v) follows.
+// Per unknown and iteration the CG then moves 48 B here + 24 B in kf_cg_update = 72 B in 2 streaming launches instead of 80 B in 3.
+// p is double-buffered (neighbouring blocks still read p_{k-1} halos while this block stores p_k).
+//
+// Slab-partitioned grids: tiles whose box reaches a ghost plane that a neighbour rank fills ("ghost class") cannot recompute p_k there.
+// They take the unfused route on a second stream -- kf2_pupd (pointwise p update) -> halo exchange of p_k -> plain staged apply --
+// WHILE the interior class runs the fused kernel: the halo exchange is overlapped with the interior stencil work.
+#pragma once
+#include <cuda.h>
+
+#include "fold.cuh"
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f2_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void f2_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f2_mbar_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void f2_tma_load_2d(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"((unsigned long long)m), "r"(bar),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void f2_tma_load_3d(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"((unsigned long long)m),
+                 "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+template <int N> struct F2Box {
+    static constexpr int BX = 34, BY = N == 2 ? 34 : 10, BZ = N == 2 ? 1 : 6;
+    static constexpr int NB = BX * BY * BZ;
+    static constexpr int BYTES = NB * 8;                           // what one TMA box delivers
+    static constexpr int SLOT = (BYTES + 127) / 128 * 128;         // 128-byte aligned shared-memory slot
+};
+struct alignas(64) F2Maps { CUtensorMap a[2]; CUtensorMap b[2]; };   // per bulk field: a = the staged vector (x, or z in MODE 5), b = p_{k-1} (MODE 5)
+
+struct F2Args {
+    FVec a, pold, y, pnew, xs, aux;
+    const double *dz; const int *bord; int nB;    // band preconditioner correction z_B - r_B (MODE 5, kf2_pupd); nullptr: none
+    int sl_old, sl_cur;                           // rho groups of the previous / the current iteration
+    StopCrit stop;
+    PolyCoef pc;
+    double *partials, *results; unsigned *counter;
+    const double *res;
+};
+
+// MODE 0..4: as kf_apply_dense (0 no dot; 1 (x, y); 2 (aux, y); 3 (y, x), (y, y); 4 y = pc.r aux + pc.z x + pc.A M^ x with (aux, y)).
+// MODE 5: fused CG step (header).  `maps` must describe A.a (and A.pold for MODE 5).
+template <int N, int MODE>
+__global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_constant__ F2Maps maps, Grid g, FoldDev fd, Items I, F2Args A)
+{
+    using B = F2Box<N>;
+    constexpr int NA = MODE == 5 ? 2 : 1;
+    constexpr int STAGE = NA * B::SLOT;
+    extern __shared__ __align__(128) unsigned char f2_smem[];
+    __shared__ __align__(8) unsigned long long bars[2];
+    if (A.stop.sl_rr >= 0 && fold_done(A.res, A.stop)) return;
+    const int tid = (int)threadIdx.x, lane = tid & 31, ty = tid >> 5;
+    const uint32_t sm0 = f2_smem_u32(f2_smem), bar0 = f2_smem_u32(&bars[0]);
+    if (tid == 0) {
+        f2_mbar_init(bar0, 1); f2_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double alpha = 0.0, beta = 0.0;
+    if (MODE == 5) {
+        alpha = A.res[FS_XPEND] != 0.0 ? A.res[FS_ALPHA] : 0.0;                       // x += alpha_{k-1} p_{k-1} (nothing pending in the first iteration)
+        beta = safe_div(rho_at(A.res, A.sl_cur), rho_at(A.res, A.sl_old));            // beta_k = rho_k / rho_{k-1}
+    }
+    auto issue = [&](int it, int stage) {   // one thread: arm the stage's barrier and start the box copies of item `it`
+        const TileRec R = I.rec[it];
+        const uint32_t dst = sm0 + stage * STAGE, bar = bar0 + 8 * stage;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read / written through the generic proxy before
+        f2_mbar_expect_tx(bar, NA * B::BYTES);
+        const CUtensorMap *ma = R.f == 0 ? &maps.a[0] : &maps.a[1];
+        if (N == 2) f2_tma_load_2d(dst, ma, bar, R.ox - 1, R.oy - 1); else f2_tma_load_3d(dst, ma, bar, R.ox - 1, R.oy - 1, R.oz - 1);
+        if (NA == 2) {
+            const CUtensorMap *mb = R.f == 0 ? &maps.b[0] : &maps.b[1];
+            if (N == 2) f2_tma_load_2d(dst + B::SLOT, mb, bar, R.ox - 1, R.oy - 1); else f2_tma_load_3d(dst + B::SLOT, mb, bar, R.ox - 1, R.oy - 1, R.oz - 1);
+        }
+    };
+    double v[2] = {0.0, 0.0};
+    uint32_t phase0 = 0, phase1 = 0;
+    int stage = 0;
+    if (tid == 0 && (int)blockIdx.x < I.n) issue(blockIdx.x, 0);
+    constexpr int TYM = N == 2 ? FU : 1, KY = N == 2 ? 1 : 0, SY = B::BX, SZ = B::BX * B::BY;
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const int nx = it + gridDim.x;
+        if (tid == 0 && nx < I.n) issue(nx, stage ^ 1);   // (that stage was released by the __syncthreads that ended the previous round)
+        const TileRec R = I.rec[it];
+        const unsigned char flags = I.uni[it];
+        const bool uni = (flags & 1) != 0;
+        const int f = R.f;
+        if (stage == 0) { f2_mbar_wait(bar0, phase0); phase0 ^= 1; } else { f2_mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+        double *__restrict__ sA = reinterpret_cast<double *>(f2_smem + stage * STAGE);
+        double *__restrict__ sP = MODE == 5 ? sA + B::SLOT / 8 : sA;   // the vector the stencil runs on
+        // this thread's FU cells: box index, global indices, validity
+        int bi[FU]; long long l[FU], q[FU]; bool ok[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, l[k], q[k]);
+            bi[k] = (lane + 1) + (ty * TYM + KY * k + 1) * SY + (N == 3 ? (k + 1) * SZ : 0);
+        }
+        double pown[FU], xown[FU];
+        if (MODE == 5) {
+            double *__restrict__ xf = f == 0 ? A.xs.f[0] : A.xs.f[1];
+#pragma unroll
+            for (int k = 0; k < FU; ++k) { pown[k] = sP[bi[k]]; xown[k] = ok[k] ? xf[q[k]] : 0.0; }
+            __syncthreads();   // every thread holds its p_{k-1} values before the box is overwritten
+            // p_k = z + beta p_{k-1} on the whole box (tile + halo)
+            for (int j = tid; j < B::NB; j += FCH) sP[j] = sA[j] + beta * sP[j];
+            if (A.dz != nullptr && (flags & 2)) {   // tiles that hold band cells: z = r + dz there
+                __syncthreads();
+                for (int j = tid; j < B::NB; j += FCH) {
+                    const int jx = j % B::BX, jy = (j / B::BX) % B::BY, jz = j / (B::BX * B::BY);
+                    const long long gx = R.ox + jx - 1, gy = R.oy + jy - 1, gz = N == 3 ? R.oz + jz - 1 : 0;
+                    if (gx >= 0 && gx < I.ld0 && gy >= 0 && gy < I.ld1 && gz >= 0 && gz < I.ld2) {
+                        const int bo = A.bord[gx + I.ld0 * (gy + I.ld1 * gz)];
+                        if (bo >= 0) sP[j] += A.dz[(size_t)f * A.nB + bo];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
+        const double *__restrict__ of0 = f == 0 ? fd.off[0][0] : fd.off[1][0];
+        const double *__restrict__ of1 = f == 0 ? fd.off[0][1] : fd.off[1][1];
+        const double *__restrict__ of2 = f == 0 ? fd.off[0][N > 2 ? 2 : 0] : fd.off[1][N > 2 ? 2 : 0];
+        double *__restrict__ yf = f == 0 ? A.y.f[0] : A.y.f[1];
+        const double *__restrict__ af = f == 0 ? A.aux.f[0] : A.aux.f[1];
+        double c[FU], acc[FU], av[FU];
+        if (uni) {
+            const double cx = uc[0], cy = uc[1], cz = N == 3 ? uc[2] : 0.0;
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+                c[k] = sP[bi[k]];
+                acc[k] = c[k] + cx * (sP[bi[k] - 1] + sP[bi[k] + 1]) + cy * (sP[bi[k] - SY] + sP[bi[k] + SY]);
+                if (N == 3) acc[k] += cz * (sP[bi[k] - SZ] + sP[bi[k] + SZ]);
+            }
+        } else {
+            double cm[FU][N], cp[FU][N];
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    const double *__restrict__ of = d == 0 ? of0 : (d == 1 ? of1 : of2);
+                    cm[k][d] = ok[k] ? of[l[k]] : 0.0;
+                    cp[k][d] = ok[k] ? of[l[k] + g.stride[d]] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+                c[k] = sP[bi[k]];
+                acc[k] = c[k] + cm[k][0] * sP[bi[k] - 1] + cp[k][0] * sP[bi[k] + 1] + cm[k][1] * sP[bi[k] - SY] + cp[k][1] * sP[bi[k] + SY];
+                if (N == 3) acc[k] += cm[k][N - 1] * sP[bi[k] - SZ] + cp[k][N - 1] * sP[bi[k] + SZ];
+            }
+        }
+        if (MODE == 2 || MODE == 4) {
+#pragma unroll
+            for (int k = 0; k < FU; ++k) av[k] = ok[k] ? af[q[k]] : 0.0;
+        }
+        if (MODE == 5) {
+            double *__restrict__ pn = f == 0 ? A.pnew.f[0] : A.pnew.f[1];
+            double *__restrict__ xf = f == 0 ? A.xs.f[0] : A.xs.f[1];
+#pragma unroll
+            for (int k = 0; k < FU; ++k)
+                if (ok[k]) {
+                    yf[q[k]] = acc[k];
+                    pn[q[k]] = c[k];
+                    xf[q[k]] = xown[k] + alpha * pown[k];
+                    v[0] += c[k] * acc[k];
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+                if (MODE == 4) acc[k] = A.pc.r * av[k] + A.pc.z * c[k] + A.pc.A * acc[k];
+                if (ok[k]) {
+                    yf[q[k]] = acc[k];
+                    if (MODE == 1) v[0] += c[k] * acc[k];
+                    if (MODE == 2 || MODE == 4) v[0] += av[k] * acc[k];
+                    if (MODE == 3) { v[0] += acc[k] * c[k]; v[1] += acc[k] * acc[k]; }
+                }
+            }
+        }
+        __syncthreads();   // the stage may be refilled
+        stage ^= 1;
+    }
+    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5) { double w[1] = {v[0]}; block_reduce_publish<1>(w, A.partials, A.results, A.counter); }
+    if (MODE == 3) block_reduce_publish<2>(v, A.partials, A.results, A.counter);
+}
+
+// Pointwise search-direction + solution update on a list of items: the ghost-class tiles of a slab-partitioned grid (whose p_k must exist
+// before the halo exchange) and the compact interface unknowns w (which the staged kernel does not touch).
+//   p_k = z + beta p_{k-1} (z = a + dz on band cells),  x += alpha_{k-1} p_{k-1}
+__global__ void __launch_bounds__(FCH) kf2_pupd(Items I, F2Args A)
+{
+    if (A.stop.sl_rr >= 0 && fold_done(A.res, A.stop)) return;
+    const double alpha = A.res[FS_XPEND] != 0.0 ? A.res[FS_ALPHA] : 0.0;
+    const double beta = safe_div(rho_at(A.res, A.sl_cur), rho_at(A.res, A.sl_old));
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        const int f = R.f;
+        const double *__restrict__ zf = f == 0 ? A.a.f[0] : (f == 1 ? A.a.f[1] : A.a.f[2]);
+        const double *__restrict__ po = f == 0 ? A.pold.f[0] : (f == 1 ? A.pold.f[1] : A.pold.f[2]);
+        double *__restrict__ pn = f == 0 ? A.pnew.f[0] : (f == 1 ? A.pnew.f[1] : A.pnew.f[2]);
+        double *__restrict__ xf = f == 0 ? A.xs.f[0] : (f == 1 ? A.xs.f[1] : A.xs.f[2]);
+        const bool band_tile = A.dz != nullptr && (f == 2 || (I.uni[it] & 2));
+        long long i[FU], iq[FU]; bool ok[FU]; double pv[FU], zv[FU], xv[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, i[k], iq[k]);
+            if (ok[k]) { pv[k] = po[iq[k]]; xv[k] = xf[iq[k]]; zv[k] = zf[iq[k]]; }
+        }
+        if (band_tile) {
+#pragma unroll
+            for (int k = 0; k < FU; ++k)
+                if (ok[k]) {
+                    const long long bo = f == 2 ? i[k] : (long long)A.bord[i[k]];
+                    if (bo >= 0) zv[k] += A.dz[(size_t)f * A.nB + bo];
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < FU; ++k)
+            if (ok[k]) {
+                pn[iq[k]] = zv[k] + beta * pv[k];
+                xf[iq[k]] = xv[k] + alpha * pv[k];
+            }
+    }
+}
+
+// CG residual update of the fused iteration: r -= alpha_k v, publishes (rho, rr); records alpha_k and the pending solution update for the
+// NEXT fused apply (or kf2_xflush).  Same arithmetic as kf_cg_update.
+// carry: single rank -- a skipped iteration copies the (rho, rr, rho_band, rho_poly_band) group forward here (several ranks: kf2_carry after the allreduce)
+__global__ void __launch_bounds__(FCH) kf2_update(Items I, double *res, int sl_rho, int sl_new, int carry, FVec qv, FVec r, double *partials, unsigned *counter, StopCrit stop)
+{
+    if (fold_done(res, stop)) {
+        if (carry && blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; res[sl_new + 3] = res[sl_rho + 3]; }
+        return;
+    }
+    const double alpha = safe_div(rho_at(res, sl_rho), res[FS_SIG_D] + res[FS_SIG_B] + res[FS_SIG_G]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { res[FS_ITERS] += 1.0; res[FS_ALPHA] = alpha; res[FS_XPEND] = 1.0; }
+    double v[2] = {0.0, 0.0};
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        const int f = R.f;
+        const double *__restrict__ qf = f == 0 ? qv.f[0] : (f == 1 ? qv.f[1] : qv.f[2]);
+        double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
+        long long i[FU], iq[FU]; bool ok[FU]; double vv[FU], rv[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, i[k], iq[k]);
+            if (ok[k]) { vv[k] = qf[iq[k]]; rv[k] = rf[iq[k]]; }
+        }
+#pragma unroll
+        for (int k = 0; k < FU; ++k)
+            if (ok[k]) {
+                const double rn = rv[k] - alpha * vv[k];
+                rf[iq[k]] = rn;
+                v[0] += rn * rn;
+            }
+    }
+    v[1] = v[0];
+    block_reduce_publish<2>(v, partials, res + sl_new, counter);
+}
+// skipped iteration: carry the whole (rho, rr, rho_band, rho_poly_band) group forward (the fused iteration has no kf_cg_p to do it)
+__global__ void kf2_carry(double *res, int sl_old, int sl_new, StopCrit stop)
+{
+    if (threadIdx.x == 0 && fold_done(res, stop)) {
+        res[sl_new] = res[sl_old]; res[sl_new + 1] = res[sl_old + 1]; res[sl_new + 2] = res[sl_old + 2]; res[sl_new + 3] = res[sl_old + 3];
+    }
+}
+
+// after the last iteration: the solution still lacks alpha_k p_k (the fused apply of iteration k+1 would have added it)
+__global__ void __launch_bounds__(FCH) kf2_xflush(Items I, const double *res, FVec p0, FVec p1, FVec xs)
+{
+    if (res[FS_XPEND] == 0.0) return;
+    const double alpha = res[FS_ALPHA];
+    const bool odd = (((long long)(res[FS_ITERS] + 0.5)) & 1) != 0;   // iteration j reads P[j & 1] and writes P[(j + 1) & 1]
+    FV_LOOP(I) {
+        (void)i;
+        const double *__restrict__ pf = odd ? p1.f[f] : p0.f[f];
+        xs.f[f][q] += alpha * pf[q];
+    }
+}

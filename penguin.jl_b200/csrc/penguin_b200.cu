@@ -7,6 +7,7 @@
 #include "geometry.cuh"
 #include "p2p.cuh"
 #include "fold.cuh"
+#include "fold2.cuh"
 
 #ifndef PB200_POLY_DEFAULT
 #define PB200_POLY_DEFAULT 1   // degree of the polynomial preconditioner of the folded CG when PB200_POLY is not set
@@ -44,6 +45,12 @@ static int ctx_common_init(pb200_ctx *c, int device)
     CUDA_TRY(c, cudaEventCreate(&c->ev0));
     CUDA_TRY(c, cudaEventCreate(&c->ev1));
     CUDA_TRY(c, cudaEventCreate(&c->ev2));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaMalloc((void **)&c->d_partials2, sizeof(double) * RED_MAXK * RED_MAXBLOCKS));
+    CUDA_TRY(c, cudaMalloc((void **)&c->d_counter2, sizeof(unsigned)));
+    CUDA_TRY(c, cudaMemset(c->d_counter2, 0, sizeof(unsigned)));
     return PB200_OK;
 }
 
@@ -95,6 +102,10 @@ extern "C" int pb200_finalize(pb200_ctx *c)
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_partials); cudaFree(c->d_results); cudaFree(c->d_counter); cudaFreeHost(c->h_results);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    cudaFree(c->d_partials2); cudaFree(c->d_counter2);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -666,7 +677,7 @@ static int fold_alloc_vec(pb200_solver *s, FVec *v)
     FoldSys &F = s->F;
     int rc;
     for (int f = 0; f < 3; ++f) v->f[f] = nullptr;
-    for (int f = 0; f < F.d.nbulk; ++f) if ((rc = dev_alloc(s->ctx, &v->f[f], s->g.nloc))) return rc;
+    for (int f = 0; f < F.d.nbulk; ++f) if ((rc = dev_alloc(s->ctx, &v->f[f], F.nlocq))) return rc;   // re-pitched layout (fold.cuh: FoldDev)
     if (F.d.has_w && (rc = dev_alloc(s->ctx, &v->f[2], F.d.nB > 0 ? F.d.nB : 1))) return rc;
     return PB200_OK;
 }
@@ -764,6 +775,10 @@ static int fold_band_spectrum(pb200_solver *s)
     return PB200_OK;
 }
 
+typedef CUresult (*pb_encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static pb_encode_tiled_t pb_encode_tiled();
+static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out);
 static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 {
     pb200_ctx *ctx = s->ctx;
@@ -787,6 +802,16 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         d.m[0] = s->m1; d.m[1] = s->m1; d.mw = s->m1;
     }
     d.ph[0] = s->p1; d.ph[1] = s->p2;
+    {
+        // layout of the Krylov vectors: x rows padded to a multiple of 32 doubles (256-byte aligned tile rows, TMA-describable)
+        const long long ld0 = g.sd == 0 ? g.lz : g.pd[0], ld1 = g.N < 2 ? 1 : (g.sd == 1 ? g.lz : g.pd[1]), ld2 = g.N < 3 ? 1 : g.lz;
+        long long P0 = ld0;
+        if (g.N >= 2 && !getenv("PB200_NO_REPITCH")) P0 = (ld0 + 31) / 32 * 32;
+        d.ld0 = ld0; d.dP = P0 - ld0;
+        d.sq[0] = 1; d.sq[1] = P0; d.sq[2] = P0 * ld1;
+        F.P0 = P0; F.nlocq = P0 * ld1 * ld2;
+        F.planeq = g.N == 1 ? 1 : (g.N == 2 ? P0 : P0 * ld1);
+    }
     int rc;
     {
         unsigned char *ml[2] = {s->m1, s->m2};
@@ -824,7 +849,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         int mb = d.nBlo > nBhi ? d.nBlo : nBhi;
         if (s->bh.lo_sendn > mb) mb = s->bh.lo_sendn;
         if (s->bh.hi_sendn > mb) mb = s->bh.hi_sendn;
-        if ((rc = p2p_setup(ctx, (size_t)d.nbulk * g.plane + mb))) return rc;   // collective (every rank builds its folded system here)
+        if ((rc = p2p_setup(ctx, (size_t)d.nbulk * F.planeq + mb))) return rc;   // collective (every rank builds its folded system here)
     }
     const int gown = red_grid(ctx, g.nown);
     DISPATCH_N(g.N, (kf_diag<N><<<gown, RED_THREADS, 0, ctx->stream>>>(g, d)));
@@ -862,12 +887,15 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         Items &I = F.I;
         memset(&I, 0, sizeof(I));
         I.sd = g.sd; I.lz = g.lz;
+        I.glo = ctx->rank > 0 ? 1 : 0; I.ghi = ctx->rank < ctx->nranks - 1 ? 1 : 0;
         I.ld0 = g.sd == 0 ? g.lz : g.pd[0];
         I.ld1 = g.N < 2 ? 1 : (g.sd == 1 ? g.lz : g.pd[1]);
         I.ld2 = g.N < 3 ? 1 : g.lz;
         if (g.N == 1) { I.T0 = FTILE; I.T1 = 1; I.T2 = 1; I.shx = 8; I.kx = FCH; I.ky = 0; I.kz = 0; I.tym = 1; I.ustride = FCH; }
         else if (g.N == 2) { I.T0 = 32; I.T1 = 32; I.T2 = 1; I.shx = 5; I.kx = 0; I.ky = 1; I.kz = 0; I.tym = FU; I.ustride = I.ld0; }
         else { I.T0 = 32; I.T1 = 8; I.T2 = 4; I.shx = 5; I.kx = 0; I.ky = 0; I.kz = 1; I.tym = 1; I.ustride = I.ld0 * I.ld1; }
+        I.P0 = F.P0;
+        I.ustrideq = g.N == 1 ? FCH : (g.N == 2 ? F.P0 : F.P0 * I.ld1);
         I.nt0 = (int)((I.ld0 + I.T0 - 1) / I.T0); I.nt1 = (int)((I.ld1 + I.T1 - 1) / I.T1);
         const long long nt2 = (I.ld2 + I.T2 - 1) / I.T2;
         const long long ntile = (long long)I.nt0 * I.nt1 * nt2;
@@ -914,39 +942,51 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         // tiles of each class +-1 for any grid size, and the order is fixed, so its reduction stays deterministic.  The streaming vector
         // kernels keep the index-ordered list: all tiles cost them the same, and neighbouring blocks on neighbouring tiles share DRAM
         // pages (the class order cost them 25 % at 384^3).
-        F.IA = I;
-        if (F.nitems > 1 && !getenv("PB200_NO_REORDER")) {
+        F.IA = I; F.IAi = I; F.IAg = I; F.IG1 = I;
+        F.IAg.n = 0; F.IG1.n = 0;
+        if (F.nitems > 0) {
             const int n = F.nitems;
-            std::vector<int> hi(n), ho;
+            std::vector<int> hi(n);
             std::vector<unsigned char> hu(n);
             std::vector<TileRec> hr(n);
             CUDA_TRY(ctx, cudaMemcpy(hi.data(), F.items, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
             CUDA_TRY(ctx, cudaMemcpy(hu.data(), F.uni, (size_t)n, cudaMemcpyDeviceToHost));
             CUDA_TRY(ctx, cudaMemcpy(hr.data(), F.rec, sizeof(TileRec) * (size_t)n, cudaMemcpyDeviceToHost));
-            ho.reserve(n);
+            // a sub-list of the items with its own records / flags / constants
+            auto make_list = [&](const std::vector<int> &ids, Items &out) -> int {
+                out = I;
+                out.n = (int)ids.size();
+                if (ids.empty()) return PB200_OK;
+                const size_t na = ids.size();
+                int *d_it = nullptr; TileRec *d_rec = nullptr; unsigned char *d_uni = nullptr; double *d_uc = nullptr;
+                CUDA_TRY(ctx, cudaMalloc((void **)&d_it, sizeof(int) * na)); F.list_mem.push_back(d_it);
+                CUDA_TRY(ctx, cudaMalloc((void **)&d_rec, sizeof(TileRec) * na)); F.list_mem.push_back(d_rec);
+                CUDA_TRY(ctx, cudaMalloc((void **)&d_uni, na)); F.list_mem.push_back(d_uni);
+                CUDA_TRY(ctx, cudaMalloc((void **)&d_uc, sizeof(double) * PB_MAXD * na)); F.list_mem.push_back(d_uc);
+                CUDA_TRY(ctx, cudaMemcpy(d_it, ids.data(), sizeof(int) * na, cudaMemcpyHostToDevice));
+                out.it = d_it;
+                kf_tile_records<<<((int)na + 255) / 256, 256, 0, ctx->stream>>>(out, d_rec); LAUNCH_CHECK(ctx);
+                out.rec = d_rec; out.uni = d_uni; out.ucoef = d_uc;
+                int ga = (int)na; if (ga > ctx->sm_count * 8) ga = ctx->sm_count * 8;
+                DISPATCH_N(g.N, (kf_tile_meta<N><<<ga, FCH, 0, ctx->stream>>>(g, d, out, d_uni, d_uc, getenv("PB200_EXACT_TILES") ? 0.0 : 1e-12, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
+                LAUNCH_CHECK(ctx);
+                double cnt2[3];
+                return fetch_results(ctx, SL_TMP, 3, cnt2);
+            };
+            // cost-class order of the bulk tiles (slow first): all / interior class / ghost class (box reaches a neighbour rank's ghost plane)
+            const bool reorder = !getenv("PB200_NO_REORDER");
+            std::vector<int> all, inner, ghost, g1;
             for (int cls = 0; cls < 2; ++cls)
                 for (int i = 0; i < n; ++i) {
                     if (hr[i].f >= 2) continue;     // (w chunks are not the dense apply's business)
-                    const int c = ((hu[i] & 1) && hr[i].full) ? 1 : 0;
-                    if (c == cls) ho.push_back(hi[i]);
+                    const int c = (!reorder || ((hu[i] & 1) && hr[i].full)) ? 1 : 0;
+                    if (c != cls) continue;
+                    all.push_back(hi[i]);
+                    (hr[i].ghost ? ghost : inner).push_back(hi[i]);
                 }
-            const int na = (int)ho.size();
-            if (na > 0) {
-                CUDA_TRY(ctx, cudaMalloc((void **)&F.itemsA, sizeof(int) * (size_t)na));
-                CUDA_TRY(ctx, cudaMalloc((void **)&F.recA, sizeof(TileRec) * (size_t)na));
-                CUDA_TRY(ctx, cudaMalloc((void **)&F.uniA, (size_t)na));
-                CUDA_TRY(ctx, cudaMalloc((void **)&F.ucoefA, sizeof(double) * PB_MAXD * (size_t)na));
-                CUDA_TRY(ctx, cudaMemcpy(F.itemsA, ho.data(), sizeof(int) * (size_t)na, cudaMemcpyHostToDevice));
-                Items &A = F.IA;
-                A.it = F.itemsA; A.n = na;
-                kf_tile_records<<<(na + 255) / 256, 256, 0, ctx->stream>>>(A, F.recA); LAUNCH_CHECK(ctx);
-                A.rec = F.recA; A.uni = F.uniA; A.ucoef = F.ucoefA;
-                int ga = na; if (ga > ctx->sm_count * 8) ga = ctx->sm_count * 8;
-                DISPATCH_N(g.N, (kf_tile_meta<N><<<ga, FCH, 0, ctx->stream>>>(g, d, A, F.uniA, F.ucoefA, getenv("PB200_EXACT_TILES") ? 0.0 : 1e-12, ctx->d_partials, ctx->d_results + SL_TMP, ctx->d_counter)));
-                LAUNCH_CHECK(ctx);
-                double cnt2[2];
-                if ((rc = fetch_results(ctx, SL_TMP, 2, cnt2))) return rc;
-            }
+            // pointwise p / x update of the fused iteration: ghost-class tiles + the compact interface unknowns (index order)
+            for (int i = 0; i < n; ++i) if (hr[i].f >= 2 || hr[i].ghost) g1.push_back(hi[i]);
+            if ((rc = make_list(all, F.IA)) || (rc = make_list(inner, F.IAi)) || (rc = make_list(ghost, F.IAg)) || (rc = make_list(g1, F.IG1))) return rc;
         }
     }
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v};
@@ -954,6 +994,9 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     F.key[0] = ac.cV; F.key[1] = ac.c; F.key[2] = ac.c2;
     F.built = true;
+    // TMA staging needs global strides that are multiples of 16 bytes (an even pitch: the re-pitched layout) and >= 2-D grids
+    F.tma_ok = g.N >= 2 && (F.P0 % 2 == 0) && !getenv("PB200_NO_TMA") && pb_encode_tiled() != nullptr;
+    if (F.tma_ok) { CUtensorMap probe; if (fold_tmap(s, F.x.f[0], &probe)) { F.tma_ok = false; cudaGetLastError(); } }
     // the band preconditioner is a COLLECTIVE decision (its set-up and every iteration contain reductions over the ranks): it is used
     // when ANY rank holds band cells, and ranks without band cells simply contribute zeros
     if (d.has_w && !getenv("PB200_NO_BAND_PREC")) {
@@ -985,15 +1028,18 @@ static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLO
 static inline int band_wgrid(int n) { int b = (n + 15) / 16; if (b > 2048) b = 2048; if (b < 1) b = 1; return b; }   // >= 8 cells per 256-thread block
 
 // ghost planes of the bulk fields and ghost entries of the compact w of one Krylov vector, ONE NCCL group (one launch)
-static int fold_halo(pb200_solver *s, const FVec &x)
+static int fold_halo(pb200_solver *s, const FVec &x, cudaStream_t st = nullptr)
 {
     pb200_ctx *ctx = s->ctx;
     if (ctx->nranks == 1) return PB200_OK;
+    if (!st) st = ctx->stream;
+    prof_mark(ctx, PB_PROF_XCHG);
+    struct Mark { pb200_ctx *c; ~Mark() { prof_mark(c, PB_PROF_XCHG); } } mark_{ctx};
     const Grid &g = s->g;
     const FoldSys &F = s->F;
     const int nB = F.d.nB, nBlo = F.d.nBlo, nBown = F.d.nBown, nBhi = nB - nBlo - nBown;
     const BandHalo &bh = s->bh;
-    const size_t cnt = (size_t)g.plane;
+    const size_t cnt = (size_t)F.planeq;   // Krylov vectors: planes of the re-pitched layout
     if (ctx->p2p && ctx->p2p->on) {
         // peer-memory path (p2p.cuh): one kernel stores the boundary data into the neighbours' mailboxes and unpacks what they stored here
         P2PState *P = ctx->p2p;
@@ -1003,20 +1049,20 @@ static int fold_halo(pb200_solver *s, const FVec &x)
         size_t total = 0;
         if (ctx->rank > 0) {
             lo.active = 1; lo.remote = P->peer[ctx->rank - 1]; lo.remote_dir = 1; lo.local_dir = 0;
-            for (int f = 0; f < F.d.nbulk; ++f) { lo.send[lo.nseg] = {x.f[f] + g.plane, nullptr, (int)cnt}; lo.recv[lo.nseg] = {nullptr, x.f[f], (int)cnt}; ++lo.nseg; total += cnt; }
+            for (int f = 0; f < F.d.nbulk; ++f) { lo.send[lo.nseg] = {x.f[f] + F.planeq, nullptr, (int)cnt}; lo.recv[lo.nseg] = {nullptr, x.f[f], (int)cnt}; ++lo.nseg; total += cnt; }
             if (band) { lo.send[lo.nseg] = {x.f[2] + bh.lo_send0, nullptr, bh.lo_sendn}; lo.recv[lo.nseg] = {nullptr, x.f[2], nBlo}; ++lo.nseg; }
         }
         if (ctx->rank < ctx->nranks - 1) {
             hi.active = 1; hi.remote = P->peer[ctx->rank + 1]; hi.remote_dir = 0; hi.local_dir = 1;
             for (int f = 0; f < F.d.nbulk; ++f) {
-                hi.send[hi.nseg] = {x.f[f] + (long long)(g.lz - 2) * g.plane, nullptr, (int)cnt};
-                hi.recv[hi.nseg] = {nullptr, x.f[f] + (long long)(g.lz - 1) * g.plane, (int)cnt};
+                hi.send[hi.nseg] = {x.f[f] + (long long)(g.lz - 2) * F.planeq, nullptr, (int)cnt};
+                hi.recv[hi.nseg] = {nullptr, x.f[f] + (long long)(g.lz - 1) * F.planeq, (int)cnt};
                 ++hi.nseg; total += cnt;
             }
             if (band) { hi.send[hi.nseg] = {x.f[2] + bh.hi_send0, nullptr, bh.hi_sendn}; hi.recv[hi.nseg] = {nullptr, x.f[2] + nBlo + nBown, nBhi}; ++hi.nseg; }
         }
         int blocks = (int)(total / 8192); if (blocks < 1) blocks = 1; if (blocks > 64) blocks = 64;
-        k_p2p_halo<<<blocks, 512, 0, ctx->stream>>>(P->mbox, P->zone_doubles, lo, hi);
+        k_p2p_halo<<<blocks, 512, 0, st>>>(P->mbox, P->zone_doubles, lo, hi);
         LAUNCH_CHECK(ctx);
         return PB200_OK;
     }
@@ -1024,27 +1070,103 @@ static int fold_halo(pb200_solver *s, const FVec &x)
     for (int f = 0; f < F.d.nbulk; ++f) {
         double *p = x.f[f];
         if (ctx->rank > 0) {
-            NCCL_TRY(ctx, g_nccl.Send(p + g.plane, cnt, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
-            NCCL_TRY(ctx, g_nccl.Recv(p, cnt, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx, g_nccl.Send(p + F.planeq, cnt, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, st));
+            NCCL_TRY(ctx, g_nccl.Recv(p, cnt, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, st));
         }
         if (ctx->rank < ctx->nranks - 1) {
-            NCCL_TRY(ctx, g_nccl.Send(p + (long long)(g.lz - 2) * g.plane, cnt, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
-            NCCL_TRY(ctx, g_nccl.Recv(p + (long long)(g.lz - 1) * g.plane, cnt, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx, g_nccl.Send(p + (long long)(g.lz - 2) * F.planeq, cnt, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, st));
+            NCCL_TRY(ctx, g_nccl.Recv(p + (long long)(g.lz - 1) * F.planeq, cnt, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, st));
         }
     }
     if (F.d.has_w && nB > 0) {
         double *p = x.f[2];
         if (ctx->rank > 0) {
-            if (bh.lo_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.lo_send0, (size_t)bh.lo_sendn, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
-            if (nBlo) NCCL_TRY(ctx, g_nccl.Recv(p, (size_t)nBlo, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, ctx->stream));
+            if (bh.lo_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.lo_send0, (size_t)bh.lo_sendn, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, st));
+            if (nBlo) NCCL_TRY(ctx, g_nccl.Recv(p, (size_t)nBlo, PB_NCCL_FLOAT64, ctx->rank - 1, ctx->comm, st));
         }
         if (ctx->rank < ctx->nranks - 1) {
-            if (bh.hi_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.hi_send0, (size_t)bh.hi_sendn, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
-            if (nBhi) NCCL_TRY(ctx, g_nccl.Recv(p + nBlo + nBown, (size_t)nBhi, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, ctx->stream));
+            if (bh.hi_sendn) NCCL_TRY(ctx, g_nccl.Send(p + bh.hi_send0, (size_t)bh.hi_sendn, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, st));
+            if (nBhi) NCCL_TRY(ctx, g_nccl.Recv(p + nBlo + nBown, (size_t)nBhi, PB_NCCL_FLOAT64, ctx->rank + 1, ctx->comm, st));
         }
     }
     NCCL_TRY(ctx, g_nccl.GroupEnd());
     return PB200_OK;
+}
+
+// ---- TMA descriptors of the Krylov vectors (fold2.cuh) ---------------------------------------------------------------------------
+static pb_encode_tiled_t pb_encode_tiled()
+{
+    static pb_encode_tiled_t fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (pb_encode_tiled_t)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+// descriptor of one bulk field of a Krylov vector: an N-d tensor of doubles (P0, ld1[, ld2]) read in boxes of tile + halo
+static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out)
+{
+    FoldSys &F = s->F;
+    auto it = F.tmaps.find(ptr);
+    if (it != F.tmaps.end()) { *out = it->second; return PB200_OK; }
+    pb_encode_tiled_t enc = pb_encode_tiled();
+    if (!enc) return set_err(s->ctx, PB200_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+    const int N = s->g.N;
+    const cuuint64_t dims[3] = {(cuuint64_t)F.P0, (cuuint64_t)F.I.ld1, (cuuint64_t)F.I.ld2};
+    const cuuint64_t strides[2] = {(cuuint64_t)F.P0 * 8, (cuuint64_t)F.P0 * (cuuint64_t)F.I.ld1 * 8};
+    const cuuint32_t box2[2] = {34, 34}, box3[3] = {34, 10, 6}, es[3] = {1, 1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)N, (void *)ptr, dims, strides, N == 2 ? box2 : box3, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(s->ctx, PB200_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    F.tmaps[ptr] = m;
+    *out = m;
+    return PB200_OK;
+}
+static int fold_maps(pb200_solver *s, const FVec &a, const FVec *b, F2Maps *out)
+{
+    memset(out, 0, sizeof(*out));
+    int rc;
+    for (int f = 0; f < s->F.d.nbulk; ++f) {
+        if ((rc = fold_tmap(s, a.f[f], &out->a[f]))) return rc;
+        if (b && (rc = fold_tmap(s, b->f[f], &out->b[f]))) return rc;
+    }
+    if (s->F.d.nbulk == 1) { out->a[1] = out->a[0]; out->b[1] = out->b[0]; }
+    return PB200_OK;
+}
+template <int N, int MODE>
+static int fold2_launch(pb200_solver *s, const Items &L, const F2Maps &maps, const F2Args &A, cudaStream_t st)
+{
+    pb200_ctx *ctx = s->ctx;
+    constexpr int smem = 2 * (MODE == 5 ? 2 : 1) * F2Box<N>::SLOT;
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf2_apply<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf2_apply<N, MODE>, FCH, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 2; }
+    int grid = L.n < ctx->sm_count * nb ? L.n : ctx->sm_count * nb;
+    if (grid < 1) grid = 1;
+    kf2_apply<N, MODE><<<grid, FCH, smem, st>>>(maps, s->g, s->F.d, L, A);
+    LAUNCH_CHECK(ctx);
+    return PB200_OK;
+}
+// the staged apply of `mode` on list L (N >= 2 only)
+static int fold2_apply(pb200_solver *s, const Items &L, const F2Maps &maps, const F2Args &A, int mode, cudaStream_t st)
+{
+    const int N = s->g.N;
+#define F2L(M_) (N == 2 ? fold2_launch<2, M_>(s, L, maps, A, st) : fold2_launch<3, M_>(s, L, maps, A, st))
+    switch (mode) {
+    case 0: return F2L(0);
+    case 1: return F2L(1);
+    case 2: return F2L(2);
+    case 3: return F2L(3);
+    case 4: return F2L(4);
+    default: return F2L(5);
+    }
+#undef F2L
 }
 
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
@@ -1063,12 +1185,23 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
     double *slotD = res + (mode == 4 ? slotD4 : (mode == 3 ? FS_TS_D : FS_SIG_D)), *slotB = res + (mode == 4 ? slotB4 : (mode == 3 ? FS_TS_B : FS_SIG_B));
     prof_mark(ctx, PB_PROF_APPLY);
     ctx->apply_launches++;
+    if (F.tma_ok) {   // staged tile + halo (fold2.cuh)
+        F2Maps maps;
+        if ((rc = fold_maps(s, x, nullptr, &maps))) return rc;
+        F2Args A;
+        memset(&A, 0, sizeof(A));
+        A.a = x; A.y = y; A.aux = aux; A.stop = stop; A.pc = pc; A.partials = ctx->d_partials; A.results = slotD; A.counter = ctx->d_counter; A.res = res;
+        if ((rc = fold2_apply(s, F.IA, maps, A, mode, ctx->stream))) return rc;
+    } else {
 #define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.IA, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop, pc)))
     if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else if (mode == 3) FOLD_DENSE(3); else FOLD_DENSE(4);
 #undef FOLD_DENSE
     LAUNCH_CHECK(ctx);
+    }
     prof_mark(ctx, PB_PROF_APPLY);
     if (F.d.has_w) {   // also on a rank without band cells: the kernel must refresh its partial-sum slots (to 0) before the in-place reduction
+        prof_mark(ctx, PB_PROF_BAPPLY);
+        struct Mark { pb200_ctx *c; ~Mark() { prof_mark(c, PB_PROF_BAPPLY); } } mark_{ctx};
         const int gb = band_wgrid(F.d.nE);
 #define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 256, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop, pc)))
         if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else if (mode == 3) FOLD_BAND(3); else FOLD_BAND(4);
@@ -1211,15 +1344,20 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
     if (band) { kf_to_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->b, F.b); LAUNCH_CHECK(ctx); }
     const bool cg = method == PB200_KRYLOV_CG;
     static_assert(FS_RR0 == FS_BB + 1, "kf_resid publishes the pair (bb, rr0)");
+    // fused CG iteration (fold2.cuh): p update + apply in one TMA-staged kernel, ghost-class tiles and the halo exchange on a second stream
+    const bool fused = cg && F.tma_ok && !getenv("PB200_NO_FUSED");
+    if (fused && !F.have_p2) { if ((rc = fold_alloc_vec(s, &F.p2))) return rc; F.have_p2 = true; }
+    if (fused && F.poly_m > 0 && !F.have_zz) { if ((rc = fold_alloc_vec(s, &F.zz))) return rc; F.have_zz = true; }
+    const int pzero = fused ? 1 : 0;
     const bool warm = gsp[0].m > 0;
     if (warm) {
         if (!dense_done) { kf_guess_dense<<<wave_grid(s, kf_guess_dense), FCH, 0, ctx->stream>>>(F.d, I, gsp[0], gsp[1], F.x); LAUNCH_CHECK(ctx); }
         if (band) { kf_guess_band<<<gb, 128, 0, ctx->stream>>>(F.d, gsp[0], gsp[1], gsp[2], F.x); LAUNCH_CHECK(ctx); }
         if ((rc = fold_apply(s, F.x, F.v, F.v, 0))) return rc;
-        kf_resid<<<wave_grid(s, kf_resid), FCH, 0, ctx->stream>>>(I, F.b, F.v, 1, F.r, F.p, F.r0, cg ? 0 : 1, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
+        kf_resid<<<wave_grid(s, kf_resid), FCH, 0, ctx->stream>>>(I, F.b, F.v, 1, F.r, F.p, F.r0, cg ? 0 : 1, pzero, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
     } else {
         kf_zero<<<grid, FCH, 0, ctx->stream>>>(I, F.x); LAUNCH_CHECK(ctx);
-        kf_resid<<<wave_grid(s, kf_resid), FCH, 0, ctx->stream>>>(I, F.b, F.v, 0, F.r, F.p, F.r0, cg ? 0 : 1, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
+        kf_resid<<<wave_grid(s, kf_resid), FCH, 0, ctx->stream>>>(I, F.b, F.v, 0, F.r, F.p, F.r0, cg ? 0 : 1, pzero, ctx->d_partials, res + FS_BB, ctx->d_counter); LAUNCH_CHECK(ctx);
     }
     if ((rc = allreduce_results(ctx, FS_BB, 2))) return rc;
     // No host look at ||b||, ||r0|| here: the device-side stopping test (fold_done) needs neither, and a converged start simply turns
@@ -1235,13 +1373,13 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         const int gE = band_wgrid(F.d.nE);
         const StopCrit nostop = {0.0, 0.0, -1};
         const bool poly = cg && F.poly_m > 0;
-        if (poly && (rc = fold_poly(s, F.r, F.p, FS_PAIR0, nostop))) return rc;   // p0 = q(M^) r0 (kf_resid had set p0 = r0)
+        if (poly && (rc = fold_poly(s, F.r, fused ? F.zz : F.p, FS_PAIR0, nostop))) return rc;   // p0 = q(M^) r0 (kf_resid had set p0 = r0; fused: z0, p0 is formed by the first apply)
         if (cg) {
             if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
                 DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
                 LAUNCH_CHECK(ctx);
                 if ((rc = allreduce_results(ctx, FS_PAIR0 + 2, 1))) return rc;
-                kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx);
+                if (!fused) { kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx); }
             }
             if (poly && ((rc = allreduce_results(ctx, FS_PAIR0, 1)) || (rc = allreduce_results(ctx, FS_PAIR0 + 3, 1)))) return rc;   // (slots 1, 2 are global already)
         }
@@ -1252,6 +1390,68 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
             StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, FS_TRIPLE(curp) + 1};
             StopCrit stn = {o.rtol * o.rtol, o.atol * o.atol, FS_TRIPLE(nxt) + 1};
             int rc2;
+            if (cg && fused) {
+                const bool multi = ctx->nranks > 1;
+                const FVec &pold = curp ? F.p2 : F.p, &pnew = curp ? F.p : F.p2;    // iteration j reads P[j & 1], writes P[(j + 1) & 1]
+                const FVec &zsrc = poly ? F.zz : F.r;
+                cudaStream_t st2 = ctx->profile ? ctx->stream : ctx->stream2;   // (per-launch event timing: everything in one stream)
+                const bool side = F.IG1.n > 0 || multi;
+                F2Args A;
+                memset(&A, 0, sizeof(A));
+                A.a = zsrc; A.pold = pold; A.y = F.v; A.pnew = pnew; A.xs = F.x; A.aux = F.v;
+                A.dz = prec ? F.dz : nullptr; A.bord = F.bord; A.nB = F.d.nB;
+                A.sl_old = FS_TRIPLE(nxt); A.sl_cur = FS_TRIPLE(curp); A.stop = st; A.res = res;
+                A.partials = ctx->d_partials; A.counter = ctx->d_counter; A.results = res + FS_SIG_D;
+                if (side) {
+                    if (st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
+                    if (F.IG1.n > 0) {   // ghost-class tiles and the compact interface unknowns: p_k and x pointwise
+                        prof_mark(ctx, PB_PROF_PUPD);
+                        int g1 = F.IG1.n < ctx->sm_count * 4 ? F.IG1.n : ctx->sm_count * 4;
+                        kf2_pupd<<<g1, FCH, 0, st2>>>(F.IG1, A); LAUNCH_CHECK(ctx);
+                        prof_mark(ctx, PB_PROF_PUPD);
+                    }
+                    if (multi && (rc2 = fold_halo(s, pnew, st2))) return rc2;   // ghost planes of p_k: in flight while the interior class computes
+                }
+                F2Maps mi;
+                if ((rc2 = fold_maps(s, zsrc, &pold, &mi))) return rc2;
+                prof_mark(ctx, PB_PROF_APPLY);
+                ctx->apply_launches++;
+                if ((rc2 = fold2_apply(s, multi ? F.IAi : F.IA, mi, A, 5, ctx->stream))) return rc2;
+                prof_mark(ctx, PB_PROF_APPLY);
+                if (side && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+                if (multi) {
+                    // ghost-class tiles: plain staged apply of p_k.  After the join: their boxes also read p_k cells of interior-class tiles,
+                    // which the fused kernel has only now finished writing.
+                    F2Maps mg;
+                    if ((rc2 = fold_maps(s, pnew, nullptr, &mg))) return rc2;
+                    F2Args G = A;
+                    G.a = pnew; G.results = res + FS_SIG_G;
+                    prof_mark(ctx, PB_PROF_APPLY);
+                    if ((rc2 = fold2_apply(s, F.IAg, mg, G, 1, ctx->stream))) return rc2;
+                    prof_mark(ctx, PB_PROF_APPLY);
+                }
+                if (F.d.has_w) {     // band part of v = M^ p_k (needs p_k everywhere)
+                    prof_mark(ctx, PB_PROF_BAPPLY);
+                    DISPATCH_N(s->g.N, (kf_apply_band<N, 1><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(s->g, F.d, pnew, F.v, F.v, ctx->d_partials, res + FS_SIG_B, ctx->d_counter, res, st, PolyCoef{0.0, 0.0, 0.0})));
+                    LAUNCH_CHECK(ctx);
+                    prof_mark(ctx, PB_PROF_BAPPLY);
+                }
+                if (multi && (rc2 = allreduce_results(ctx, FS_SIG_D, 3))) return rc2;
+                prof_mark(ctx, PB_PROF_UPDATE);
+                kf2_update<<<wave_grid(s, kf2_update), FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), multi ? 0 : 1, F.v, F.r, ctx->d_partials, ctx->d_counter, st); LAUNCH_CHECK(ctx);
+                prof_mark(ctx, PB_PROF_UPDATE);
+                if (poly && (rc2 = fold_poly(s, F.r, F.zz, FS_TRIPLE(nxt), st))) return rc2;
+                if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 2))) return rc2;
+                if (prec) {
+                    prof_mark(ctx, PB_PROF_BPREC);
+                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
+                    LAUNCH_CHECK(ctx);
+                    prof_mark(ctx, PB_PROF_BPREC);
+                    if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 3))) return rc2;
+                }
+                if (multi) { kf2_carry<<<1, 32, 0, ctx->stream>>>(res, FS_TRIPLE(curp), FS_TRIPLE(nxt), st); LAUNCH_CHECK(ctx); }
+                return PB200_OK;
+            }
             if (cg) {
                 if ((rc2 = fold_apply(s, F.p, F.v, F.v, 1, st))) return rc2;
                 prof_mark(ctx, PB_PROF_UPDATE);
@@ -1261,8 +1461,10 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 if (poly && (rc2 = fold_poly(s, F.r, F.v, FS_TRIPLE(nxt), st))) return rc2;
                 if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 2))) return rc2;
                 if (prec) {   // z += (q(M^_BB) - 1) r_B on the band: rho_new += (r_B, dz_B)
+                    prof_mark(ctx, PB_PROF_BPREC);
                     DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
                     LAUNCH_CHECK(ctx);
+                    prof_mark(ctx, PB_PROF_BPREC);
                     if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 3))) return rc2;
                 }
                 prof_mark(ctx, PB_PROF_PUPD);
@@ -1288,7 +1490,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
         const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
         const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
-        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen + 1024.0 * F.poly_m, o.rtol + F.poly_lo, o.atol + F.poly_hi, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
+        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen + 1024.0 * F.poly_m + (fused ? 4096.0 : 0.0), o.rtol + F.poly_lo, o.atol + F.poly_hi, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
         if (use_graph && memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
             for (auto &kv : F.graphs) cudaGraphExecDestroy(kv.second.exec);
             F.graphs.clear();
@@ -1334,9 +1536,14 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
             if (!(rnorm == rnorm)) break;
         }
         F.last_iters = it;
+        if (fused) {   // x += alpha_k p_k of the last iteration (the next fused apply would have added it)
+            kf2_xflush<<<wave_grid(s, kf2_xflush), FCH, 0, ctx->stream>>>(I, res, F.p, F.p2, F.x); LAUNCH_CHECK(ctx);
+        }
     }
+    prof_mark(ctx, PB_PROF_EPILOGUE);
     kf_from_scaled_dense<<<wave_grid(s, kf_from_scaled_dense), FCH, 0, ctx->stream>>>(F.d, I, F.x, s->x); LAUNCH_CHECK(ctx);
     if (band) { kf_from_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, F.x, s->x); LAUNCH_CHECK(ctx); }
+    prof_mark(ctx, PB_PROF_EPILOGUE);
     *iters = it; *conv = converged; *rnorm_out = rnorm; *bnorm_out = bnorm;
     return PB200_OK;
 }

@@ -64,9 +64,22 @@ def diph256(pb):
     return dict(p1=p1g, p2=p2g, u0=u0, dt=dt, states=states)
 
 
+# implementations of the Krylov iteration on the folded system (csrc/fold2.cuh): the default is the fused, TMA-staged one; the switches
+# peel it back layer by layer so that a parity failure names its layer
+VARIANTS = {"fused_tma": {}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1"},
+            "reference_pitch": {"PB200_NO_REPITCH": "1"}}
+
+
+@pytest.fixture(params=list(VARIANTS))
+def variant(request, monkeypatch):
+    for k, v in VARIANTS[request.param].items():
+        monkeypatch.setenv(k, v)
+    return request.param
+
+
 @pytest.mark.parametrize("scheme", ["BE", "CN"])
 @pytest.mark.parametrize("check_every", [2, 8])
-def test_diph_256_interior_tiles_vs_oracle(pb, diph256, scheme, check_every):
+def test_diph_256_interior_tiles_vs_oracle(pb, diph256, scheme, check_every, variant):
     # check_every = 2 with a zero initial guess: the first solve is ~15 chunks of graph replay, later ones a long first chunk + short ones
     d = diph256
     ic = pb.InterfaceConditions(pb.ScalarJump(1.0, 1.0, 0.0), pb.FluxJump(1.0, 1.0, 0.0))
@@ -99,7 +112,7 @@ def test_diph_256_at_the_bench_settings(pb, diph256):
 
 
 @pytest.mark.parametrize("poly", ["0", "1", "2"])
-def test_mono_256_cn_polynomial_preconditioner_vs_oracle(pb, poly, monkeypatch):
+def test_mono_256_cn_polynomial_preconditioner_vs_oracle(pb, poly, monkeypatch, variant):
     # Heat-type monophasic problem, fluid OUTSIDE a circle (interface Dirichlet => no interface unknowns => the polynomial step, MODE 4,
     # runs on the interior tiles), Dirichlet borders, first step BE then CN (benchmark/Heat3D.jl:53-74 in 2-D)
     monkeypatch.setenv("PB200_POLY", poly)
@@ -122,7 +135,7 @@ def test_mono_256_cn_polynomial_preconditioner_vs_oracle(pb, poly, monkeypatch):
         assert rel_l2(a, b) < TOL
 
 
-def test_mono_3d_interior_tiles_vs_oracle(pb):
+def test_mono_3d_interior_tiles_vs_oracle(pb, variant):
     # 72 x 20 x 12: x >= 64 so that a 32 x 8 x 4 tile of full cells exists away from the border ring; small sphere off to one side
     dims, L = (72, 20, 12), (4.0, 4.0, 4.0)
     mo, mg = po.Mesh(dims, L), pb.Mesh(dims, L)
@@ -143,7 +156,7 @@ def test_mono_3d_interior_tiles_vs_oracle(pb):
         assert rel_l2(a, b) < TOL
 
 
-def test_diph_3d_interior_tiles_vs_oracle(pb):
+def test_diph_3d_interior_tiles_vs_oracle(pb, variant):
     # examples/3D/Diffusion/Heat_2ph.jl:13-30 on a 72 x 24 x 12 slab of isotropic cells (h = 1/24): the sphere (r = 0.9) is thicker than the
     # slab, so the interface is two spherical caps across the whole y-z section and phase 1 holds a whole 32 x 8 x 4 tile of full cells
     dims, L = (72, 24, 12), (3.0, 1.0, 0.5)
