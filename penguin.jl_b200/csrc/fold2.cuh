@@ -5,7 +5,7 @@
 //
 // Staging.  The Krylov vectors live in a re-pitched copy of the local grid (x pitch = multiple of 32 doubles), which makes them
 // describable to the Tensor Memory Accelerator: one `cp.async.bulk.tensor` (SASS: UTMALDG) brings a tile PLUS its one-cell halo --
-// a 34 x 34 (2-D) or 34 x 10 x 6 (3-D) box of doubles -- into shared memory and signals an mbarrier; out-of-range coordinates (boxes
+// a 36 x 34 (2-D) or 36 x 10 x 6 (3-D) box of doubles -- into shared memory and signals an mbarrier; out-of-range coordinates (boxes
 // hanging over the array) are zero-filled by the hardware.  A block walks its tile list with TWO stages: the box of tile i+1 is in
 // flight while tile i is computed, so the dependent chain record -> address -> data that bounded the register kernel (one round trip
 // per tile, 20 us launches at 2048^2) is gone, and every neighbour value is read once from L2 instead of up to 3 times.
@@ -34,8 +34,10 @@ __device__ __forceinline__ void f2_mbar_expect_tx(uint32_t bar, uint32_t bytes)
 __device__ __forceinline__ void f2_mbar_wait(uint32_t bar, uint32_t phase)
 {
     uint32_t ok;
+    const long long t0 = clock64();
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+        if (!ok && clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a box that never lands is a bug (bad descriptor), not something to wait out
     } while (!ok);
 }
 __device__ __forceinline__ void f2_tma_load_2d(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1)
@@ -52,7 +54,9 @@ __device__ __forceinline__ void f2_tma_load_3d(uint32_t dst, const CUtensorMap *
 }
 
 template <int N> struct F2Box {
-    static constexpr int BX = 34, BY = N == 2 ? 34 : 10, BZ = N == 2 ? 1 : 6;
+    // x extent 36 = tile 32 + TWO cells on either side: the innermost TMA coordinate must be 16-byte aligned (measured on B200: a box of
+    // doubles starting at an odd x raises "illegal instruction", tests/experiments/tma_box_probe.cu), so the box starts at x0 - 2
+    static constexpr int HX = 2, BX = 32 + 2 * HX, BY = N == 2 ? 34 : 10, BZ = N == 2 ? 1 : 6;
     static constexpr int NB = BX * BY * BZ;
     static constexpr int BYTES = NB * 8;                           // what one TMA box delivers
     static constexpr int SLOT = (BYTES + 127) / 128 * 128;         // 128-byte aligned shared-memory slot
@@ -98,10 +102,10 @@ __global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_co
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read / written through the generic proxy before
         f2_mbar_expect_tx(bar, NA * B::BYTES);
         const CUtensorMap *ma = R.f == 0 ? &maps.a[0] : &maps.a[1];
-        if (N == 2) f2_tma_load_2d(dst, ma, bar, R.ox - 1, R.oy - 1); else f2_tma_load_3d(dst, ma, bar, R.ox - 1, R.oy - 1, R.oz - 1);
+        if (N == 2) f2_tma_load_2d(dst, ma, bar, R.ox - B::HX, R.oy - 1); else f2_tma_load_3d(dst, ma, bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
         if (NA == 2) {
             const CUtensorMap *mb = R.f == 0 ? &maps.b[0] : &maps.b[1];
-            if (N == 2) f2_tma_load_2d(dst + B::SLOT, mb, bar, R.ox - 1, R.oy - 1); else f2_tma_load_3d(dst + B::SLOT, mb, bar, R.ox - 1, R.oy - 1, R.oz - 1);
+            if (N == 2) f2_tma_load_2d(dst + B::SLOT, mb, bar, R.ox - B::HX, R.oy - 1); else f2_tma_load_3d(dst + B::SLOT, mb, bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
         }
     };
     double v[2] = {0.0, 0.0};
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_co
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             ok[k] = tile_cell(I, R, k, l[k], q[k]);
-            bi[k] = (lane + 1) + (ty * TYM + KY * k + 1) * SY + (N == 3 ? (k + 1) * SZ : 0);
+            bi[k] = (lane + B::HX) + (ty * TYM + KY * k + 1) * SY + (N == 3 ? (k + 1) * SZ : 0);
         }
         double pown[FU], xown[FU];
         if (MODE == 5) {
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_co
                 __syncthreads();
                 for (int j = tid; j < B::NB; j += FCH) {
                     const int jx = j % B::BX, jy = (j / B::BX) % B::BY, jz = j / (B::BX * B::BY);
-                    const long long gx = R.ox + jx - 1, gy = R.oy + jy - 1, gz = N == 3 ? R.oz + jz - 1 : 0;
+                    const long long gx = R.ox + jx - B::HX, gy = R.oy + jy - 1, gz = N == 3 ? R.oz + jz - 1 : 0;
                     if (gx >= 0 && gx < I.ld0 && gy >= 0 && gy < I.ld1 && gz >= 0 && gz < I.ld2) {
                         const int bo = A.bord[gx + I.ld0 * (gy + I.ld1 * gz)];
                         if (bo >= 0) sP[j] += A.dz[(size_t)f * A.nB + bo];

@@ -1118,7 +1118,7 @@ static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out)
     const int N = s->g.N;
     const cuuint64_t dims[3] = {(cuuint64_t)F.P0, (cuuint64_t)F.I.ld1, (cuuint64_t)F.I.ld2};
     const cuuint64_t strides[2] = {(cuuint64_t)F.P0 * 8, (cuuint64_t)F.P0 * (cuuint64_t)F.I.ld1 * 8};
-    const cuuint32_t box2[2] = {34, 34}, box3[3] = {34, 10, 6}, es[3] = {1, 1, 1};
+    const cuuint32_t box2[2] = {(cuuint32_t)F2Box<2>::BX, (cuuint32_t)F2Box<2>::BY}, box3[3] = {(cuuint32_t)F2Box<3>::BX, (cuuint32_t)F2Box<3>::BY, (cuuint32_t)F2Box<3>::BZ}, es[3] = {1, 1, 1};
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)N, (void *)ptr, dims, strides, N == 2 ? box2 : box3, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
