@@ -287,8 +287,8 @@ static int halo_exchange(pb200_ctx *ctx, const Grid &g, double *const *fields, i
 
 template <int K>
 __device__ __forceinline__ void block_reduce_publish(double (&v)[K], double *__restrict__ partials, double *__restrict__ results,
-                                                     unsigned *__restrict__ counter)
-{
+                                                     unsigned *__restrict__ counter, bool accumulate = false)
+{   // accumulate: results[k] += sum (a later launch of the same stream adds its share of one dot product: the order stays fixed)
     __shared__ double sm[RED_MAXK][32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -336,7 +336,7 @@ __device__ __forceinline__ void block_reduce_publish(double (&v)[K], double *__r
                 double r = lane < nw ? sm[k][lane] : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-                if (lane == 0) results[k] = r;
+                if (lane == 0) results[k] = accumulate ? results[k] + r : r;
             }
         }
         if (threadIdx.x == 0) *counter = 0u;

@@ -90,6 +90,7 @@ struct Items {
     int tym;                       // thread row ty covers tile rows ty * tym + ky * k  (2-D: FU consecutive rows per thread; else 1)
     long long ustride;             // linear index advance per k
     long long P0, ustrideq;        // x pitch and per-k advance of the re-pitched Krylov vectors
+    long long nq, nl;              // sizes of the re-pitched / reference-pitch arrays (debug bounds checks)
     long long ld0, ld1, ld2;       // local array extents
     int T0, T1, T2, nt0, nt1;      // tile extents and tiles per direction (build-time only)
     int sd, lz;                    // slab dimension and its local extent (first / last plane of it are ghosts)
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
         }
         __syncthreads();
         cnt[s_uni ? 0 : 1] += (double)nok;
-        if (s_uni && R.full) cnt[2] += (double)nok;
+        if (s_uni && R.full && !anyb) cnt[2] += (double)nok;
         __syncthreads();
     }
     block_reduce_publish<3>(cnt, partials, results, counter);
@@ -1145,14 +1146,18 @@ struct FoldSys {
     long long cells_fast = 0;                         // cells of full tiles with constant coefficients (the apply kernel's staged interior branch)
     Items I;                                // every item, index order (vector kernels)
     Items IA;                               // bulk tiles in cost-class order (operator apply)
-    Items IAi, IAg;                         // ... split into the interior class and the ghost class (box reaches a neighbour rank's ghost plane)
+    Items IAg;                              // the ghost class (box reaches a neighbour rank's ghost plane), every kind of tile
+    Items IAf, IAgen;                       // interior class: tiles of the pipelined kernel (all cells valid, constant coefficients) / the rest
+    Items IFall, IGall;                     // the same split over both classes (plain applies with the halo already exchanged)
     Items IG1;                              // ghost-class tiles + compact interface unknowns: pointwise p / x update of the fused iteration
     std::vector<void *> list_mem;           // device arrays behind the sub-lists
     FVec x, b, r, p, v, r0, s, t, z;
     FVec p2 = {}, zz = {};                  // fused iteration: second search-direction buffer, preconditioned residual (polynomial)
     bool have_p2 = false, have_zz = false;
     bool tma_ok = false;                    // the Krylov vectors are describable to TMA (fold2.cuh)
-    std::map<const double *, CUtensorMap> tmaps;
+    bool pipe = false;                      // ... and the interior constant-coefficient tiles go through the pipelined kernel (kf3_apply)
+    Items IAi_all;                          // interior class, every kind of tile (fused iteration without the pipelined kernel)
+    std::map<std::pair<const double *, int>, CUtensorMap> tmaps;
     bool have_bicg = false, have_z = false;
     int poly_m = 0;                         // degree of the polynomial preconditioner q(M^) (0: none)
     double poly_lo = 0.0, poly_hi = 0.0;    // Chebyshev interval of the bulk spectrum

@@ -71,7 +71,11 @@ struct F2Args {
     PolyCoef pc;
     double *partials, *results; unsigned *counter;
     const double *res;
+    int accumulate;                               // the published dot product is ADDED to the slot (a second launch of the same apply)
+    int dbg;                                      // debugging switches (PB200_DBG_F3)
 };
+// debugging: record an out-of-range index (code = kernel * 100 + site) in res[28] and SKIP the access
+#define F2_BAD(A, code) (*(const_cast<double *>((A).res) + 28) = (double)(code))
 
 // MODE 0..4: as kf_apply_dense (0 no dot; 1 (x, y); 2 (aux, y); 3 (y, x), (y, y); 4 y = pc.r aux + pc.z x + pc.A M^ x with (aux, y)).
 // MODE 5: fused CG step (header).  `maps` must describe A.a (and A.pold for MODE 5).
@@ -130,6 +134,10 @@ __global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_co
             ok[k] = tile_cell(I, R, k, l[k], q[k]);
             bi[k] = (lane + B::HX) + (ty * TYM + KY * k + 1) * SY + (N == 3 ? (k + 1) * SZ : 0);
         }
+        if (A.dbg & 16) {
+#pragma unroll
+            for (int k = 0; k < FU; ++k) if (ok[k] && (q[k] < 0 || q[k] >= I.nq)) { F2_BAD(A, 202); ok[k] = false; }
+        }
         double pown[FU], xown[FU];
         if (MODE == 5) {
             double *__restrict__ xf = f == 0 ? A.xs.f[0] : A.xs.f[1];
@@ -173,6 +181,7 @@ __global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_co
 #pragma unroll
                 for (int d = 0; d < N; ++d) {
                     const double *__restrict__ of = d == 0 ? of0 : (d == 1 ? of1 : of2);
+                    if ((A.dbg & 16) && ok[k] && (l[k] < 0 || l[k] + g.stride[d] >= I.nl)) { F2_BAD(A, 201); ok[k] = false; }
                     cm[k][d] = ok[k] ? of[l[k]] : 0.0;
                     cp[k][d] = ok[k] ? of[l[k] + g.stride[d]] : 0.0;
                 }
@@ -214,8 +223,8 @@ __global__ void __launch_bounds__(FCH, N == 2 ? 4 : 3) kf2_apply(const __grid_co
         __syncthreads();   // the stage may be refilled
         stage ^= 1;
     }
-    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5) { double w[1] = {v[0]}; block_reduce_publish<1>(w, A.partials, A.results, A.counter); }
-    if (MODE == 3) block_reduce_publish<2>(v, A.partials, A.results, A.counter);
+    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5) { double w[1] = {v[0]}; block_reduce_publish<1>(w, A.partials, A.results, A.counter, A.accumulate != 0); }
+    if (MODE == 3) block_reduce_publish<2>(v, A.partials, A.results, A.counter, A.accumulate != 0);
 }
 
 // Pointwise search-direction + solution update on a list of items: the ghost-class tiles of a slab-partitioned grid (whose p_k must exist
@@ -309,5 +318,199 @@ __global__ void __launch_bounds__(FCH) kf2_xflush(Items I, const double *res, FV
         (void)i;
         const double *__restrict__ pf = odd ? p1.f[f] : p0.f[f];
         xs.f[f][q] += alpha * pf[q];
+    }
+}
+
+// =================================================================================================================================
+// kf3_apply -- the interior constant-coefficient tiles (every cell valid, one constant per direction: 80-88 % of the cells of the
+// benchmark problems), as a warp-specialised TMA pipeline.
+//
+// Measured with kf2_apply above (one box in flight per block, operands of the epilogue loaded with ordinary loads): ~3 us per tile and
+// block whatever the box size -- the chain  tile record -> wait for the box -> x / coefficient loads -> stores  is a series of exposed
+// memory round trips, and four resident blocks do not hide it (0.28 of the HBM peak at 2048^2, 0.26 at 512^3).  Here
+//   * ONE producer thread (warp 8) runs S stages ahead: it reads the tile record, copies what the consumers need of it (store offset,
+//     field, the stencil constants) into the stage header, arms the stage's FULL barrier and issues every read of the tile as a TMA
+//     copy -- the box of the staged vector, the box of p_{k-1} (MODE 5), the 32 x 32 / 32 x 8 x 4 tile of x (MODE 5) or of aux;
+//   * EIGHT consumer warps wait on FULL, compute from shared memory only, store v / p_k / x straight from registers (256-byte rows)
+//     and release the stage through its EMPTY barrier (one arrival per warp).  No block-wide barrier in the loop: p_k = z + beta p_{k-1}
+//     is formed on the fly for the cell and its neighbours (a column of FU + 2 values per thread is shared along the k direction).
+// General tiles (interface band, border ring, partial tiles) keep kf2_apply; they run beside this kernel on the second stream.
+// =================================================================================================================================
+struct alignas(64) F3Maps { CUtensorMap a[2], b[2], t[2]; };   // boxes of the staged vector and of p_{k-1}; tile (no halo) of x (MODE 5) / aux (MODE 2, 4)
+struct F3Hdr { long long baseq; double cx, cy, cz; int f; int pad; };
+template <int N> struct F3Tile { static constexpr int BYTES = FTILE * 8; };
+
+__device__ __forceinline__ void f3_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// has_t: the third map is valid (MODE 5 always; MODE 2 / 4: aux is a vector of its own -- otherwise aux == the staged vector)
+template <int N, int MODE, int S>
+__global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__ F3Maps maps, Items I, F2Args A, int has_t, int dbg)
+{
+    using B = F2Box<N>;
+    constexpr int NBX = MODE == 5 ? 2 : 1;
+    constexpr bool TT = MODE == 5 || MODE == 2 || MODE == 4;               // a tile slot exists in the stage
+    constexpr int STAGE = NBX * B::SLOT + (TT ? F3Tile<N>::BYTES : 0);
+    extern __shared__ unsigned char f3_raw[];
+    __shared__ __align__(8) unsigned long long full[S], empty[S];
+    __shared__ F3Hdr hdr[S];
+    if (A.stop.sl_rr >= 0 && fold_done(A.res, A.stop)) return;
+    const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t raw = f2_smem_u32(f3_raw), sm0 = (raw + 127u) & ~127u;   // TMA destinations must be 128-byte aligned
+    unsigned char *smem = f3_raw + (sm0 - raw);
+    const uint32_t fb = f2_smem_u32(&full[0]), eb = f2_smem_u32(&empty[0]);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { f2_mbar_init(fb + 8 * s, 1); f2_mbar_init(eb + 8 * s, FCH / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double v[2] = {0.0, 0.0};
+    if (wid == FCH / 32) {
+        // ---- producer ----------------------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            const bool use_t = TT && (MODE == 5 || has_t);
+            const uint32_t bytes = NBX * B::BYTES + (use_t ? F3Tile<N>::BYTES : 0);
+            int n = 0;
+            TileRec Rn;
+            if ((int)blockIdx.x < I.n) Rn = I.rec[blockIdx.x];
+            for (int it = blockIdx.x; it < I.n; it += gridDim.x, ++n) {
+                const TileRec R = Rn;
+                const double c0 = I.ucoef[(size_t)it * PB_MAXD], c1 = I.ucoef[(size_t)it * PB_MAXD + 1], c2 = I.ucoef[(size_t)it * PB_MAXD + 2];
+                if (it + (int)gridDim.x < I.n) Rn = I.rec[it + gridDim.x];      // next record: in flight while this tile is issued
+                const int s = n % S, k = n / S;
+                if (k > 0) f2_mbar_wait(eb + 8 * s, (uint32_t)((k - 1) & 1));      // the consumers have released the stage's previous tile
+                F3Hdr h;
+                h.baseq = R.baseq; h.cx = c0; h.cy = c1; h.cz = c2; h.f = R.f; h.pad = 0;
+                hdr[s] = h;
+                const uint32_t dst = sm0 + s * STAGE, bar = fb + 8 * s;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                f2_mbar_expect_tx(bar, bytes);                                       // (release: the header is visible to whoever passes the barrier)
+                const int fi = R.f == 0 ? 0 : 1;
+                if (N == 2) f2_tma_load_2d(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1); else f2_tma_load_3d(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
+                if (MODE == 5) {
+                    if (N == 2) f2_tma_load_2d(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1);
+                    else f2_tma_load_3d(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
+                }
+                if (use_t) {
+                    if (N == 2) f2_tma_load_2d(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy); else f2_tma_load_3d(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy, R.oz);
+                }
+            }
+        }
+    } else {
+        // ---- consumers ---------------------------------------------------------------------------------------------------------
+        double alpha = 0.0, beta = 0.0;
+        if (MODE == 5) {
+            alpha = A.res[FS_XPEND] != 0.0 ? A.res[FS_ALPHA] : 0.0;
+            beta = safe_div(rho_at(A.res, A.sl_cur), rho_at(A.res, A.sl_old));
+        }
+        constexpr int TYM = N == 2 ? FU : 1, SY = B::BX, SZ = B::BX * B::BY;
+        constexpr int SK = N == 2 ? SY : SZ;                  // box stride of the k direction (the FU cells of a thread)
+        const int ty = wid;
+        const bool use_t = TT && (MODE == 5 || has_t);
+        int n = 0;
+        for (int it = blockIdx.x; it < I.n; it += gridDim.x, ++n) {
+            const int s = n % S, k0 = n / S;
+            f2_mbar_wait(fb + 8 * s, (uint32_t)(k0 & 1));
+            const F3Hdr h = hdr[s];
+            if (dbg & 16) {   // debugging: the header must be the one of this tile, and the staged boxes must hold this tile's data
+                const TileRec Rc = I.rec[it];
+                if (h.baseq != Rc.baseq || h.f != Rc.f) atomicAdd(const_cast<double *>(A.res) + 30, 1.0);
+                const double *__restrict__ sAc = reinterpret_cast<const double *>(smem + s * STAGE);
+                const int bb = (lane + B::HX) + (ty * (N == 2 ? FU : 1) + 1) * B::BX + (N == 3 ? B::BX * B::BY : 0);
+                const double *__restrict__ ga = Rc.f == 0 ? A.a.f[0] : A.a.f[1];
+                const long long qq = Rc.baseq + lane + (long long)(ty * (N == 2 ? FU : 1)) * I.P0;
+                if (sAc[bb] != ga[qq]) atomicAdd(const_cast<double *>(A.res) + 31, 1.0);
+            }
+            const double *__restrict__ sA = reinterpret_cast<const double *>(smem + s * STAGE);
+            const double *__restrict__ sB = sA + B::SLOT / 8;
+            const double *__restrict__ sT = sA + NBX * (B::SLOT / 8);
+            const int b0 = (lane + B::HX) + (ty * TYM + 1) * SY + (N == 3 ? SZ : 0);   // box index of the thread's cell k = 0
+            const int t0 = lane + (ty * TYM) * 32;                                    // tile index of it (2-D: rows; 3-D: plane k adds 256)
+            constexpr int TK = N == 2 ? 32 : 256;
+            // the staged vector on the thread's column (k = -1 .. FU) and on the neighbours of its FU cells
+#define F3_AT(j) (MODE == 5 ? sA[(j)] + beta * sB[(j)] : sA[(j)])
+            double col[FU + 2];
+#pragma unroll
+            for (int k = -1; k <= FU; ++k) col[k + 1] = F3_AT(b0 + k * SK);
+            double acc[FU];
+#pragma unroll
+            for (int k = 0; k < FU; ++k) {
+                const int b = b0 + k * SK;
+                double a = col[k + 1] + h.cx * (F3_AT(b - 1) + F3_AT(b + 1));
+                if (N == 2) a += h.cy * (col[k] + col[k + 2]);
+                else a += h.cy * (F3_AT(b - SY) + F3_AT(b + SY)) + h.cz * (col[k] + col[k + 2]);
+                acc[k] = a;
+            }
+#undef F3_AT
+            const long long q0 = h.baseq + lane + (long long)(ty * TYM) * I.P0;
+            const int f = h.f;
+            double *__restrict__ yf = f == 0 ? A.y.f[0] : A.y.f[1];
+            if ((dbg & 16) && MODE == 5 && N == 3) {   // debugging: recompute the thread's four cells from GLOBAL memory
+                const double *__restrict__ gz = f == 0 ? A.a.f[0] : A.a.f[1];
+                const double *__restrict__ gp = f == 0 ? A.pold.f[0] : A.pold.f[1];
+                const double *__restrict__ uc = I.ucoef + (size_t)it * PB_MAXD;
+                for (int k = 0; k < FU; ++k) {
+                    const long long q = q0 + (long long)k * I.ustrideq, sy = I.P0, sz = I.ustrideq;
+#define GP(j) (gz[(j)] + beta * gp[(j)])
+                    const double ref = GP(q) + uc[0] * (GP(q - 1) + GP(q + 1)) + uc[1] * (GP(q - sy) + GP(q + sy)) + uc[2] * (GP(q - sz) + GP(q + sz));
+#undef GP
+                    if (fabs(ref - acc[k]) > 1e-12 * (1.0 + fabs(ref))) atomicAdd(const_cast<double *>(A.res) + 29, 1.0);
+                }
+            }
+            if ((dbg & 16) && (q0 < 0 || q0 + (long long)(FU - 1) * I.ustrideq >= I.nq)) { F2_BAD(A, 301); __syncwarp(); if (lane == 0) f3_mbar_arrive(eb + 8 * s); continue; }
+            if (MODE == 5) {
+                double *__restrict__ pn = f == 0 ? A.pnew.f[0] : A.pnew.f[1];
+                double *__restrict__ xf = f == 0 ? A.xs.f[0] : A.xs.f[1];
+#pragma unroll
+                for (int k = 0; k < FU; ++k) {
+                    const long long q = q0 + (long long)k * I.ustrideq;
+                    const double pold = sB[b0 + k * SK], xo = (dbg & 1) ? xf[q] : sT[t0 + k * TK];
+                    yf[q] = acc[k];
+                    pn[q] = col[k + 1];
+                    xf[q] = xo + alpha * pold;
+                    v[0] += col[k + 1] * acc[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < FU; ++k) {
+                    const long long q = q0 + (long long)k * I.ustrideq;
+                    const double av = (MODE == 2 || MODE == 4) ? (use_t ? sT[t0 + k * TK] : col[k + 1]) : 0.0;
+                    double a = acc[k];
+                    if (MODE == 4) a = A.pc.r * av + A.pc.z * col[k + 1] + A.pc.A * a;
+                    yf[q] = a;
+                    if (MODE == 1) v[0] += col[k + 1] * a;
+                    if (MODE == 2 || MODE == 4) v[0] += av * a;
+                    if (MODE == 3) { v[0] += a * col[k + 1]; v[1] += a * a; }
+                }
+            }
+            if (dbg & 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) f3_mbar_arrive(eb + 8 * s);    // this warp has read everything it needs of the stage
+        }
+    }
+    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5) { double w[1] = {v[0]}; block_reduce_publish<1>(w, A.partials, A.results, A.counter, A.accumulate != 0); }
+    if (MODE == 3) block_reduce_publish<2>(v, A.partials, A.results, A.counter, A.accumulate != 0);
+}
+
+// debugging aid (PB200_DBG_CHECK): compare two vectors on the tiles of a list; out[0] = number of differing cells, out[1] = item index of the last one seen,
+// out[2] = its flags (uni | full << 4 | ghost << 5), out[3] = max |a - b|
+__global__ void __launch_bounds__(FCH) kf2_dbg_compare(Items I, FVec a, FVec b, double tol, double *out)
+{
+    for (int it = blockIdx.x; it < I.n; it += gridDim.x) {
+        const TileRec R = I.rec[it];
+        if (R.f >= 2) continue;
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            long long i, q;
+            if (!tile_cell(I, R, k, i, q)) continue;
+            const double d = fabs(a.f[R.f][q] - b.f[R.f][q]);
+            if (d > tol) {
+                atomicAdd(out, 1.0);
+                out[1] = (double)it; out[2] = (double)(I.uni[it] | (R.full << 4) | (R.ghost << 5));
+                if (d > out[3]) out[3] = d;
+                atomicMin((int *)(out + 4), it);
+                atomicMax((int *)(out + 5), it);
+                if (k == 0 && threadIdx.x == 0) atomicAdd(out + 6, 1.0);   // tiles (counted at their first cell)
+            }
+        }
     }
 }

@@ -201,6 +201,7 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     memset(&mine, 0, sizeof(mine));
     if (cudaMalloc((void **)&P->mbox, P->bytes) != cudaSuccess) ok = 0;
     if (ok && cudaMemset(P->mbox, 0, P->bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaDeviceSynchronize() != cudaSuccess) ok = 0;   // (default-stream memset vs the non-blocking streams that use the mailbox next)
     if (ok && cudaIpcGetMemHandle(&mine, P->mbox) != cudaSuccess) ok = 0;
     cudaGetLastError();
     // all-gather the handles (64 bytes each) and the ok flags through NCCL

@@ -51,6 +51,7 @@ static int ctx_common_init(pb200_ctx *c, int device)
     CUDA_TRY(c, cudaMalloc((void **)&c->d_partials2, sizeof(double) * RED_MAXK * RED_MAXBLOCKS));
     CUDA_TRY(c, cudaMalloc((void **)&c->d_counter2, sizeof(unsigned)));
     CUDA_TRY(c, cudaMemset(c->d_counter2, 0, sizeof(unsigned)));
+    CUDA_TRY(c, cudaDeviceSynchronize());   // the memsets above ran on the legacy default stream; the library's streams are non-blocking and do not wait for it
     return PB200_OK;
 }
 
@@ -259,6 +260,7 @@ extern "C" int pb200_capacity_destroy(pb200_capacity *c)
 // DiffusionOps
 // =================================================================================================================
 struct pb200_ops {
+    pb200_ctx *ctx;          // (kept here: the destroy path must not reach through `cap`, which a garbage-collected host may have released first)
     pb200_capacity *cap;
     double *Wd[PB_MAXD] = {};
 };
@@ -272,16 +274,18 @@ static PhaseDev phase_dev(const pb200_ops *o, const double *Darr, double Dc)
 }
 static inline int sgrid(pb200_ctx *ctx, int64_t n) { return red_grid(ctx, n); }
 
+extern "C" int pb200_ops_destroy(pb200_ops *o);
 extern "C" int pb200_ops_create(pb200_capacity *cap, pb200_ops **out)
 {
     if (!cap || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
     pb200_ctx *ctx = cap->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_ops *o = new pb200_ops();
+    o->ctx = ctx;
     o->cap = cap;
     for (int d = 0; d < cap->g.N; ++d) {
         int rc = dev_alloc(ctx, &o->Wd[d], cap->g.nloc);
-        if (rc) return rc;
+        if (rc) { pb200_ops_destroy(o); return rc; }
         k_wdag<<<sgrid(ctx, cap->g.nloc), RED_THREADS, 0, ctx->stream>>>(cap->g.nloc, cap->W[d], o->Wd[d]);
         LAUNCH_CHECK(ctx);
     }
@@ -292,8 +296,8 @@ extern "C" int pb200_ops_create(pb200_capacity *cap, pb200_ops **out)
 extern "C" int pb200_ops_destroy(pb200_ops *o)
 {
     if (!o) return PB200_OK;
-    cudaSetDevice(o->cap->ctx->device);
-    cudaStreamSynchronize(o->cap->ctx->stream);
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
     for (int d = 0; d < PB_MAXD; ++d) dev_free(o->Wd[d]);
     delete o;
     return PB200_OK;
@@ -778,7 +782,7 @@ static int fold_band_spectrum(pb200_solver *s)
 typedef CUresult (*pb_encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static pb_encode_tiled_t pb_encode_tiled();
-static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out);
+static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out, int kind = 0);
 static int fold_build(pb200_solver *s, const ApplyCoef &ac)
 {
     pb200_ctx *ctx = s->ctx;
@@ -894,7 +898,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         if (g.N == 1) { I.T0 = FTILE; I.T1 = 1; I.T2 = 1; I.shx = 8; I.kx = FCH; I.ky = 0; I.kz = 0; I.tym = 1; I.ustride = FCH; }
         else if (g.N == 2) { I.T0 = 32; I.T1 = 32; I.T2 = 1; I.shx = 5; I.kx = 0; I.ky = 1; I.kz = 0; I.tym = FU; I.ustride = I.ld0; }
         else { I.T0 = 32; I.T1 = 8; I.T2 = 4; I.shx = 5; I.kx = 0; I.ky = 0; I.kz = 1; I.tym = 1; I.ustride = I.ld0 * I.ld1; }
-        I.P0 = F.P0;
+        I.P0 = F.P0; I.nq = F.nlocq; I.nl = g.nloc;
         I.ustrideq = g.N == 1 ? FCH : (g.N == 2 ? F.P0 : F.P0 * I.ld1);
         I.nt0 = (int)((I.ld0 + I.T0 - 1) / I.T0); I.nt1 = (int)((I.ld1 + I.T1 - 1) / I.T1);
         const long long nt2 = (I.ld2 + I.T2 - 1) / I.T2;
@@ -942,8 +946,8 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         // tiles of each class +-1 for any grid size, and the order is fixed, so its reduction stays deterministic.  The streaming vector
         // kernels keep the index-ordered list: all tiles cost them the same, and neighbouring blocks on neighbouring tiles share DRAM
         // pages (the class order cost them 25 % at 384^3).
-        F.IA = I; F.IAi = I; F.IAg = I; F.IG1 = I;
-        F.IAg.n = 0; F.IG1.n = 0;
+        F.IA = I; F.IAg = I; F.IG1 = I; F.IAf = I; F.IAgen = I; F.IFall = I; F.IGall = I; F.IAi_all = I;
+        F.IAg.n = 0; F.IG1.n = 0; F.IAf.n = 0; F.IAgen.n = 0; F.IFall.n = 0; F.IGall.n = 0; F.IAi_all.n = 0;
         if (F.nitems > 0) {
             const int n = F.nitems;
             std::vector<int> hi(n);
@@ -963,7 +967,10 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
                 CUDA_TRY(ctx, cudaMalloc((void **)&d_rec, sizeof(TileRec) * na)); F.list_mem.push_back(d_rec);
                 CUDA_TRY(ctx, cudaMalloc((void **)&d_uni, na)); F.list_mem.push_back(d_uni);
                 CUDA_TRY(ctx, cudaMalloc((void **)&d_uc, sizeof(double) * PB_MAXD * na)); F.list_mem.push_back(d_uc);
-                CUDA_TRY(ctx, cudaMemcpy(d_it, ids.data(), sizeof(int) * na, cudaMemcpyHostToDevice));
+                // Stream-ordered: a plain cudaMemcpy from pageable memory returns when the data is STAGED, the DMA to the device may still be
+                // running, and the kernels below are launched on a non-blocking stream that does not wait for the legacy default stream
+                // (seen on B200: a run-dependent suffix of a list read as zeros = tile 0 -> stray work on tile 0, garbage on the real tiles).
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_it, ids.data(), sizeof(int) * na, cudaMemcpyHostToDevice, ctx->stream));
                 out.it = d_it;
                 kf_tile_records<<<((int)na + 255) / 256, 256, 0, ctx->stream>>>(out, d_rec); LAUNCH_CHECK(ctx);
                 out.rec = d_rec; out.uni = d_uni; out.ucoef = d_uc;
@@ -975,18 +982,53 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
             };
             // cost-class order of the bulk tiles (slow first): all / interior class / ghost class (box reaches a neighbour rank's ghost plane)
             const bool reorder = !getenv("PB200_NO_REORDER");
-            std::vector<int> all, inner, ghost, g1;
+            std::vector<int> all, ghost, g1, fast_i, gen_i, fast_all, gen_all, inner_all;
             for (int cls = 0; cls < 2; ++cls)
                 for (int i = 0; i < n; ++i) {
                     if (hr[i].f >= 2) continue;     // (w chunks are not the dense apply's business)
-                    const int c = (!reorder || ((hu[i] & 1) && hr[i].full)) ? 1 : 0;
+                    // every cell valid, one constant per direction, no band cell: the pipelined kernel (kf3_apply).  (A tile in which a field lives on
+                    // cut cells only has all-zero coefficients -- "constant" -- and still holds band cells, whose z carries the band correction.)
+                    const bool fast = (hu[i] & 1) && hr[i].full && !(hu[i] & 2);
+                    const int c = (!reorder || fast) ? 1 : 0;
                     if (c != cls) continue;
                     all.push_back(hi[i]);
-                    (hr[i].ghost ? ghost : inner).push_back(hi[i]);
+                    (fast ? fast_all : gen_all).push_back(hi[i]);
+                    if (hr[i].ghost) ghost.push_back(hi[i]);
+                    else { (fast ? fast_i : gen_i).push_back(hi[i]); inner_all.push_back(hi[i]); }
                 }
             // pointwise p / x update of the fused iteration: ghost-class tiles + the compact interface unknowns (index order)
             for (int i = 0; i < n; ++i) if (hr[i].f >= 2 || hr[i].ghost) g1.push_back(hi[i]);
-            if ((rc = make_list(all, F.IA)) || (rc = make_list(inner, F.IAi)) || (rc = make_list(ghost, F.IAg)) || (rc = make_list(g1, F.IG1))) return rc;
+            if ((rc = make_list(all, F.IA)) || (rc = make_list(ghost, F.IAg)) || (rc = make_list(g1, F.IG1)) || (rc = make_list(fast_i, F.IAf)) ||
+                (rc = make_list(gen_i, F.IAgen)) || (rc = make_list(fast_all, F.IFall)) || (rc = make_list(gen_all, F.IGall)) || (rc = make_list(inner_all, F.IAi_all))) return rc;
+            if (getenv("PB200_DBG_LISTS")) {   // debugging: every sub-list must carry the base list's records / flags / constants for its items
+                std::vector<double> hc((size_t)n * PB_MAXD);
+                CUDA_TRY(ctx, cudaMemcpy(hc.data(), F.ucoef, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+                std::map<int, int> pos;
+                for (int i = 0; i < n; ++i) pos[hi[i]] = i;
+                const Items *Ls[8] = {&F.IA, &F.IAg, &F.IG1, &F.IAf, &F.IAgen, &F.IFall, &F.IGall, &F.IAi_all};
+                const char *nm[8] = {"IA", "IAg", "IG1", "IAf", "IAgen", "IFall", "IGall", "IAi_all"};
+                for (int q = 0; q < 8; ++q) {
+                    const Items &Lq = *Ls[q];
+                    if (Lq.n == 0) continue;
+                    std::vector<int> li(Lq.n); std::vector<TileRec> lr(Lq.n); std::vector<unsigned char> lu(Lq.n); std::vector<double> lc((size_t)Lq.n * PB_MAXD);
+                    CUDA_TRY(ctx, cudaMemcpy(li.data(), Lq.it, sizeof(int) * (size_t)Lq.n, cudaMemcpyDeviceToHost));
+                    CUDA_TRY(ctx, cudaMemcpy(lr.data(), Lq.rec, sizeof(TileRec) * (size_t)Lq.n, cudaMemcpyDeviceToHost));
+                    CUDA_TRY(ctx, cudaMemcpy(lu.data(), Lq.uni, (size_t)Lq.n, cudaMemcpyDeviceToHost));
+                    CUDA_TRY(ctx, cudaMemcpy(lc.data(), Lq.ucoef, sizeof(double) * lc.size(), cudaMemcpyDeviceToHost));
+                    long bad_rec = 0, bad_uni = 0, bad_c = 0; int first = -1;
+                    for (int j = 0; j < Lq.n; ++j) {
+                        const int b = pos[li[j]];
+                        const bool r_ok = lr[j].base == hr[b].base && lr[j].baseq == hr[b].baseq && lr[j].f == hr[b].f && lr[j].full == hr[b].full && lr[j].ox == hr[b].ox && lr[j].oz == hr[b].oz;
+                        const bool bulk = hr[b].f < 2;
+                        const bool u_ok = !bulk || lu[j] == hu[b];
+                        bool c_ok = true;
+                        if (bulk) for (int dd = 0; dd < g.N; ++dd) c_ok = c_ok && lc[(size_t)j * PB_MAXD + dd] == hc[(size_t)b * PB_MAXD + dd];
+                        if (!r_ok) ++bad_rec; if (!u_ok) ++bad_uni; if (!c_ok) ++bad_c;
+                        if ((!r_ok || !u_ok || !c_ok) && first < 0) first = j;
+                    }
+                    fprintf(stderr, "[pb200] list %s: %d items, bad records %ld, bad flags %ld, bad constants %ld (first bad item %d)\n", nm[q], Lq.n, bad_rec, bad_uni, bad_c, first);
+                }
+            }
         }
     }
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v};
@@ -997,6 +1039,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
     // TMA staging needs global strides that are multiples of 16 bytes (an even pitch: the re-pitched layout) and >= 2-D grids
     F.tma_ok = g.N >= 2 && (F.P0 % 2 == 0) && !getenv("PB200_NO_TMA") && pb_encode_tiled() != nullptr;
     if (F.tma_ok) { CUtensorMap probe; if (fold_tmap(s, F.x.f[0], &probe)) { F.tma_ok = false; cudaGetLastError(); } }
+    F.pipe = F.tma_ok && !getenv("PB200_NO_PIPE");
     // the band preconditioner is a COLLECTIVE decision (its set-up and every iteration contain reductions over the ranks): it is used
     // when ANY rank holds band cells, and ranks without band cells simply contribute zeros
     if (d.has_w && !getenv("PB200_NO_BAND_PREC")) {
@@ -1108,22 +1151,24 @@ static pb_encode_tiled_t pb_encode_tiled()
     return fn;
 }
 // descriptor of one bulk field of a Krylov vector: an N-d tensor of doubles (P0, ld1[, ld2]) read in boxes of tile + halo
-static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out)
+static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out, int kind)   // kind 0: tile + halo box, 1: tile
 {
     FoldSys &F = s->F;
-    auto it = F.tmaps.find(ptr);
+    auto it = F.tmaps.find(std::make_pair(ptr, kind));
     if (it != F.tmaps.end()) { *out = it->second; return PB200_OK; }
     pb_encode_tiled_t enc = pb_encode_tiled();
     if (!enc) return set_err(s->ctx, PB200_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available");
     const int N = s->g.N;
     const cuuint64_t dims[3] = {(cuuint64_t)F.P0, (cuuint64_t)F.I.ld1, (cuuint64_t)F.I.ld2};
     const cuuint64_t strides[2] = {(cuuint64_t)F.P0 * 8, (cuuint64_t)F.P0 * (cuuint64_t)F.I.ld1 * 8};
-    const cuuint32_t box2[2] = {(cuuint32_t)F2Box<2>::BX, (cuuint32_t)F2Box<2>::BY}, box3[3] = {(cuuint32_t)F2Box<3>::BX, (cuuint32_t)F2Box<3>::BY, (cuuint32_t)F2Box<3>::BZ}, es[3] = {1, 1, 1};
+    cuuint32_t box2[2] = {(cuuint32_t)F2Box<2>::BX, (cuuint32_t)F2Box<2>::BY}, box3[3] = {(cuuint32_t)F2Box<3>::BX, (cuuint32_t)F2Box<3>::BY, (cuuint32_t)F2Box<3>::BZ};
+    const cuuint32_t es[3] = {1, 1, 1};
+    if (kind == 1) { box2[0] = 32; box2[1] = 32; box3[0] = 32; box3[1] = 8; box3[2] = 4; }
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)N, (void *)ptr, dims, strides, N == 2 ? box2 : box3, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(s->ctx, PB200_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
-    F.tmaps[ptr] = m;
+    F.tmaps[std::make_pair(ptr, kind)] = m;
     *out = m;
     return PB200_OK;
 }
@@ -1169,6 +1214,60 @@ static int fold2_apply(pb200_solver *s, const Items &L, const F2Maps &maps, cons
 #undef F2L
 }
 
+// ---- the pipelined kernel (kf3_apply) on a list of interior constant-coefficient tiles ------------------------------------------------
+static int fold_maps3(pb200_solver *s, const FVec &a, const FVec *b, const FVec *t, F3Maps *out)
+{
+    memset(out, 0, sizeof(*out));
+    int rc;
+    for (int f = 0; f < s->F.d.nbulk; ++f) {
+        if ((rc = fold_tmap(s, a.f[f], &out->a[f]))) return rc;
+        if (b && (rc = fold_tmap(s, b->f[f], &out->b[f]))) return rc;
+        if (t && (rc = fold_tmap(s, t->f[f], &out->t[f], 1))) return rc;
+    }
+    if (s->F.d.nbulk == 1) { out->a[1] = out->a[0]; out->b[1] = out->b[0]; out->t[1] = out->t[0]; }
+    return PB200_OK;
+}
+template <int N, int MODE>
+static int fold3_launch(pb200_solver *s, const Items &L, const F3Maps &maps, const F2Args &A, int has_t, cudaStream_t st)
+{
+    pb200_ctx *ctx = s->ctx;
+    constexpr int S = MODE == 5 ? (N == 2 ? 3 : 2) : (N == 2 ? 4 : 3);
+    constexpr bool TT = MODE == 5 || MODE == 2 || MODE == 4;
+    constexpr int STAGE = (MODE == 5 ? 2 : 1) * F2Box<N>::SLOT + (TT ? FTILE * 8 : 0);
+    constexpr int smem = S * STAGE + 128;
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf3_apply<N, MODE, S>, FCH + 32, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    int grid = L.n < ctx->sm_count * nb ? L.n : ctx->sm_count * nb;
+    const int dbg = getenv("PB200_DBG_F3") ? atoi(getenv("PB200_DBG_F3")) : 0;
+    if ((dbg & 4) && grid > ctx->sm_count) grid = ctx->sm_count;
+    if (grid < 1) grid = 1;
+    if ((dbg & 8) && MODE == 5) {   // one stage: no overlap, tests the pipeline logic
+        constexpr int smem1 = STAGE + 128;
+        static bool attr1 = false;
+        if (!attr1) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1)); attr1 = true; }
+        kf3_apply<N, MODE, 1><<<grid, FCH + 32, smem1, st>>>(maps, L, A, has_t, dbg);
+    } else
+    kf3_apply<N, MODE, S><<<grid, FCH + 32, smem, st>>>(maps, L, A, has_t, dbg);
+    LAUNCH_CHECK(ctx);
+    return PB200_OK;
+}
+static int fold3_apply(pb200_solver *s, const Items &L, const F3Maps &maps, const F2Args &A, int mode, int has_t, cudaStream_t st)
+{
+    const int N = s->g.N;
+#define F3L(M_) (N == 2 ? fold3_launch<2, M_>(s, L, maps, A, has_t, st) : fold3_launch<3, M_>(s, L, maps, A, has_t, st))
+    switch (mode) {
+    case 0: return F3L(0);
+    case 1: return F3L(1);
+    case 2: return F3L(2);
+    case 3: return F3L(3);
+    case 4: return F3L(4);
+    default: return F3L(5);
+    }
+#undef F3L
+}
+
 // y = M^ x with the dot products of `mode` published (dense part -> *_D slots, band part -> *_B slots) and summed over the ranks
 // mode 4 (one step of the polynomial preconditioner, y = pc.r aux + pc.z x + pc.A M^ x): the partial sums of (aux, y) go to the
 // caller's slots (dense part, band part) and are reduced over the ranks by the caller together with the rest of their group
@@ -1191,7 +1290,15 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
         F2Args A;
         memset(&A, 0, sizeof(A));
         A.a = x; A.y = y; A.aux = aux; A.stop = stop; A.pc = pc; A.partials = ctx->d_partials; A.results = slotD; A.counter = ctx->d_counter; A.res = res;
-        if ((rc = fold2_apply(s, F.IA, maps, A, mode, ctx->stream))) return rc;
+        A.dbg = getenv("PB200_DBG_F3") ? atoi(getenv("PB200_DBG_F3")) : 0;
+        if (F.pipe && !getenv("PB200_DBG_NOPIPE_PLAIN")) {   // interior constant-coefficient tiles: the pipelined kernel; the rest adds its share of the dot products afterwards
+            const int has_t = (mode == 2 || mode == 4) && aux.f[0] != x.f[0];
+            F3Maps m3;
+            if ((rc = fold_maps3(s, x, nullptr, has_t ? &aux : nullptr, &m3))) return rc;
+            if ((rc = fold3_apply(s, F.IFall, m3, A, mode, has_t, ctx->stream))) return rc;
+            A.accumulate = 1;
+            if ((rc = fold2_apply(s, F.IGall, maps, A, mode, ctx->stream))) return rc;
+        } else if ((rc = fold2_apply(s, F.IA, maps, A, mode, ctx->stream))) return rc;
     } else {
 #define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.IA, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop, pc)))
     if (mode == 0) FOLD_DENSE(0); else if (mode == 1) FOLD_DENSE(1); else if (mode == 2) FOLD_DENSE(2); else if (mode == 3) FOLD_DENSE(3); else FOLD_DENSE(4);
@@ -1394,7 +1501,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 const bool multi = ctx->nranks > 1;
                 const FVec &pold = curp ? F.p2 : F.p, &pnew = curp ? F.p : F.p2;    // iteration j reads P[j & 1], writes P[(j + 1) & 1]
                 const FVec &zsrc = poly ? F.zz : F.r;
-                cudaStream_t st2 = ctx->profile ? ctx->stream : ctx->stream2;   // (per-launch event timing: everything in one stream)
+                cudaStream_t st2 = (ctx->profile || getenv("PB200_DBG_SERIAL")) ? ctx->stream : ctx->stream2;   // (per-launch event timing: everything in one stream)
                 const bool side = F.IG1.n > 0 || multi;
                 F2Args A;
                 memset(&A, 0, sizeof(A));
@@ -1402,6 +1509,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 A.dz = prec ? F.dz : nullptr; A.bord = F.bord; A.nB = F.d.nB;
                 A.sl_old = FS_TRIPLE(nxt); A.sl_cur = FS_TRIPLE(curp); A.stop = st; A.res = res;
                 A.partials = ctx->d_partials; A.counter = ctx->d_counter; A.results = res + FS_SIG_D;
+                A.dbg = getenv("PB200_DBG_F3") ? atoi(getenv("PB200_DBG_F3")) : 0;
                 if (side) {
                     if (st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
                     if (F.IG1.n > 0) {   // ghost-class tiles and the compact interface unknowns: p_k and x pointwise
@@ -1414,21 +1522,62 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 }
                 F2Maps mi;
                 if ((rc2 = fold_maps(s, zsrc, &pold, &mi))) return rc2;
+                const bool split = F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED");     // interior class: pipelined kernel on the constant-coefficient tiles + general kernel on the rest (beside it)
+                if (split) {
+                    if (!side && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
+                    F2Args Gn = A;
+                    Gn.partials = ctx->d_partials2; Gn.counter = ctx->d_counter2; Gn.results = res + FS_SIG_G;
+                    if (getenv("PB200_DBG_ONESLOT")) { Gn.partials = ctx->d_partials; Gn.counter = ctx->d_counter; Gn.results = res + FS_SIG_D; A.accumulate = 1; }
+                    prof_mark(ctx, PB_PROF_APPLY);
+                    if ((rc2 = fold2_apply(s, F.IAgen, mi, Gn, 5, st2))) return rc2;
+                    prof_mark(ctx, PB_PROF_APPLY);
+                }
                 prof_mark(ctx, PB_PROF_APPLY);
                 ctx->apply_launches++;
-                if ((rc2 = fold2_apply(s, multi ? F.IAi : F.IA, mi, A, 5, ctx->stream))) return rc2;
+                if (split) {
+                    F3Maps m3;
+                    if ((rc2 = fold_maps3(s, zsrc, &pold, &F.x, &m3))) return rc2;
+                    if (getenv("PB200_DBG_SPLIT2")) { if ((rc2 = fold2_apply(s, F.IAf, mi, A, 5, ctx->stream))) return rc2; }
+                    else if ((rc2 = fold3_apply(s, F.IAf, m3, A, 5, 1, ctx->stream))) return rc2;
+                } else if ((rc2 = fold2_apply(s, multi ? F.IAi_all : F.IA, mi, A, 5, ctx->stream))) return rc2;
                 prof_mark(ctx, PB_PROF_APPLY);
-                if (side && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+                if ((side || split) && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
                 if (multi) {
                     // ghost-class tiles: plain staged apply of p_k.  After the join: their boxes also read p_k cells of interior-class tiles,
-                    // which the fused kernel has only now finished writing.
+                    // which the fused kernels have only now finished writing.
                     F2Maps mg;
                     if ((rc2 = fold_maps(s, pnew, nullptr, &mg))) return rc2;
                     F2Args G = A;
-                    G.a = pnew; G.results = res + FS_SIG_G;
+                    G.a = pnew; G.results = res + FS_SIG_G; G.accumulate = split ? 1 : 0;
                     prof_mark(ctx, PB_PROF_APPLY);
                     if ((rc2 = fold2_apply(s, F.IAg, mg, G, 1, ctx->stream))) return rc2;
                     prof_mark(ctx, PB_PROF_APPLY);
+                }
+                if (getenv("PB200_DBG_CHECK") && !multi) {
+                    // recompute v = M^ p_k with the register kernel and compare, list by list
+                    if (!F.have_bicg) { FVec *vs[] = {&F.r0, &F.s, &F.t}; for (FVec *vv : vs) if ((rc2 = fold_alloc_vec(s, vv))) return rc2; F.have_bicg = true; }
+                    const StopCrit ns = {0.0, 0.0, -1};
+                    DISPATCH_N(s->g.N, (kf_apply_dense<N, 0><<<wave_grid(s, kf_apply_dense<N, 0>), FCH, 0, ctx->stream>>>(s->g, F.d, F.IA, pnew, F.t, F.t, ctx->d_partials, res + FS_TMP, ctx->d_counter, res, ns, PolyCoef{0.0, 0.0, 0.0})));
+                    LAUNCH_CHECK(ctx);
+                    double *d_out = nullptr;
+                    CUDA_TRY(ctx, cudaMalloc((void **)&d_out, 8 * sizeof(double)));
+                    const Items *Ls[2] = {&F.IAgen, &F.IAf};
+                    for (int q = 0; q < 2; ++q) {
+                        CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, 8 * sizeof(double), ctx->stream));
+                        { const int big = 1 << 30; CUDA_TRY(ctx, cudaMemcpyAsync(d_out + 4, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); }
+                        if (Ls[q]->n > 0) { kf2_dbg_compare<<<Ls[q]->n < 1024 ? Ls[q]->n : 1024, FCH, 0, ctx->stream>>>(*Ls[q], F.v, F.t, 1e-11, d_out); LAUNCH_CHECK(ctx); }
+                        double h[8];
+                        CUDA_TRY(ctx, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+                        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                        double done_h[2];
+                        CUDA_TRY(ctx, cudaMemcpy(done_h, res + st.sl_rr, sizeof(double), cudaMemcpyDeviceToHost));
+                        fprintf(stderr, "[pb200] check v (%s list, %d tiles): %g cells differ, last item %g flags %g max diff %.3e; items %d..%d, tiles (first cell bad) %g\n", q ? "fast" : "general", Ls[q]->n, h[0], h[1], h[2], h[3], *(int *)&h[4], *(int *)&h[5], h[6]);
+                    }
+                    cudaFree(d_out);
+                    double dbg2[3];
+                    CUDA_TRY(ctx, cudaMemcpy(dbg2, res + 29, sizeof(dbg2), cudaMemcpyDeviceToHost));
+                    { double bad; CUDA_TRY(ctx, cudaMemcpy(&bad, res + 28, sizeof(double), cudaMemcpyDeviceToHost)); if (bad != 0.0) fprintf(stderr, "[pb200] BOUNDS violation code %g\n", bad); }
+                    fprintf(stderr, "[pb200] check kf3: header mismatches %g, staged-box mismatches %g, v vs global recompute mismatches %g (cumulative)\n", dbg2[1], dbg2[2], dbg2[0]);
                 }
                 if (F.d.has_w) {     // band part of v = M^ p_k (needs p_k everywhere)
                     prof_mark(ctx, PB_PROF_BAPPLY);

@@ -76,7 +76,7 @@ def diph256(pb):
 
 # implementations of the Krylov iteration on the folded system (csrc/fold2.cuh): the default is the fused, TMA-staged one; the switches
 # peel it back layer by layer so that a parity failure names its layer
-VARIANTS = {"fused_tma": {}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1"},
+VARIANTS = {"fused_pipelined": {}, "fused_two_stage": {"PB200_NO_PIPE": "1"}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1"},
             "reference_pitch": {"PB200_NO_REPITCH": "1"}}
 
 
