@@ -47,11 +47,14 @@ struct FoldDev {
     const int *bord;
     double *Linv;    // [5][nB]: i00 i11 i20 i21 i22
     int *EB;         // [nE]
-    int *EnbrB;      // [nE][2N]   (AoS: one warp works on one band cell)
-    double *Eblk;    // [nE][(1+2N)*9]  block 0: self, 1+2d: lower neighbour in d, 2+2d: upper; each 3x3 row-major
+    int *EnbrB;      // [2N][nEp]        (SoA: one THREAD works on one band / fringe cell, consecutive threads on consecutive cells)
+    double *Eblk;    // [(1+2N)*9][nEp]  block 0: self, 1+2d: lower neighbour in d, 2+2d: upper; each 3x3 row-major
+    unsigned char *Efix;   // [nE] bit k: gathered cell k (0 self, 1 + kk neighbours) lies in a tile of the fused kernel (its p lacks the band correction dz)
+    int nEp;         // nE rounded up to a multiple of 32
     // Krylov vectors (FVec bulk fields) live in a RE-PITCHED copy of the local grid: x rows padded from ld0 (the reference's odd n+1) to P0,
     // a multiple of 32 doubles, so that every 32-cell tile row is 256-byte aligned and the arrays can be described to TMA (global
     // strides must be multiples of 16 bytes).  They never cross the ABI; capacities, masks, states keep the reference pitch.
+    int fix_lo, fix_hi;          // local planes of the slab dimension whose tiles the fused kernel processes (kf_blocks -> Efix)
     long long ld0, dP;           // reference pitch, P0 - ld0
     long long sq[PB_MAXD];       // strides of the re-pitched layout (1, P0, P0 * ld1)
 };
@@ -402,10 +405,16 @@ __global__ void kf_blocks(Grid g, FoldDev fd)
 #pragma unroll
             for (int k = 0; k < 9; ++k) R[k] = 0.0;
         }
-        constexpr int NC = (1 + 2 * N) * 9;
-        double *__restrict__ eb = fd.Eblk + (size_t)e * NC;
+        double *__restrict__ eb = fd.Eblk + e;   // SoA: entry j of cell e at eb[j * nEp]
+        const size_t ES = (size_t)fd.nEp;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) eb[k] = R[k];
+        for (int k = 0; k < 9; ++k) eb[k * ES] = R[k];
+        // cells whose tile the fused kernel processes (interior class): local plane of the slab dimension in [fix_lo, fix_hi)
+        unsigned fixm = 0;
+        {
+            const int pl = (int)(l / g.plane);
+            if (pl >= fd.fix_lo && pl < fd.fix_hi) fixm |= 1u;
+        }
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             const long long s = g.stride[d];
@@ -431,14 +440,21 @@ __global__ void kf_blocks(Grid g, FoldDev fd)
                     tri_sandwich(Li, O, Lj, RU);
                 }
             }
-            fd.EnbrB[(size_t)e * (2 * N) + 2 * d] = nbL;
-            fd.EnbrB[(size_t)e * (2 * N) + 2 * d + 1] = nbU;
+            fd.EnbrB[(size_t)(2 * d) * ES + e] = nbL;
+            fd.EnbrB[(size_t)(2 * d + 1) * ES + e] = nbU;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                eb[(1 + 2 * d) * 9 + k] = RL[k];
-                eb[(2 + 2 * d) * 9 + k] = RU[k];
+                eb[((1 + 2 * d) * 9 + k) * ES] = RL[k];
+                eb[((2 + 2 * d) * 9 + k) * ES] = RU[k];
+            }
+            {
+                const int pl = (int)(l / g.plane);
+                const int plL = d == g.sd ? pl - 1 : pl, plU = d == g.sd ? pl + 1 : pl;
+                if (plL >= fd.fix_lo && plL < fd.fix_hi) fixm |= 1u << (1 + 2 * d);
+                if (plU >= fd.fix_lo && plU < fd.fix_hi) fixm |= 1u << (2 + 2 * d);
             }
         }
+        fd.Efix[e] = (unsigned char)fixm;
     }
 }
 
@@ -654,96 +670,115 @@ __global__ void __launch_bounds__(FCH, 4) kf_apply_dense(Grid g, FoldDev fd, Ite
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
 }
 
-// One WARP per band / fringe cell e: lanes 0..3(1+2N)-1 gather the 3 unknowns of the cell and of its 2N neighbours, every lane
-// multiplies its share of the (1+2N) 3x3 coefficient blocks (contiguous in memory: coalesced) and three shuffle reductions give the rows.
+// One THREAD per band / fringe cell e (consecutive threads on consecutive cells of the sorted list): the (1 + 2N) 3 x 3 coefficient blocks are
+// stored SoA ([entry][cell]: coalesced), the 3 unknowns of the cell and of its 2N neighbours are gathered by the thread itself -- up to
+// 9 (1 + 2N) + 3 (1 + 2N) independent loads in flight per thread instead of 2-4 per lane of the former warp-per-cell kernel (measured:
+// the band kernels were 30 % of a 3-D diphasic iteration, 4-6 x off their bandwidth).  Blocks between two non-band cells are zero by
+// construction (the dense stencil carries those couplings) and are skipped.
 // BAND_ONLY restricts the columns to band cells (the principal submatrix M^_BB) and adds the identity diagonal.
-// LPC lanes work on one cell: 16 in 1-D / 2-D (3 (1 + 2N) <= 15 gathered values), 32 in 3-D -- two cells per warp halve the number of
-// warps, so that the whole band is in flight in one wave.
-template <int N> struct BandLanes { static constexpr int LPC = (3 * (1 + 2 * N) <= 16) ? 16 : 32; };
-template <int N, bool BAND_ONLY>
-__device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int e, const FVec &x, int lane, double &a0, double &a1, double &a2, double &x0,
-                                          double &x1, double &xw, long long &l, int &bo)
+// dzadd (fused iteration): the bulk components of band cells are gathered as x + dz where Efix says so (see kf_apply_band).
+// LPC lanes share one cell (lane `sub` takes the blocks k = sub, sub + LPC, ...): 1 for large bands (3-D: every SM is busy with one thread per cell,
+// and a thread keeps up to 84 independent loads in flight), 8 for small ones (2-D: a few ten thousand cells -- shorter chains, 8 x the threads).
+template <int N, bool BAND_ONLY, int LPC>
+__device__ __forceinline__ void band_rows(const Grid &g, const FoldDev &fd, int e, const FVec &x, double &a0, double &a1, double &a2, double &x0,
+                                          double &x1, double &xw, long long &l, int &bo, int sub, const double *__restrict__ dzadd = nullptr)
 {
-    constexpr int NB = 1 + 2 * N, NC = NB * 9, NX = NB * 3, LPC = BandLanes<N>::LPC;
+    (void)g;
+    const size_t ES = (size_t)fd.nEp;
     l = fd.Ecell[e];
     bo = fd.EB[e];
-    double xv = 0.0;
-    if (lane < NX) {
-        const int k = lane / 3, c = lane - 3 * k;
-        long long ln = fd_q(fd, l);   // (index into the re-pitched Krylov vectors)
+    const long long lq = fd_q(fd, l);
+    const bool two = fd.nbulk > 1;
+    const unsigned fixm = dzadd != nullptr ? fd.Efix[e] : 0u;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    x0 = x1 = xw = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < 1 + 2 * N; k0 += LPC) {
+        const int k = k0 + sub;
+        if (LPC > 1 && k >= 1 + 2 * N) break;
+        long long ln = lq;
         int nb = bo;
         if (k > 0) {
             const int kk = k - 1, d = kk >> 1;
-            ln = (kk & 1) ? ln + fd.sq[d] : ln - fd.sq[d];
-            nb = fd.EnbrB[(size_t)e * (2 * N) + kk];
+            ln = (kk & 1) ? lq + fd.sq[d] : lq - fd.sq[d];
+            nb = fd.EnbrB[(size_t)kk * ES + e];
         }
         // BAND_ONLY: the preconditioner block is the band block of THIS rank (neighbours in the ghost planes are left out), so that
         // applying it needs no halo exchange; the operator itself (BAND_ONLY == false) couples across ranks as usual
         const bool use = !(BAND_ONLY && (nb < 0 || (k > 0 && (nb < fd.nBlo || nb >= fd.nBlo + fd.nBown))));
-        if (use) {
-            if (c == 0) xv = x.f[0][ln];
-            else if (c == 1) { if (fd.nbulk > 1) xv = x.f[1][ln]; }
-            else if (nb >= 0) xv = x.f[2][nb];
+        const bool nonzero = k == 0 ? bo >= 0 : (bo >= 0 || nb >= 0);     // (kf_blocks: other blocks are exactly zero)
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (use && (nonzero || k == 0)) {
+            v0 = x.f[0][ln];
+            if (two) v1 = x.f[1][ln];
+            if (nb >= 0) v2 = x.f[2][nb];
+            if (nb >= 0 && ((fixm >> k) & 1u)) { v0 += dzadd[nb]; if (two) v1 += dzadd[(size_t)fd.nB + nb]; }
+        }
+        if (k == 0) { x0 = v0; x1 = v1; xw = v2; }
+        if (use && nonzero) {
+            const double *__restrict__ c = fd.Eblk + (size_t)(k * 9) * ES + e;
+            r0 += c[0] * v0 + c[ES] * v1 + c[2 * ES] * v2;
+            r1 += c[3 * ES] * v0 + c[4 * ES] * v1 + c[5 * ES] * v2;
+            r2 += c[6 * ES] * v0 + c[7 * ES] * v1 + c[8 * ES] * v2;
         }
     }
-    x0 = __shfl_sync(0xffffffffu, xv, 0, LPC); x1 = __shfl_sync(0xffffffffu, xv, 1, LPC); xw = __shfl_sync(0xffffffffu, xv, 2, LPC);
-    const double *__restrict__ blk = fd.Eblk + (size_t)e * NC;
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    if (LPC > 1) {
 #pragma unroll
-    for (int jj = 0; jj < (NC + LPC - 1) / LPC; ++jj) {
-        const int j = jj * LPC + lane;
-        const bool in = j < NC;
-        const int jc = in ? j : 0;
-        const int k = jc / 9, rem = jc - 9 * k, r = rem / 3, c = rem - 3 * r;
-        const double xx = __shfl_sync(0xffffffffu, xv, k * 3 + c, LPC);
-        const double pr = in ? blk[jc] * xx : 0.0;
-        r0 += r == 0 ? pr : 0.0; r1 += r == 1 ? pr : 0.0; r2 += r == 2 ? pr : 0.0;
-    }
-#pragma unroll
-    for (int o = LPC / 2; o > 0; o >>= 1) {
-        r0 += __shfl_xor_sync(0xffffffffu, r0, o, LPC); r1 += __shfl_xor_sync(0xffffffffu, r1, o, LPC); r2 += __shfl_xor_sync(0xffffffffu, r2, o, LPC);
+        for (int o = LPC / 2; o > 0; o >>= 1) {
+            r0 += __shfl_xor_sync(0xffffffffu, r0, o, LPC); r1 += __shfl_xor_sync(0xffffffffu, r1, o, LPC); r2 += __shfl_xor_sync(0xffffffffu, r2, o, LPC);
+        }
+        x0 = __shfl_sync(0xffffffffu, x0, 0, LPC); x1 = __shfl_sync(0xffffffffu, x1, 0, LPC); xw = __shfl_sync(0xffffffffu, xw, 0, LPC);
     }
     a0 = r0; a1 = r1; a2 = r2;
     if (BAND_ONLY) { a0 += x0; a1 += x1; a2 += xw; }
 }
+// cell loop shared by the band kernels: groups of LPC lanes walk the cell list; groups past the end redo the last cell (the shuffles are warp-wide)
+#define BAND_LOOP(LPC_)                                                                              \
+    const int sub = (int)threadIdx.x % (LPC_), gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) / (LPC_)); \
+    const int ngroups = (int)(gridDim.x * blockDim.x / (LPC_));                                      \
+    const int rounds = fd.nE > 0 ? (fd.nE + ngroups - 1) / ngroups : 0;                              \
+    for (int rd = 0; rd < rounds; ++rd)                                                              \
+        if (const int e_raw = rd * ngroups + gid; true)                                              \
+            if (const bool live = e_raw < fd.nE; true)                                               \
+                if (const int e = live ? e_raw : fd.nE - 1; true)
 
-// band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here
-template <int N, int MODE>
+// band part (after the dense kernel): adds every coupling that involves a band cell; w rows are written here.
+// dzfix (MODE 1, fused iteration): x holds p' = r + beta p_old on the bulk unknowns of the band cells of the fused kernel's tiles; the correction dz
+// is added HERE -- to the gathered values and to y (the dense kernel wrote y = p' on band cells: their dense couplings are all zero); x itself is
+// corrected by kf_band_poly (other threads still gather p' here) -- so that the tile kernels need no band look-ups at all.
+template <int N, int MODE, int LPC>
 __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x, FVec y, FVec aux, double *partials, double *results, unsigned *counter,
-                                                     const double *res, StopCrit stop, PolyCoef pc)
+                                                     const double *res, StopCrit stop, PolyCoef pc, const double *__restrict__ dzfix = nullptr)
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[2] = {0.0, 0.0};
-    constexpr int LPC = BandLanes<N>::LPC;
-    const int lane = threadIdx.x & (LPC - 1), gpb = blockDim.x / LPC;   // groups of LPC lanes per block
     const bool two = fd.nbulk > 1;
-    // every group runs the same number of rounds (the shuffles inside band_rows are warp-wide); out-of-range groups redo the last cell
-    const int rounds = (fd.nE + gridDim.x * gpb - 1) / (gridDim.x * gpb);
-    for (int rd = 0; rd < rounds; ++rd) {
-        const int e_raw = (rd * gridDim.x + blockIdx.x) * gpb + (int)threadIdx.x / LPC;
-        const bool live = e_raw < fd.nE;
-        const int e = live ? e_raw : fd.nE - 1;
+    BAND_LOOP(LPC) {
         double a0, a1, a2, x0, x1, xw;
         long long l; int bo;
-        band_rows<N, false>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);
-        if (lane == 0 && live) {
-            const long long lq = fd_q(fd, l);
-            const double y0p = y.f[0][lq], y1p = two ? y.f[1][lq] : 0.0;
-            if (MODE == 4) { a0 *= pc.A; a1 *= pc.A; }   // the dense kernel has written pc.r aux + pc.z x + pc.A (dense part of M^ x)
-            y.f[0][lq] = y0p + a0;
-            if (two) y.f[1][lq] = y1p + a1;
-            double yw = 0.0;
-            if (bo >= 0) {
-                yw = xw + a2;
-                if (MODE == 4) yw = pc.r * aux.f[2][bo] + pc.z * xw + pc.A * yw;
-                y.f[2][bo] = yw;
-            }
-            if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
-            if (MODE == 2 || MODE == 4) v[0] += aux.f[0][lq] * a0 + (two ? aux.f[1][lq] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
-            if (MODE == 3) {
-                v[0] += x0 * a0 + x1 * a1 + xw * yw;
-                v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
-            }
+        band_rows<N, false, LPC>(g, fd, e, x, a0, a1, a2, x0, x1, xw, l, bo, sub, dzfix);
+        if (sub != 0 || !live) continue;
+        const long long lq = fd_q(fd, l);
+        const double y0p = y.f[0][lq], y1p = two ? y.f[1][lq] : 0.0;
+        if (MODE == 4) { a0 *= pc.A; a1 *= pc.A; }   // the dense kernel has written pc.r aux + pc.z x + pc.A (dense part of M^ x)
+        double d0 = 0.0, d1 = 0.0;
+        if (MODE == 1 && dzfix != nullptr && bo >= fd.nBlo && bo < fd.nBlo + fd.nBown && (fd.Efix[e] & 1u)) {   // band cell of a fused-kernel tile: y = p' -> p_k (+ couplings below)
+            d0 = dzfix[bo]; d1 = two ? dzfix[(size_t)fd.nB + bo] : 0.0;
+            v[0] += d0 * y0p + d1 * y1p + x0 * d0 + x1 * d1;
+        }
+        y.f[0][lq] = y0p + d0 + a0;
+        if (two) y.f[1][lq] = y1p + d1 + a1;
+        double yw = 0.0;
+        if (bo >= 0) {
+            yw = xw + a2;
+            if (MODE == 4) yw = pc.r * aux.f[2][bo] + pc.z * xw + pc.A * yw;
+            y.f[2][bo] = yw;
+        }
+        if (MODE == 1) v[0] += x0 * a0 + x1 * a1 + xw * yw;
+        if (MODE == 2 || MODE == 4) v[0] += aux.f[0][lq] * a0 + (two ? aux.f[1][lq] * a1 : 0.0) + (bo >= 0 ? aux.f[2][bo] * yw : 0.0);
+        if (MODE == 3) {
+            v[0] += x0 * a0 + x1 * a1 + xw * yw;
+            v[1] += (2.0 * y0p + a0) * a0 + (2.0 * y1p + a1) * a1 + yw * yw;
         }
     }
     if (MODE == 1 || MODE == 2 || MODE == 4) { double w[1] = {v[0]}; block_reduce_publish<1>(w, partials, results, counter); }
@@ -755,29 +790,30 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
 // unknowns are coupled across faces; tests/experiments/krylov_experiment3.py).  They are removed by a low-degree Chebyshev polynomial of the band
 // block M^_BB (all unknowns of the band cells) used as preconditioner on the band only: z = r outside the band, z_B = q(M^_BB) r_B.
 // out[c][bo] = ca x_c + cb (M^_BB x)_c for every OWNED band cell; publishes sum_c x_c out_c  (x read from an FVec)
-template <int N>
+// pfix (fused iteration): before `out` (= dz) is overwritten, the OLD correction is added to the bulk entries of pfix on the band cells of the fused
+// kernel's tiles (p_k = p' + dz, see kf_apply_band).
+template <int N, int LPC>
 __global__ void __launch_bounds__(256) kf_band_poly(Grid g, FoldDev fd, FVec x, double *out, double ca, double cb, double *partials, double *results,
-                                                    unsigned *counter, const double *res, StopCrit stop)
+                                                    unsigned *counter, const double *res, StopCrit stop, FVec pfix = FVec{{nullptr, nullptr, nullptr}})
 {
     if (stop.sl_rr >= 0 && fold_done(res, stop)) return;
     double v[1] = {0.0};
-    constexpr int LPC = BandLanes<N>::LPC;
-    const int lane = threadIdx.x & (LPC - 1), gpb = blockDim.x / LPC;
-    const int rounds = (fd.nE + gridDim.x * gpb - 1) / (gridDim.x * gpb);
-    for (int rd = 0; rd < rounds; ++rd) {
-        const int e_raw = (rd * gridDim.x + blockIdx.x) * gpb + (int)threadIdx.x / LPC;
-        const bool live = e_raw < fd.nE;
-        const int e = live ? e_raw : fd.nE - 1;
+    BAND_LOOP(LPC) {
+        if (LPC == 1 && fd.EB[e] < 0) continue;                // fringe cells carry no preconditioner row
         double a0, a1, a2, x0, x1, xw;
         long long l; int bo;
-        band_rows<N, true>(g, fd, e, x, lane, a0, a1, a2, x0, x1, xw, l, bo);   // fringe cells (bo < 0) are computed and dropped
-        if (lane == 0 && live && bo >= 0) {
-            const double o0 = ca * x0 + cb * a0, o1 = ca * x1 + cb * a1, o2 = ca * xw + cb * a2;
-            out[(size_t)0 * fd.nB + bo] = o0;
-            out[(size_t)1 * fd.nB + bo] = o1;
-            out[(size_t)2 * fd.nB + bo] = o2;
-            v[0] += x0 * o0 + x1 * o1 + xw * o2;
+        band_rows<N, true, LPC>(g, fd, e, x, a0, a1, a2, x0, x1, xw, l, bo, sub);
+        if (sub != 0 || !live || bo < 0) continue;
+        if (pfix.f[0] != nullptr && bo >= fd.nBlo && bo < fd.nBlo + fd.nBown && (fd.Efix[e] & 1u)) {
+            const long long lq = fd_q(fd, l);
+            pfix.f[0][lq] += out[(size_t)0 * fd.nB + bo];
+            if (fd.nbulk > 1) pfix.f[1][lq] += out[(size_t)1 * fd.nB + bo];
         }
+        const double o0 = ca * x0 + cb * a0, o1 = ca * x1 + cb * a1, o2 = ca * xw + cb * a2;
+        out[(size_t)0 * fd.nB + bo] = o0;
+        out[(size_t)1 * fd.nB + bo] = o1;
+        out[(size_t)2 * fd.nB + bo] = o2;
+        v[0] += x0 * o0 + x1 * o1 + xw * o2;
     }
     block_reduce_publish<1>(v, partials, results, counter);
 }
@@ -1131,6 +1167,7 @@ struct FoldSys {
     long long *Bcell = nullptr, *Ecell = nullptr;
     int *bord = nullptr, *EB = nullptr, *EnbrB = nullptr, *items = nullptr;
     double *Linv = nullptr, *Eblk = nullptr;
+    unsigned char *Efix = nullptr;
     int nitems = 0;
     unsigned char *uni = nullptr;
     double *ucoef = nullptr;
@@ -1176,6 +1213,7 @@ static void fold_free(FoldSys &F)
     if (F.Bcell) cudaFree(F.Bcell); if (F.Ecell) cudaFree(F.Ecell); if (F.bord) cudaFree(F.bord); if (F.EB) cudaFree(F.EB);
     if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
+    if (F.Efix) cudaFree(F.Efix); F.Efix = nullptr;
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
     for (void *m : F.list_mem) cudaFree(m);
     F.list_mem.clear();

@@ -73,6 +73,7 @@ struct F2Args {
     const double *res;
     int accumulate;                               // the published dot product is ADDED to the slot (a second launch of the same apply)
     int dbg;                                      // debugging switches (PB200_DBG_F3)
+    const double *off[2][PB_MAXD];                // coefficient arrays of the tiles without constants (reference pitch)
 };
 // debugging: record an out-of-range index (code = kernel * 100 + site) in res[28] and SKIP the access
 #define F2_BAD(A, code) (*(const_cast<double *>((A).res) + 28) = (double)(code))
@@ -337,7 +338,13 @@ __global__ void __launch_bounds__(FCH) kf2_xflush(Items I, const double *res, FV
 // General tiles (interface band, border ring, partial tiles) keep kf2_apply; they run beside this kernel on the second stream.
 // =================================================================================================================================
 struct alignas(64) F3Maps { CUtensorMap a[2], b[2], t[2]; };   // boxes of the staged vector and of p_{k-1}; tile (no halo) of x (MODE 5) / aux (MODE 2, 4)
-struct F3Hdr { long long baseq; double cx, cy, cz; int f; int pad; };
+struct F3Hdr {
+    long long baseq, base;            // tile origin in the re-pitched Krylov vectors / in the reference-pitch arrays (coefficients, band map)
+    double cx, cy, cz;                // the tile's constants (flags & 1)
+    int f, flags;                     // field; bit 0 constant coefficients, bit 1 holds band cells, bit 2 every cell valid
+    int ox, oy, oz;
+    short nx; signed char ylo, yhi, zlo, zhi;
+};
 template <int N> struct F3Tile { static constexpr int BYTES = FTILE * 8; };
 
 __device__ __forceinline__ void f3_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -379,7 +386,9 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
                 const int s = n % S, k = n / S;
                 if (k > 0) f2_mbar_wait(eb + 8 * s, (uint32_t)((k - 1) & 1));      // the consumers have released the stage's previous tile
                 F3Hdr h;
-                h.baseq = R.baseq; h.cx = c0; h.cy = c1; h.cz = c2; h.f = R.f; h.pad = 0;
+                h.baseq = R.baseq; h.base = R.base; h.cx = c0; h.cy = c1; h.cz = c2; h.f = R.f;
+                h.flags = (int)I.uni[it] | (R.full ? 4 : 0);
+                h.ox = R.ox; h.oy = R.oy; h.oz = R.oz; h.nx = R.nx; h.ylo = R.ylo; h.yhi = R.yhi; h.zlo = R.zlo; h.zhi = R.zhi;
                 hdr[s] = h;
                 const uint32_t dst = sm0 + s * STAGE, bar = fb + 8 * s;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -426,6 +435,64 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
             const int b0 = (lane + B::HX) + (ty * TYM + 1) * SY + (N == 3 ? SZ : 0);   // box index of the thread's cell k = 0
             const int t0 = lane + (ty * TYM) * 32;                                    // tile index of it (2-D: rows; 3-D: plane k adds 256)
             constexpr int TK = N == 2 ? 32 : 256;
+            if ((h.flags & 7) != 5) {
+                // ---- general tile: streamed coefficients and / or partial validity and / or band cells -----------------------------------
+                const int f = h.f;
+                // (band cells: p = r + beta p_old is formed WITHOUT the band correction dz here; kf_apply_band adds it -- their dense couplings are zero)
+                const bool uni = (h.flags & 1) != 0;
+                const double *__restrict__ of0 = f == 0 ? A.off[0][0] : A.off[1][0];
+                const double *__restrict__ of1 = f == 0 ? A.off[0][1] : A.off[1][1];
+                const double *__restrict__ of2 = f == 0 ? A.off[0][N > 2 ? 2 : 0] : A.off[1][N > 2 ? 2 : 0];
+                const long long l0 = h.base + lane + (long long)(ty * TYM) * I.ld0, q0g = h.baseq + lane + (long long)(ty * TYM) * I.P0;
+                const long long st1 = I.ld0, st2 = I.ld0 * I.ld1;
+                bool ok[FU];
+                double cm[FU][N], cp[FU][N];
+#pragma unroll
+                for (int k = 0; k < FU; ++k) {
+                    const int yr = ty * TYM + (N == 2 ? k : 0), zr = N == 3 ? k : 0;
+                    ok[k] = lane < h.nx && yr >= h.ylo && yr < h.yhi && zr >= h.zlo && zr < h.zhi;
+                    const long long l = l0 + (long long)k * I.ustride;
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        const double *__restrict__ of = d == 0 ? of0 : (d == 1 ? of1 : of2);
+                        const long long sd = d == 0 ? 1 : (d == 1 ? st1 : st2);
+                        const double cu = d == 0 ? h.cx : (d == 1 ? h.cy : h.cz);
+                        cm[k][d] = !ok[k] ? 0.0 : (uni ? cu : of[l]);
+                        cp[k][d] = !ok[k] ? 0.0 : (uni ? cu : of[l + sd]);
+                    }
+                }
+#define F3_AT(j) (MODE == 5 ? sA[(j)] + beta * sB[(j)] : sA[(j)])
+                double *__restrict__ yf = f == 0 ? A.y.f[0] : A.y.f[1];
+#pragma unroll
+                for (int k = 0; k < FU; ++k) {
+                    const int b = b0 + k * SK;
+                    const double c = F3_AT(b);
+                    double a = c + cm[k][0] * F3_AT(b - 1) + cp[k][0] * F3_AT(b + 1) + cm[k][1] * F3_AT(b - SY) + cp[k][1] * F3_AT(b + SY);
+                    if (N == 3) a += cm[k][N - 1] * F3_AT(b - SZ) + cp[k][N - 1] * F3_AT(b + SZ);
+                    if (ok[k]) {
+                        const long long q = q0g + (long long)k * I.ustrideq;
+                        if (MODE == 5) {
+                            double *__restrict__ pn = f == 0 ? A.pnew.f[0] : A.pnew.f[1];
+                            double *__restrict__ xf = f == 0 ? A.xs.f[0] : A.xs.f[1];
+                            yf[q] = a;
+                            pn[q] = c;
+                            xf[q] = sT[t0 + k * TK] + alpha * sB[b];
+                            v[0] += c * a;
+                        } else {
+                            const double av = (MODE == 2 || MODE == 4) ? (use_t ? sT[t0 + k * TK] : c) : 0.0;
+                            if (MODE == 4) a = A.pc.r * av + A.pc.z * c + A.pc.A * a;
+                            yf[q] = a;
+                            if (MODE == 1) v[0] += c * a;
+                            if (MODE == 2 || MODE == 4) v[0] += av * a;
+                            if (MODE == 3) { v[0] += a * c; v[1] += a * a; }
+                        }
+                    }
+                }
+#undef F3_AT
+                __syncwarp();
+                if (lane == 0) f3_mbar_arrive(eb + 8 * s);
+                continue;
+            }
             // the staged vector on the thread's column (k = -1 .. FU) and on the neighbours of its FU cells
 #define F3_AT(j) (MODE == 5 ? sA[(j)] + beta * sB[(j)] : sA[(j)])
             double col[FU + 2];

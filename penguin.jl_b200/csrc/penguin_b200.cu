@@ -19,6 +19,10 @@
         else { constexpr int N = 3; __VA_ARGS__; } \
     } while (0)
 
+// band kernels: lanes per cell chosen by the size of the band (fold.cuh: band_rows)
+#define BAND_POLY_LAUNCH(...) (band_lpc(F.d.nE) == 8 ? kf_band_poly<N, 8><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__) : kf_band_poly<N, 1><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__))
+#define BAND_APPLY_LAUNCH(M_, ...) (band_lpc(F.d.nE) == 8 ? kf_apply_band<N, M_, 8><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__) : kf_apply_band<N, M_, 1><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__))
+
 // =================================================================================================================
 // lifecycle
 // =================================================================================================================
@@ -716,6 +720,7 @@ static int fold_compact(pb200_ctx *ctx, Launch launch, long long **list, int *n)
 
 static inline int band_grid(int n);
 static inline int band_wgrid(int n);
+static inline int band_lpc(int n);
 // extreme eigenvalues of the band block M^_BB by power iteration (set-up, O(band) work) -> coefficients of the band preconditioner
 static int fold_band_spectrum(pb200_solver *s)
 {
@@ -739,7 +744,7 @@ static int fold_band_spectrum(pb200_solver *s)
         double rq = 0.0;
         for (int it = 0; it < iters; ++it) {
             // ||x||^2 via (x, 1 x + 0 A x)
-            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 256, 0, ctx->stream>>>(g, d, F.v, F.dz, 1.0, 0.0, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
+            DISPATCH_N(g.N, (BAND_POLY_LAUNCH(g, d, F.v, F.dz, 1.0, 0.0, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
             LAUNCH_CHECK(ctx);
             if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
             if ((rc = fetch_results(ctx, SL_TMP, 1, h))) return rc;
@@ -747,7 +752,7 @@ static int fold_band_spectrum(pb200_solver *s)
             if (!(nrm2 > 0.0)) { *lam = 0.0; return PB200_OK; }
             kf_band_put<<<gB, 128, 0, ctx->stream>>>(d, F.v, F.dz, 1.0 / sqrt(nrm2), 0, res, none); LAUNCH_CHECK(ctx);
             // y = (shift + sign A) x ; Rayleigh quotient (x, y)
-            DISPATCH_N(g.N, (kf_band_poly<N><<<gb, 256, 0, ctx->stream>>>(g, d, F.v, F.dz, shift, sign, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
+            DISPATCH_N(g.N, (BAND_POLY_LAUNCH(g, d, F.v, F.dz, shift, sign, ctx->d_partials, res + SL_TMP, ctx->d_counter, res, none)));
             LAUNCH_CHECK(ctx);
             if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
             if ((rc = fetch_results(ctx, SL_TMP, 1, h))) return rc;
@@ -868,11 +873,19 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         else if (g.N == 2) { if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { kf_mark_E<2><<<gown, RED_THREADS, 0, st>>>(gg, bord, list, cnt, cap); }, &F.Ecell, &d.nE))) return rc; }
         else { if ((rc = fold_compact(ctx, [&](long long *list, int *cnt, int cap) { kf_mark_E<3><<<gown, RED_THREADS, 0, st>>>(gg, bord, list, cnt, cap); }, &F.Ecell, &d.nE))) return rc; }
         d.Ecell = F.Ecell;
-        const size_t nE = d.nE > 0 ? d.nE : 1;
+        d.nEp = (d.nE + 31) / 32 * 32;
+        const size_t nE = d.nEp > 0 ? d.nEp : 32;
         CUDA_TRY(ctx, cudaMalloc((void **)&F.EB, sizeof(int) * nE));
         CUDA_TRY(ctx, cudaMalloc((void **)&F.EnbrB, sizeof(int) * 2 * g.N * nE));
         CUDA_TRY(ctx, cudaMalloc((void **)&F.Eblk, sizeof(double) * (1 + 2 * g.N) * 9 * nE));
-        d.EB = F.EB; d.EnbrB = F.EnbrB; d.Eblk = F.Eblk;
+        CUDA_TRY(ctx, cudaMalloc((void **)&F.Efix, nE));
+        d.EB = F.EB; d.EnbrB = F.EnbrB; d.Eblk = F.Eblk; d.Efix = F.Efix;
+        if (d.nEp == 0) d.nEp = 32;
+        {   // local planes of the slab dimension whose tiles are interior class (fused kernel): see kf_tile_records (ghost flag)
+            const int Tsd = g.N == 1 ? FTILE : (g.N == 2 ? 32 : 4);
+            d.fix_lo = ctx->rank > 0 ? Tsd : 0;
+            d.fix_hi = ctx->rank < ctx->nranks - 1 ? ((g.lz - 2) / Tsd) * Tsd : g.lz;
+        }
     }
     DISPATCH_N(g.N, (kf_off<N><<<gown, RED_THREADS, 0, ctx->stream>>>(g, d)));
     LAUNCH_CHECK(ctx);
@@ -1068,7 +1081,9 @@ static inline int wave_grid(pb200_solver *s, K kernel)
 static inline int band_grid(int n) { int b = (n + 127) / 128; if (b > RED_MAXBLOCKS) b = RED_MAXBLOCKS; if (b < 1) b = 1; return b; }
 // kernels that put one warp on one band cell: 1024-thread blocks, so that every cell is in flight at once while the number of
 // blocks (= serialised ticket atomics and partial sums of the fused reduction) stays small
-static inline int band_wgrid(int n) { int b = (n + 15) / 16; if (b > 2048) b = 2048; if (b < 1) b = 1; return b; }   // >= 8 cells per 256-thread block
+// one thread per band / fringe cell; small bands (2-D) use 64-thread blocks so that their few thousand cells still spread over every SM
+static inline int band_lpc(int n) { return n < 148 * 512 ? 8 : 1; }
+static inline int band_wgrid(int n) { const long long t = (long long)n * band_lpc(n); long long b = (t + 255) / 256; if (b > 2048) b = 2048; if (b < 1) b = 1; return (int)b; }
 
 // ghost planes of the bulk fields and ghost entries of the compact w of one Krylov vector, ONE NCCL group (one launch)
 static int fold_halo(pb200_solver *s, const FVec &x, cudaStream_t st = nullptr)
@@ -1295,9 +1310,8 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
             const int has_t = (mode == 2 || mode == 4) && aux.f[0] != x.f[0];
             F3Maps m3;
             if ((rc = fold_maps3(s, x, nullptr, has_t ? &aux : nullptr, &m3))) return rc;
-            if ((rc = fold3_apply(s, F.IFall, m3, A, mode, has_t, ctx->stream))) return rc;
-            A.accumulate = 1;
-            if ((rc = fold2_apply(s, F.IGall, maps, A, mode, ctx->stream))) return rc;
+            for (int p = 0; p < 2; ++p) for (int dd = 0; dd < PB_MAXD; ++dd) A.off[p][dd] = F.d.off[p][dd];
+            if ((rc = fold3_apply(s, F.IA, m3, A, mode, has_t, ctx->stream))) return rc;
         } else if ((rc = fold2_apply(s, F.IA, maps, A, mode, ctx->stream))) return rc;
     } else {
 #define FOLD_DENSE(M_) DISPATCH_N(g.N, (kf_apply_dense<N, M_><<<wave_grid(s, kf_apply_dense<N, M_>), FCH, 0, ctx->stream>>>(g, F.d, F.IA, x, y, aux, ctx->d_partials, slotD, ctx->d_counter, res, stop, pc)))
@@ -1310,7 +1324,7 @@ static int fold_apply(pb200_solver *s, const FVec &x, const FVec &y, const FVec 
         prof_mark(ctx, PB_PROF_BAPPLY);
         struct Mark { pb200_ctx *c; ~Mark() { prof_mark(c, PB_PROF_BAPPLY); } } mark_{ctx};
         const int gb = band_wgrid(F.d.nE);
-#define FOLD_BAND(M_) DISPATCH_N(g.N, (kf_apply_band<N, M_><<<gb, 256, 0, ctx->stream>>>(g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop, pc)))
+#define FOLD_BAND(M_) DISPATCH_N(g.N, (BAND_APPLY_LAUNCH(M_, g, F.d, x, y, aux, ctx->d_partials, slotB, ctx->d_counter, res, stop, pc)))
         if (mode == 0) FOLD_BAND(0); else if (mode == 1) FOLD_BAND(1); else if (mode == 2) FOLD_BAND(2); else if (mode == 3) FOLD_BAND(3); else FOLD_BAND(4);
 #undef FOLD_BAND
         LAUNCH_CHECK(ctx);
@@ -1483,7 +1497,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         if (poly && (rc = fold_poly(s, F.r, fused ? F.zz : F.p, FS_PAIR0, nostop))) return rc;   // p0 = q(M^) r0 (kf_resid had set p0 = r0; fused: z0, p0 is formed by the first apply)
         if (cg) {
             if (prec) {   // p0 = z0 = r0 + (q(M^_BB) - 1) r0_B ; rho0 = (r0, z0)
-                DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
+                DISPATCH_N(s->g.N, (BAND_POLY_LAUNCH(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_PAIR0 + 2, ctx->d_counter, res, nostop)));
                 LAUNCH_CHECK(ctx);
                 if ((rc = allreduce_results(ctx, FS_PAIR0 + 2, 1))) return rc;
                 if (!fused) { kf_band_put<<<gb, 128, 0, ctx->stream>>>(F.d, F.p, F.dz, 1.0, 1, res, nostop); LAUNCH_CHECK(ctx); }
@@ -1510,6 +1524,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 A.sl_old = FS_TRIPLE(nxt); A.sl_cur = FS_TRIPLE(curp); A.stop = st; A.res = res;
                 A.partials = ctx->d_partials; A.counter = ctx->d_counter; A.results = res + FS_SIG_D;
                 A.dbg = getenv("PB200_DBG_F3") ? atoi(getenv("PB200_DBG_F3")) : 0;
+                for (int pp = 0; pp < 2; ++pp) for (int dd = 0; dd < PB_MAXD; ++dd) A.off[pp][dd] = F.d.off[pp][dd];
                 if (side) {
                     if (st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
                     if (F.IG1.n > 0) {   // ghost-class tiles and the compact interface unknowns: p_k and x pointwise
@@ -1523,34 +1538,28 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 F2Maps mi;
                 if ((rc2 = fold_maps(s, zsrc, &pold, &mi))) return rc2;
                 const bool split = F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED");     // interior class: pipelined kernel on the constant-coefficient tiles + general kernel on the rest (beside it)
-                if (split) {
-                    if (!side && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
-                    F2Args Gn = A;
-                    Gn.partials = ctx->d_partials2; Gn.counter = ctx->d_counter2; Gn.results = res + FS_SIG_G;
-                    if (getenv("PB200_DBG_ONESLOT")) { Gn.partials = ctx->d_partials; Gn.counter = ctx->d_counter; Gn.results = res + FS_SIG_D; A.accumulate = 1; }
-                    prof_mark(ctx, PB_PROF_APPLY);
-                    if ((rc2 = fold2_apply(s, F.IAgen, mi, Gn, 5, st2))) return rc2;
-                    prof_mark(ctx, PB_PROF_APPLY);
-                }
                 prof_mark(ctx, PB_PROF_APPLY);
                 ctx->apply_launches++;
-                if (split) {
+                if (split) {   // one pipelined launch: constant-coefficient interior tiles and general tiles alike
                     F3Maps m3;
                     if ((rc2 = fold_maps3(s, zsrc, &pold, &F.x, &m3))) return rc2;
-                    if (getenv("PB200_DBG_SPLIT2")) { if ((rc2 = fold2_apply(s, F.IAf, mi, A, 5, ctx->stream))) return rc2; }
-                    else if ((rc2 = fold3_apply(s, F.IAf, m3, A, 5, 1, ctx->stream))) return rc2;
+                    if ((rc2 = fold3_apply(s, multi ? F.IAi_all : F.IA, m3, A, 5, 1, ctx->stream))) return rc2;
                 } else if ((rc2 = fold2_apply(s, multi ? F.IAi_all : F.IA, mi, A, 5, ctx->stream))) return rc2;
                 prof_mark(ctx, PB_PROF_APPLY);
-                if ((side || split) && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+                if (side && st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
                 if (multi) {
                     // ghost-class tiles: plain staged apply of p_k.  After the join: their boxes also read p_k cells of interior-class tiles,
                     // which the fused kernels have only now finished writing.
                     F2Maps mg;
                     if ((rc2 = fold_maps(s, pnew, nullptr, &mg))) return rc2;
                     F2Args G = A;
-                    G.a = pnew; G.results = res + FS_SIG_G; G.accumulate = split ? 1 : 0;
+                    G.a = pnew; G.results = res + FS_SIG_G;
                     prof_mark(ctx, PB_PROF_APPLY);
-                    if ((rc2 = fold2_apply(s, F.IAg, mg, G, 1, ctx->stream))) return rc2;
+                    if (split) {
+                        F3Maps m3g;
+                        if ((rc2 = fold_maps3(s, pnew, nullptr, nullptr, &m3g))) return rc2;
+                        if ((rc2 = fold3_apply(s, F.IAg, m3g, G, 1, 0, ctx->stream))) return rc2;
+                    } else if ((rc2 = fold2_apply(s, F.IAg, mg, G, 1, ctx->stream))) return rc2;
                     prof_mark(ctx, PB_PROF_APPLY);
                 }
                 if (getenv("PB200_DBG_CHECK") && !multi) {
@@ -1581,7 +1590,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 }
                 if (F.d.has_w) {     // band part of v = M^ p_k (needs p_k everywhere)
                     prof_mark(ctx, PB_PROF_BAPPLY);
-                    DISPATCH_N(s->g.N, (kf_apply_band<N, 1><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(s->g, F.d, pnew, F.v, F.v, ctx->d_partials, res + FS_SIG_B, ctx->d_counter, res, st, PolyCoef{0.0, 0.0, 0.0})));
+                    DISPATCH_N(s->g.N, (BAND_APPLY_LAUNCH(1, s->g, F.d, pnew, F.v, F.v, ctx->d_partials, res + FS_SIG_B, ctx->d_counter, res, st, PolyCoef{0.0, 0.0, 0.0},
+                                                                                                          (split && prec) ? F.dz : nullptr)));
                     LAUNCH_CHECK(ctx);
                     prof_mark(ctx, PB_PROF_BAPPLY);
                 }
@@ -1593,7 +1603,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 2))) return rc2;
                 if (prec) {
                     prof_mark(ctx, PB_PROF_BPREC);
-                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
+                    DISPATCH_N(s->g.N, (BAND_POLY_LAUNCH(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st,
+                                                                                   split ? pnew : FVec{{nullptr, nullptr, nullptr}})));
                     LAUNCH_CHECK(ctx);
                     prof_mark(ctx, PB_PROF_BPREC);
                     if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 3))) return rc2;
@@ -1611,7 +1622,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 if (!prec && (rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 2))) return rc2;
                 if (prec) {   // z += (q(M^_BB) - 1) r_B on the band: rho_new += (r_B, dz_B)
                     prof_mark(ctx, PB_PROF_BPREC);
-                    DISPATCH_N(s->g.N, (kf_band_poly<N><<<gE, 256, 0, ctx->stream>>>(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
+                    DISPATCH_N(s->g.N, (BAND_POLY_LAUNCH(s->g, F.d, F.r, F.dz, F.pa0 - 1.0, F.pa1, ctx->d_partials, res + FS_TRIPLE(nxt) + 2, ctx->d_counter, res, st)));
                     LAUNCH_CHECK(ctx);
                     prof_mark(ctx, PB_PROF_BPREC);
                     if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), poly ? FS_NGROUP : 3))) return rc2;
