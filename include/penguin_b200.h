@@ -206,6 +206,8 @@ typedef struct {
     /* cells of the tiles that take the apply kernel's staged interior branch (every cell valid AND constant coefficients) -- the parity
      * tests assert this is > 0 so that the branch the benchmark runs is the branch they compare with the oracle */
     int64_t apply_cells_fast;
+    /* interface band of this rank: band cells (cells with an active interface unknown) and rows of the band kernels (band + fringe cells) */
+    int64_t band_cells, band_rows;
 } pb200_step_stats;
 
 /* one solve: builds b from the device-resident state (b_*_unstead_diff / b_*_stead_diff), applies the border

@@ -37,7 +37,7 @@ class StepStats(C.Structure):
                 ("solve_ms", C.c_double), ("setup_ms", C.c_double), ("dof_bulk", C.c_int64), ("dof_ifc", C.c_int64),
                 ("launches", C.c_int64), ("apply_ms", C.c_double), ("apply_launches", C.c_int64),
                 ("apply_cells_uniform", C.c_int64), ("apply_cells_general", C.c_int64),
-                ("kernel_ms", C.c_double * 8), ("kernel_launches", C.c_int64 * 8), ("apply_cells_fast", C.c_int64)]
+                ("kernel_ms", C.c_double * 8), ("kernel_launches", C.c_int64 * 8), ("apply_cells_fast", C.c_int64), ("band_cells", C.c_int64), ("band_rows", C.c_int64)]
 
 
 # every symbol include/penguin_b200.h declares (tests/test_abi.py checks the .so exports them all)

@@ -378,6 +378,7 @@ struct pb200_solver {
     double *bvals[6] = {};
     bool masks_dirty = true;
     bool values_dirty = false;           // border values changed, kinds did not: refresh ufix only
+    bool have_generic = false;           // Krylov vectors of the generic path allocated
     unsigned char *m1 = nullptr, *m2 = nullptr;
     double *ufix1 = nullptr, *ufix2 = nullptr;
     double *Tw[2] = {}, *Tg[2] = {};
@@ -456,7 +457,8 @@ extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, p
     for (int ph = 0; ph < (diph ? 2 : 1); ++ph)
         if ((rc = dev_alloc(ctx, &s->Tw[ph], g.nloc)) || (rc = dev_alloc(ctx, &s->Tg[ph], g.nloc))) return rc;
     if ((rc = dev_alloc(ctx, &s->gK, g.nloc))) return rc;
-    MVec *vs[] = {&s->x, &s->b, &s->r, &s->r0, &s->p, &s->ph, &s->v, &s->s, &s->sh, &s->t, &s->dinv};
+    // x, b: both solve paths.  The Krylov vectors of the generic path (9 more: 30 GB at 512^3 diphasic) are allocated when that path first runs.
+    MVec *vs[] = {&s->x, &s->b};
     for (MVec *v : vs) if ((rc = solver_vec(s, v))) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
@@ -1936,6 +1938,11 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
             k_guess<<<grid, RED_THREADS, 0, ctx->stream>>>(g, guess_spec(s->Tg[1], s->histG[1]), s->m2, MB_IFREE, s->x.f[2]); LAUNCH_CHECK(ctx);
         }
     }
+    if (!use_fold && !s->have_generic) {
+        MVec *vs[] = {&s->r, &s->r0, &s->p, &s->ph, &s->v, &s->s, &s->sh, &s->t, &s->dinv};
+        for (MVec *v : vs) if ((rc = solver_vec(s, v))) return rc;
+        s->have_generic = true;
+    }
     if (use_fold) {
     } else if (memcmp(&ac, &s->diag_key, sizeof(ac)) != 0) {   // Jacobi diagonal (cached per coefficient set)
         if (!diph) {
@@ -2077,6 +2084,8 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
         stats->apply_cells_uniform = use_fold ? s->F.cells_uniform : 0;
         stats->apply_cells_general = use_fold ? s->F.cells_general : 0;
         stats->apply_cells_fast = use_fold ? s->F.cells_fast : 0;
+        stats->band_cells = use_fold ? s->F.d.nBown : 0;
+        stats->band_rows = use_fold ? s->F.d.nE : 0;
     }
     if (!converged) return set_err(ctx, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
     return PB200_OK;

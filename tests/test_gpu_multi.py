@@ -18,3 +18,29 @@ def test_two_rank_parity():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_PARITY_OK" in out.stdout
+
+
+def _torchrun(n, script, args, env=None, port="29521", timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", port, os.path.join(ROOT, "tests", script)] + args
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e)
+
+
+@pytest.mark.parametrize("nccl_only", [False, True])
+def test_ranks_agree_with_one_gpu(tmp_path, nccl_only):
+    """2 (and 4, when present) ranks vs the same problems on ONE GPU: interior + ghost-class tiles, fused iteration with the halo exchange on the
+    second stream, ghost planes of 17.7 k doubles (multi-block peer-memory halo kernel); with the peer-memory exchange and with NCCL only."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs 2 GPUs")
+    ref = str(tmp_path / "ref.npz")
+    cases = "diph3d" if nccl_only else "diph3d,mono3d,diph2d"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "multi_gpu_variants.py"), "--single", ref, "--cases", cases], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "SINGLE_GPU_REFERENCE_WRITTEN" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    for n in ([2, 4] if ng >= 4 and not nccl_only else [2]):
+        out = _torchrun(n, "multi_gpu_variants.py", ["--ref", ref, "--cases", cases], env={"PB200_NO_P2P": "1"} if nccl_only else None)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+        assert "MULTI_GPU_VARIANTS_OK" in out.stdout
