@@ -365,9 +365,21 @@ def run_gpu(args):
     # Spin-up: a fresh box idles at low clocks and the first launches build the folded system and capture the CUDA graphs.  Run the
     # workload untimed for ~0.75 s, then RESET the state to the initial condition so that the W warm-up steps and the K timed steps are
     # steps 1..W and W+1..W+K of the run, exactly as without spin-up (later steps of the transient need fewer Krylov iterations).
+    # (seen once on a fresh box: the first process ran its first ~100 ms of steps 4x slower than every later one -- host side still paging in --
+    # so the spin-up also waits until blocks of 25 steps have stopped getting faster, for at most 4 s)
     t_spin = time.perf_counter()
-    while allmax(time.perf_counter() - t_spin) < args.spinup:     # a COLLECTIVE decision: every rank runs the same number of steps
-        step()
+    best, settled = None, 0
+    while True:
+        tb = time.perf_counter()
+        for _ in range(25):
+            step()
+        ctx.sync()
+        blk = time.perf_counter() - tb
+        settled = settled + 1 if (best is not None and blk <= 1.1 * best) else 0
+        best = blk if best is None else min(best, blk)
+        el = time.perf_counter() - t_spin
+        if allmax(0.0 if (el >= args.spinup and settled >= 3) or el >= 4.0 else 1.0) == 0.0:     # a COLLECTIVE decision: every rank runs the same number of steps
+            break
     ctx.sync()
     L.check(lib.pb200_solver_set_state(s._h, u0.ctypes.data_as(L.dp)), ctx.h)
     for _ in range(args.warmup):

@@ -1517,7 +1517,9 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 const bool multi = ctx->nranks > 1;
                 const FVec &pold = curp ? F.p2 : F.p, &pnew = curp ? F.p : F.p2;    // iteration j reads P[j & 1], writes P[(j + 1) & 1]
                 const FVec &zsrc = poly ? F.zz : F.r;
-                cudaStream_t st2 = (ctx->profile || getenv("PB200_DBG_SERIAL")) ? ctx->stream : ctx->stream2;   // (per-launch event timing: everything in one stream)
+                // The second stream exists to overlap the HALO EXCHANGE with the interior tiles.  On one rank the side work is the pointwise update of
+                // the interface unknowns only, and running it beside the staged kernel cost more than it hid (512^3 diphasic: 85 vs 65 ms per step).
+                cudaStream_t st2 = (ctx->profile || !multi || getenv("PB200_DBG_SERIAL")) && !getenv("PB200_DBG_FORK") ? ctx->stream : ctx->stream2;
                 const bool side = F.IG1.n > 0 || multi;
                 F2Args A;
                 memset(&A, 0, sizeof(A));
@@ -1666,6 +1668,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 auto gi = F.graphs.find(chunk);
                 if (gi == F.graphs.end()) {
                     cudaGraph_t gr = nullptr;
+                    if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] capturing a graph of %d iterations (%zu cached)\n", chunk, F.graphs.size());
                     const int64_t l0 = ctx->launches, a0 = ctx->apply_launches;
                     CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
                     int rcc = PB200_OK;
