@@ -43,6 +43,11 @@ int pb200_init(pb200_ctx **ctx, int device);
 /* one process per GPU; `nccl_id` = 128 bytes from pb200_nccl_unique_id() of rank 0, broadcast by the host. */
 int pb200_nccl_unique_id(char id[128]);
 int pb200_init_dist(pb200_ctx **ctx, int device, int rank, int nranks, const char nccl_id[128]);
+/* ONE process driving ndev GPUs of one box (the reference's scripts are single-process Julia): the returned handle stands for the whole team.
+ * Every call below then takes and returns per-cell host arrays of the reference's GLOBAL padded length -- the library cuts them into slabs of the
+ * slowest dimension, runs one host thread per GPU (NCCL / peer-memory exchanges between them) and reassembles the results.  An unchanged
+ * single-process script reaches N > 1 GPUs by calling this instead of pb200_init.  (pb200_solver_get_state_async is synchronous on a team handle.) */
+int pb200_init_multi(pb200_ctx **ctx, const int *devices, int ndev);
 int pb200_finalize(pb200_ctx *ctx);
 const char *pb200_last_error(pb200_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
 int pb200_sync(pb200_ctx *ctx);

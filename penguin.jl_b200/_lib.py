@@ -45,6 +45,7 @@ SYMBOLS = {
     "pb200_init": ([C.POINTER(C.c_void_p), C.c_int], C.c_int),
     "pb200_nccl_unique_id": ([C.c_char_p], C.c_int),
     "pb200_init_dist": ([C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_char_p], C.c_int),
+    "pb200_init_multi": ([C.POINTER(C.c_void_p), ip, C.c_int], C.c_int),
     "pb200_finalize": ([C.c_void_p], C.c_int),
     "pb200_last_error": ([C.c_void_p], C.c_char_p),
     "pb200_sync": ([C.c_void_p], C.c_int),

@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib as L
 
 __all__ = [
-    "init", "init_distributed", "finalize", "context", "Mesh", "Circle", "Sphere", "Interval", "Balls", "HalfSpace", "Capacity",
+    "init", "init_distributed", "init_multi", "finalize", "context", "Mesh", "Circle", "Sphere", "Interval", "Balls", "HalfSpace", "Capacity",
     "DiffusionOps", "grad", "div", "Phase", "Dirichlet", "Neumann", "Robin", "Periodic", "ScalarJump", "FluxJump",
     "BorderConditions", "InterfaceConditions", "Solver", "DiffusionSteadyMono", "solve_DiffusionSteadyMono_",
     "DiffusionSteadyDiph", "solve_DiffusionSteadyDiph_", "DiffusionUnsteadyMono", "solve_DiffusionUnsteadyMono_",
@@ -83,6 +83,18 @@ def init_distributed(rank, nranks, device, bcast):
     h = C.c_void_p()
     L.check(L.lib().pb200_init_dist(C.byref(h), int(device), int(rank), int(nranks), ident))
     _ctx = _Context(h, rank, nranks)
+    return _ctx
+
+
+def init_multi(devices):
+    """pb200_init_multi: ONE process driving several GPUs.  Every per-cell array keeps the GLOBAL padded length; the library cuts the slabs."""
+    global _ctx
+    if _ctx is not None:
+        raise RuntimeError("context already initialised")
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    h = C.c_void_p()
+    L.check(L.lib().pb200_init_multi(C.byref(h), C.cast(dev, L.ip), len(devices)))
+    _ctx = _Context(h)
     return _ctx
 
 

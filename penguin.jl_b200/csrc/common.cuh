@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/penguin_b200.h"
@@ -41,6 +42,10 @@ struct pb200_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double *d_partials2 = nullptr;
     unsigned *d_counter2 = nullptr;
+    // one PROCESS driving several GPUs (pb200_init_multi): the team handle (is_team) fans every call out to its member contexts, one host thread
+    // per GPU; members know their team so that the peer-memory exchange maps the mailboxes directly (CUDA IPC does not work inside one process)
+    struct Team *team = nullptr;
+    bool is_team = false;
     // peer-memory exchange (p2p.cuh): every rank's mailbox is mapped into every other rank with CUDA IPC; halos and the Krylov
     // scalar reductions are then plain kernels that store into the peers' mailboxes over NVLink and spin on sequence flags
     struct P2PState *p2p = nullptr;

@@ -161,11 +161,17 @@ __global__ void k_p2p_allreduce(char *mbox, char *p0, char *p1, char *p2, char *
     if (tid == 0) me->seq_red = seq;
 }
 
+struct Team {
+    int n = 0;
+    std::vector<pb200_ctx *> ctx;      // member contexts, rank r on devices[r]
+    std::vector<char *> mbox;          // mailboxes of the members (same process: mapped directly with peer access)
+};
+
 static void p2p_free(pb200_ctx *ctx)
 {
     P2PState *P = ctx->p2p;
     if (!P) return;
-    for (int r = 0; r < P->n; ++r) if (r != P->rank && P->peer[r]) cudaIpcCloseMemHandle(P->peer[r]);
+    if (!ctx->team) for (int r = 0; r < P->n; ++r) if (r != P->rank && P->peer[r]) cudaIpcCloseMemHandle(P->peer[r]);
     if (P->mbox) cudaFree(P->mbox);
     delete P;
     ctx->p2p = nullptr;
@@ -202,8 +208,19 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     if (cudaMalloc((void **)&P->mbox, P->bytes) != cudaSuccess) ok = 0;
     if (ok && cudaMemset(P->mbox, 0, P->bytes) != cudaSuccess) ok = 0;
     if (ok && cudaDeviceSynchronize() != cudaSuccess) ok = 0;   // (default-stream memset vs the non-blocking streams that use the mailbox next)
-    if (ok && cudaIpcGetMemHandle(&mine, P->mbox) != cudaSuccess) ok = 0;
+    if (ok && !ctx->team && cudaIpcGetMemHandle(&mine, P->mbox) != cudaSuccess) ok = 0;
     cudaGetLastError();
+    if (ctx->team) {   // one process: publish the raw pointer (the all-gather below is the barrier), enable peer access to the other members' devices
+        ctx->team->mbox[P->rank] = ok ? P->mbox : nullptr;
+        for (int r = 0; r < P->n && ok; ++r) {
+            if (r == P->rank) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctx->device, ctx->team->ctx[r]->device) != cudaSuccess || !can) { ok = 0; break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctx->team->ctx[r]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+            cudaGetLastError();
+        }
+    }
     // all-gather the handles (64 bytes each) and the ok flags through NCCL
     const size_t HS = sizeof(cudaIpcMemHandle_t) + 8;
     std::vector<unsigned char> h_all(HS * P->n, 0);
@@ -218,6 +235,7 @@ static int p2p_setup(pb200_ctx *ctx, size_t zone_doubles)
     if (ok) {
         for (int r = 0; r < P->n && ok; ++r) {
             if (r == P->rank) { P->peer[r] = P->mbox; continue; }
+            if (ctx->team) { P->peer[r] = ctx->team->mbox[r]; if (!P->peer[r]) ok = 0; continue; }
             cudaIpcMemHandle_t hr;
             memcpy(&hr, h_all.data() + HS * r, sizeof(hr));
             void *ptr = nullptr;

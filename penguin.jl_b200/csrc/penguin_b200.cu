@@ -23,6 +23,9 @@
 #define BAND_POLY_LAUNCH(...) (band_lpc(F.d.nE) == 8 ? kf_band_poly<N, 8><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__) : kf_band_poly<N, 1><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__))
 #define BAND_APPLY_LAUNCH(M_, ...) (band_lpc(F.d.nE) == 8 ? kf_apply_band<N, M_, 8><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__) : kf_apply_band<N, M_, 1><<<band_wgrid(F.d.nE), 256, 0, ctx->stream>>>(__VA_ARGS__))
 
+template <typename F> static int team_run(pb200_ctx *tc, F f);   // one host thread per member of a team context (pb200_init_multi, end of this file)
+#define IS_TEAM(ctx_) ((ctx_) && (ctx_)->is_team)
+
 // =================================================================================================================
 // lifecycle
 // =================================================================================================================
@@ -101,6 +104,13 @@ extern "C" int pb200_init_dist(pb200_ctx **ctx, int device, int rank, int nranks
 extern "C" int pb200_finalize(pb200_ctx *c)
 {
     if (!c) return PB200_OK;
+    if (c->is_team) {
+        Team *T = c->team;
+        team_run(c, [&](int r) { T->ctx[r]->team = nullptr; return pb200_finalize(T->ctx[r]); });   // (teardown of the communicator is collective)
+        delete T;
+        delete c;
+        return PB200_OK;
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     p2p_free(c);
@@ -117,22 +127,47 @@ extern "C" int pb200_finalize(pb200_ctx *c)
     return PB200_OK;
 }
 extern "C" const char *pb200_last_error(pb200_ctx *c) { return c ? c->err.c_str() : g_last_error.c_str(); }
-extern "C" int pb200_sync(pb200_ctx *c) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return PB200_OK; }
-extern "C" int64_t pb200_launch_count(pb200_ctx *c) { return c ? c->launches : 0; }
-extern "C" uint64_t pb200_stream(pb200_ctx *c) { return (uint64_t)(uintptr_t)c->stream; }
+extern "C" int pb200_sync(pb200_ctx *c)
+{
+    if (IS_TEAM(c)) { for (pb200_ctx *m : c->team->ctx) { int rc = pb200_sync(m); if (rc) return rc; } return PB200_OK; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return PB200_OK;
+}
+extern "C" int64_t pb200_launch_count(pb200_ctx *c)
+{
+    if (IS_TEAM(c)) { int64_t n = 0; for (pb200_ctx *m : c->team->ctx) n += m->launches; return n; }
+    return c ? c->launches : 0;
+}
+extern "C" uint64_t pb200_stream(pb200_ctx *c) { return (uint64_t)(uintptr_t)(IS_TEAM(c) ? c->team->ctx[0]->stream : c->stream); }
 extern "C" int pb200_set_profiling(pb200_ctx *c, int enable)
 {
     if (!c) return set_err(nullptr, PB200_EINVAL, "NULL ctx");
+    if (c->is_team) { for (pb200_ctx *m : c->team->ctx) pb200_set_profiling(m, enable); return PB200_OK; }
     c->profile = enable != 0;
     c->pev_used = 0;
     return PB200_OK;
 }
+
+
+// ---- one process, several GPUs (pb200_init_multi): team versions of the entry points, defined at the end of this file ---------------------
+static int team_capacity_create(pb200_ctx *, int, const int *, const double *, const double *, const pb200_levelset *, int, pb200_capacity **);
+static int team_capacity_import(pb200_ctx *, int, const int *, const double *, const double *, const double *, const double *, const double *, const double *,
+                                const double *, const double *, const double *, const double *, pb200_capacity **);
+static int team_capacity_export(pb200_capacity *, double *, double *, double *, double *, double *, double *, double *, double *);
+static int team_ops_create(pb200_capacity *, pb200_ops **);
+static int team_ops_vec(pb200_ops *, int what, const double *a, const double *b, double *out);
+static int team_solver_create(pb200_ctx *, const pb200_solver_desc *, pb200_solver **);
+static int team_solver_state(pb200_solver *, const double *in, double *out);
+static int team_solver_step(pb200_solver *, const pb200_step_in *, const pb200_krylov_opts *, pb200_step_stats *);
+static int team_solver_norms(pb200_solver *, int, const double *, double, int, double *);
 
 // =================================================================================================================
 // Capacity
 // =================================================================================================================
 struct pb200_capacity {
     pb200_ctx *ctx;
+    std::vector<pb200_capacity *> parts;   // team handle (pb200_init_multi): one capacity per member rank
     Grid g;
     double *V = nullptr, *Gam = nullptr, *ct = nullptr;
     double *A[PB_MAXD] = {}, *B[PB_MAXD] = {}, *W[PB_MAXD] = {}, *Co[PB_MAXD] = {}, *Cg[PB_MAXD] = {};
@@ -169,6 +204,7 @@ extern "C" int pb200_capacity_import(pb200_ctx *ctx, int ndim, const int *n, con
                                      const double *C_gamma, pb200_capacity **out)
 {
     if (!ctx || !out) return set_err(ctx, PB200_EINVAL, "NULL argument");
+    if (IS_TEAM(ctx)) return team_capacity_import(ctx, ndim, n, x0, L, V, Gamma, cell_types, A, B, W, C_omega, C_gamma, out);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_capacity *c = new pb200_capacity();
     c->ctx = ctx;
@@ -200,6 +236,7 @@ extern "C" int pb200_capacity_create(pb200_ctx *ctx, int ndim, const int *n, con
                                      int compute_centroids, pb200_capacity **out)
 {
     if (!ctx || !out || !ls) return set_err(ctx, PB200_EINVAL, "NULL argument");
+    if (IS_TEAM(ctx)) return team_capacity_create(ctx, ndim, n, x0, L, ls, compute_centroids, out);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_capacity *c = new pb200_capacity();
     c->ctx = ctx;
@@ -225,6 +262,7 @@ extern "C" int pb200_capacity_export(pb200_capacity *c, double *V, double *Gamma
                                      double *C_gamma)
 {
     if (!c) return set_err(nullptr, PB200_EINVAL, "NULL capacity");
+    if (!c->parts.empty()) return team_capacity_export(c, V, Gamma, cell_types, A, B, W, C_omega, C_gamma);
     pb200_ctx *ctx = c->ctx;
     const Grid &g = c->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -244,6 +282,7 @@ extern "C" int pb200_capacity_export(pb200_capacity *c, double *V, double *Gamma
 extern "C" int pb200_capacity_local(pb200_capacity *c, int *k0, int *k1, int64_t *nloc)
 {
     if (!c) return set_err(nullptr, PB200_EINVAL, "NULL capacity");
+    if (!c->parts.empty()) { if (k0) *k0 = 0; if (k1) *k1 = c->g.pd[c->g.sd]; if (nloc) *nloc = c->g.ntot; return PB200_OK; }   // team handle: the whole grid
     if (k0) *k0 = c->g.k0;
     if (k1) *k1 = c->g.k1;
     if (nloc) *nloc = c->g.nown;
@@ -252,6 +291,7 @@ extern "C" int pb200_capacity_local(pb200_capacity *c, int *k0, int *k1, int64_t
 extern "C" int pb200_capacity_destroy(pb200_capacity *c)
 {
     if (!c) return PB200_OK;
+    if (!c->parts.empty()) { for (pb200_capacity *p : c->parts) pb200_capacity_destroy(p); delete c; return PB200_OK; }
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     dev_free(c->V); dev_free(c->Gam); dev_free(c->ct);
@@ -264,6 +304,7 @@ extern "C" int pb200_capacity_destroy(pb200_capacity *c)
 // DiffusionOps
 // =================================================================================================================
 struct pb200_ops {
+    std::vector<pb200_ops *> parts;        // team handle
     pb200_ctx *ctx;          // (kept here: the destroy path must not reach through `cap`, which a garbage-collected host may have released first)
     pb200_capacity *cap;
     double *Wd[PB_MAXD] = {};
@@ -282,6 +323,7 @@ extern "C" int pb200_ops_destroy(pb200_ops *o);
 extern "C" int pb200_ops_create(pb200_capacity *cap, pb200_ops **out)
 {
     if (!cap || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!cap->parts.empty()) return team_ops_create(cap, out);
     pb200_ctx *ctx = cap->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_ops *o = new pb200_ops();
@@ -300,6 +342,7 @@ extern "C" int pb200_ops_create(pb200_capacity *cap, pb200_ops **out)
 extern "C" int pb200_ops_destroy(pb200_ops *o)
 {
     if (!o) return PB200_OK;
+    if (!o->parts.empty()) { for (pb200_ops *p : o->parts) pb200_ops_destroy(p); delete o; return PB200_OK; }
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     for (int d = 0; d < PB_MAXD; ++d) dev_free(o->Wd[d]);
@@ -309,6 +352,7 @@ extern "C" int pb200_ops_destroy(pb200_ops *o)
 extern "C" int pb200_ops_export_wdag(pb200_ops *o, double *wdag)
 {
     if (!o || !wdag) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!o->parts.empty()) return team_ops_vec(o, 0, nullptr, nullptr, wdag);
     pb200_ctx *ctx = o->cap->ctx;
     const Grid &g = o->cap->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -320,6 +364,7 @@ extern "C" int pb200_ops_export_wdag(pb200_ops *o, double *wdag)
 extern "C" int pb200_ops_grad(pb200_ops *o, const double *p, double *out)
 {
     if (!o || !p || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!o->parts.empty()) return team_ops_vec(o, 1, p, nullptr, out);
     pb200_ctx *ctx = o->cap->ctx;
     const Grid &g = o->cap->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -342,6 +387,7 @@ extern "C" int pb200_ops_grad(pb200_ops *o, const double *p, double *out)
 extern "C" int pb200_ops_div(pb200_ops *o, const double *qo, const double *qg, double *out)
 {
     if (!o || !qo || !qg || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!o->parts.empty()) return team_ops_vec(o, 2, qo, qg, out);
     pb200_ctx *ctx = o->cap->ctx;
     const Grid &g = o->cap->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -369,6 +415,8 @@ extern "C" int pb200_ops_div(pb200_ops *o, const double *qo, const double *qg, d
 // =================================================================================================================
 struct pb200_solver {
     pb200_ctx *ctx;
+    std::vector<pb200_solver *> parts;     // team handle
+    int team_nblk = 0;                     // blocks of the state vector (2 mono, 4 diph)
     Grid g;
     SysParams sp;
     pb200_ops *o1 = nullptr, *o2 = nullptr;
@@ -418,6 +466,7 @@ extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, p
 {
     if (!ctx || !d || !out || !d->ops1) return set_err(ctx, PB200_EINVAL, "NULL argument");
     if (d->phase_type == PB200_DIPH && !d->ops2) return set_err(ctx, PB200_EINVAL, "diphasic solver needs ops2");
+    if (IS_TEAM(ctx)) return team_solver_create(ctx, d, out);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     pb200_solver *s = new pb200_solver();
     s->ctx = ctx;
@@ -472,6 +521,12 @@ extern "C" int pb200_solver_create(pb200_ctx *ctx, const pb200_solver_desc *d, p
 extern "C" int pb200_solver_destroy(pb200_solver *s)
 {
     if (!s) return PB200_OK;
+    if (!s->parts.empty()) {
+        pb200_ctx *tc = s->ctx;
+        team_run(tc, [&](int r) { return pb200_solver_destroy(s->parts[r]); });   // (in parallel: destroying may synchronise streams that wait on peers)
+        delete s;
+        return PB200_OK;
+    }
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (double *p : s->owned) cudaFree(p);
@@ -498,6 +553,10 @@ static int64_t side_cells(const Grid &g, int side)
 extern "C" int pb200_solver_set_border(pb200_solver *s, int side, int kind, double value, const double *values)
 {
     if (!s || side < 0 || side > 5) return set_err(nullptr, PB200_EINVAL, "bad side");
+    if (!s->parts.empty()) {   // the side array is indexed by GLOBAL cell coordinates on every rank: the same host array goes to every member
+        for (pb200_solver *p : s->parts) { int rc = pb200_solver_set_border(p, side, kind, value, values); if (rc) return set_err(s->ctx, rc, g_last_error); }
+        return PB200_OK;
+    }
     pb200_ctx *ctx = s->ctx;
     const int dim = (side == PB200_LEFT || side == PB200_RIGHT) ? 1 : (side == PB200_BOTTOM || side == PB200_TOP) ? 0 : 2;
     if (dim >= s->g.N) return PB200_OK;   // keys of absent dimensions never match a cell (src/solver.jl:379-409)
@@ -530,6 +589,7 @@ extern "C" int pb200_solver_set_border(pb200_solver *s, int side, int kind, doub
 extern "C" int pb200_solver_set_state(pb200_solver *s, const double *x)
 {
     if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!s->parts.empty()) return team_solver_state(s, x, nullptr);
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -546,6 +606,7 @@ extern "C" int pb200_solver_set_state(pb200_solver *s, const double *x)
 extern "C" int pb200_solver_get_state(pb200_solver *s, double *x)
 {
     if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!s->parts.empty()) return team_solver_state(s, nullptr, x);
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -563,6 +624,7 @@ extern "C" int pb200_solver_get_state(pb200_solver *s, double *x)
 extern "C" int pb200_solver_error_norms(pb200_solver *s, int phase, const double *u_ana, double p, int relative, double out[4])
 {
     if (!s || !u_ana || !out) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!s->parts.empty()) return team_solver_norms(s, phase, u_ana, p, relative, out);
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     const int np = s->sp.phase_type == PB200_DIPH ? 2 : 1;
@@ -602,6 +664,7 @@ extern "C" int pb200_solver_error_norms(pb200_solver *s, int phase, const double
 extern "C" int pb200_solver_get_state_async(pb200_solver *s, double *x)
 {
     if (!s || !x) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!s->parts.empty()) return team_solver_state(s, nullptr, x);   // team handle: the slabs are reassembled on the host, synchronously
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -624,6 +687,7 @@ extern "C" int pb200_solver_get_state_async(pb200_solver *s, double *x)
 extern "C" int pb200_solver_wait_state(pb200_solver *s)
 {
     if (!s) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!s->parts.empty()) return PB200_OK;
     if (s->copy_pending) { CUDA_TRY(s->ctx, cudaEventSynchronize(s->copy_done)); s->copy_pending = false; }
     return PB200_OK;
 }
@@ -1205,8 +1269,8 @@ static int fold2_launch(pb200_solver *s, const Items &L, const F2Maps &maps, con
 {
     pb200_ctx *ctx = s->ctx;
     constexpr int smem = 2 * (MODE == 5 ? 2 : 1) * F2Box<N>::SLOT;
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf2_apply<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    static bool attr_set[64] = {};   // per DEVICE: a function attribute belongs to the context of the device it was set on
+    if (!attr_set[ctx->device & 63]) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf2_apply<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set[ctx->device & 63] = true; }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf2_apply<N, MODE>, FCH, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 2; }
     int grid = L.n < ctx->sm_count * nb ? L.n : ctx->sm_count * nb;
@@ -1252,8 +1316,8 @@ static int fold3_launch(pb200_solver *s, const Items &L, const F3Maps &maps, con
     constexpr bool TT = MODE == 5 || MODE == 2 || MODE == 4;
     constexpr int STAGE = (MODE == 5 ? 2 : 1) * F2Box<N>::SLOT + (TT ? FTILE * 8 : 0);
     constexpr int smem = S * STAGE + 128;
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    static bool attr_set[64] = {};   // per DEVICE (one process may drive several: pb200_init_multi)
+    if (!attr_set[ctx->device & 63]) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set[ctx->device & 63] = true; }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf3_apply<N, MODE, S>, FCH + 32, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
     int grid = L.n < ctx->sm_count * nb ? L.n : ctx->sm_count * nb;
@@ -1262,8 +1326,8 @@ static int fold3_launch(pb200_solver *s, const Items &L, const F3Maps &maps, con
     if (grid < 1) grid = 1;
     if ((dbg & 8) && MODE == 5) {   // one stage: no overlap, tests the pipeline logic
         constexpr int smem1 = STAGE + 128;
-        static bool attr1 = false;
-        if (!attr1) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1)); attr1 = true; }
+        static bool attr1[64] = {};
+        if (!attr1[ctx->device & 63]) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1)); attr1[ctx->device & 63] = true; }
         kf3_apply<N, MODE, 1><<<grid, FCH + 32, smem1, st>>>(maps, L, A, has_t, dbg);
     } else
     kf3_apply<N, MODE, S><<<grid, FCH + 32, smem, st>>>(maps, L, A, has_t, dbg);
@@ -1776,6 +1840,7 @@ static int stage_src(pb200_solver *s, double **slot, const double *host, double 
 extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const pb200_krylov_opts *opts_in, pb200_step_stats *stats)
 {
     if (!s || !in) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!s->parts.empty()) return team_solver_step(s, in, opts_in, stats);
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -2092,4 +2157,240 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     }
     if (!converged) return set_err(ctx, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
     return PB200_OK;
+}
+
+
+// =================================================================================================================================
+// One process driving several GPUs -- pb200_init_multi ("Julia is one process"; the reference's scripts are single-process).
+// The team handle stands for ndev member contexts, rank r on devices[r]; every entry point fans out to the members on one host thread per
+// GPU (the calls contain collective steps -- halo exchanges, reductions -- that all ranks must reach together) and cuts / reassembles the
+// host arrays: per-cell arrays keep the reference's GLOBAL padded length n = prod(n_i + 1); member r owns the planes [k0_r, k1_r) of the
+// slowest dimension, a contiguous range of every block of n doubles.
+// =================================================================================================================================
+template <typename F>
+static int team_run(pb200_ctx *tc, F f)
+{
+    Team *T = tc->team;
+    std::vector<int> rc(T->n, 0);
+    std::vector<std::string> err(T->n);
+    std::vector<std::thread> th;
+    for (int r = 0; r < T->n; ++r)
+        th.emplace_back([&, r]() {
+            if (T->ctx[r]) cudaSetDevice(T->ctx[r]->device);   // (the members do not exist yet while pb200_init_multi creates them)
+            rc[r] = f(r);
+            if (rc[r]) err[r] = g_last_error;
+        });
+    for (std::thread &t : th) t.join();
+    for (int r = 0; r < T->n; ++r)
+        if (rc[r]) return set_err(tc, rc[r], "rank " + std::to_string(r) + ": " + err[r]);
+    return PB200_OK;
+}
+
+extern "C" int pb200_init_multi(pb200_ctx **ctx, const int *devices, int ndev)
+{
+    if (!ctx || !devices || ndev < 1 || ndev > P2P_MAXR) return set_err(nullptr, PB200_EINVAL, "need 1 .. 8 devices");
+    if (ndev == 1) return pb200_init(ctx, devices[0]);
+    char id[128];
+    int rc = pb200_nccl_unique_id(id);
+    if (rc) return rc;
+    pb200_ctx *tc = new pb200_ctx();
+    Team *T = new Team();
+    T->n = ndev; T->ctx.assign(ndev, nullptr); T->mbox.assign(ndev, nullptr);
+    tc->team = T; tc->is_team = true; tc->device = devices[0]; tc->nranks = ndev;
+    rc = team_run(tc, [&](int r) { return pb200_init_dist(&T->ctx[r], devices[r], r, ndev, id); });   // ncclCommInitRank: all ranks together
+    if (rc) {
+        for (pb200_ctx *m : T->ctx) if (m) pb200_finalize(m);
+        const std::string msg = tc->err;
+        delete T; delete tc;
+        return set_err(nullptr, rc, msg);
+    }
+    for (pb200_ctx *m : T->ctx) m->team = T;
+    *ctx = tc;
+    return PB200_OK;
+}
+
+// blocks of `n` doubles of a global host array <-> blocks of nown doubles of member r
+static void team_cut(const Grid &gr, int64_t ntot, const double *glob, int nblk, std::vector<double> &loc)
+{
+    loc.resize((size_t)nblk * gr.nown);
+    for (int b = 0; b < nblk; ++b) memcpy(loc.data() + (size_t)b * gr.nown, glob + (size_t)b * ntot + (size_t)gr.k0 * gr.plane, sizeof(double) * (size_t)gr.nown);
+}
+static void team_paste(const Grid &gr, int64_t ntot, const std::vector<double> &loc, int nblk, double *glob)
+{
+    for (int b = 0; b < nblk; ++b) memcpy(glob + (size_t)b * ntot + (size_t)gr.k0 * gr.plane, loc.data() + (size_t)b * gr.nown, sizeof(double) * (size_t)gr.nown);
+}
+static int team_global_grid(pb200_ctx *tc, int ndim, const int *n, const double *x0, const double *L, Grid *g)
+{
+    pb200_ctx one;          // (a single-rank description of the whole grid: sizes only)
+    one.rank = 0; one.nranks = 1;
+    return make_grid(&one, ndim, n, x0, L, g) ? set_err(tc, PB200_EINVAL, g_last_error) : PB200_OK;
+}
+
+static int team_capacity_create(pb200_ctx *tc, int ndim, const int *n, const double *x0, const double *L, const pb200_levelset *ls, int cc, pb200_capacity **out)
+{
+    Team *T = tc->team;
+    pb200_capacity *c = new pb200_capacity();
+    c->ctx = tc; c->has_cg = cc != 0;
+    int rc = team_global_grid(tc, ndim, n, x0, L, &c->g);
+    if (rc) { delete c; return rc; }
+    c->parts.assign(T->n, nullptr);
+    rc = team_run(tc, [&](int r) { return pb200_capacity_create(T->ctx[r], ndim, n, x0, L, ls, cc, &c->parts[r]); });
+    if (rc) { pb200_capacity_destroy(c); return rc; }
+    *out = c;
+    return PB200_OK;
+}
+static int team_capacity_import(pb200_ctx *tc, int ndim, const int *n, const double *x0, const double *L, const double *V, const double *Gamma, const double *ct,
+                                const double *A, const double *B, const double *W, const double *Co, const double *Cg, pb200_capacity **out)
+{
+    Team *T = tc->team;
+    pb200_capacity *c = new pb200_capacity();
+    c->ctx = tc; c->has_cg = Cg != nullptr;
+    int rc = team_global_grid(tc, ndim, n, x0, L, &c->g);
+    if (rc) { delete c; return rc; }
+    c->parts.assign(T->n, nullptr);
+    const int64_t nt = c->g.ntot;
+    rc = team_run(tc, [&](int r) {
+        Grid gr;
+        int rr = make_grid(T->ctx[r], ndim, n, x0, L, &gr);
+        if (rr) return rr;
+        std::vector<double> a, b, w, co, cg;
+        if (A) team_cut(gr, nt, A, ndim, a);
+        if (B) team_cut(gr, nt, B, ndim, b);
+        if (W) team_cut(gr, nt, W, ndim, w);
+        if (Co) team_cut(gr, nt, Co, ndim, co);
+        if (Cg) team_cut(gr, nt, Cg, ndim, cg);
+        const size_t off = (size_t)gr.k0 * gr.plane;     // single blocks: a pointer offset is enough
+        return pb200_capacity_import(T->ctx[r], ndim, n, x0, L, V ? V + off : nullptr, Gamma ? Gamma + off : nullptr, ct ? ct + off : nullptr, A ? a.data() : nullptr,
+                                     B ? b.data() : nullptr, W ? w.data() : nullptr, Co ? co.data() : nullptr, Cg ? cg.data() : nullptr, &c->parts[r]);
+    });
+    if (rc) { pb200_capacity_destroy(c); return rc; }
+    *out = c;
+    return PB200_OK;
+}
+static int team_capacity_export(pb200_capacity *c, double *V, double *Gamma, double *ct, double *A, double *B, double *W, double *Co, double *Cg)
+{
+    pb200_ctx *tc = c->ctx;
+    const int64_t nt = c->g.ntot;
+    const int N = c->g.N;
+    return team_run(tc, [&](int r) {
+        const Grid &gr = c->parts[r]->g;
+        std::vector<double> a(A ? (size_t)N * gr.nown : 0), b(B ? (size_t)N * gr.nown : 0), w(W ? (size_t)N * gr.nown : 0), co(Co ? (size_t)N * gr.nown : 0),
+            cg(Cg ? (size_t)N * gr.nown : 0);
+        const size_t off = (size_t)gr.k0 * gr.plane;
+        int rr = pb200_capacity_export(c->parts[r], V ? V + off : nullptr, Gamma ? Gamma + off : nullptr, ct ? ct + off : nullptr, A ? a.data() : nullptr,
+                                       B ? b.data() : nullptr, W ? w.data() : nullptr, Co ? co.data() : nullptr, Cg ? cg.data() : nullptr);
+        if (rr) return rr;
+        if (A) team_paste(gr, nt, a, N, A);
+        if (B) team_paste(gr, nt, b, N, B);
+        if (W) team_paste(gr, nt, w, N, W);
+        if (Co) team_paste(gr, nt, co, N, Co);
+        if (Cg) team_paste(gr, nt, cg, N, Cg);
+        return PB200_OK;
+    });
+}
+static int team_ops_create(pb200_capacity *cap, pb200_ops **out)
+{
+    pb200_ctx *tc = cap->ctx;
+    pb200_ops *o = new pb200_ops();
+    o->ctx = tc; o->cap = cap;
+    o->parts.assign(tc->team->n, nullptr);
+    int rc = team_run(tc, [&](int r) { return pb200_ops_create(cap->parts[r], &o->parts[r]); });
+    if (rc) { pb200_ops_destroy(o); return rc; }
+    *out = o;
+    return PB200_OK;
+}
+// what: 0 export W! (out: N blocks), 1 grad (a: 2 blocks, out: N blocks), 2 div (a, b: N blocks each, out: 1 block)
+static int team_ops_vec(pb200_ops *o, int what, const double *a, const double *b, double *out)
+{
+    pb200_ctx *tc = o->ctx;
+    const int64_t nt = o->cap->g.ntot;
+    const int N = o->cap->g.N;
+    return team_run(tc, [&](int r) {
+        const Grid &gr = o->parts[r]->cap->g;
+        std::vector<double> la, lb, lo((size_t)(what == 2 ? 1 : N) * gr.nown);
+        int rr;
+        if (what == 0) rr = pb200_ops_export_wdag(o->parts[r], lo.data());
+        else if (what == 1) { team_cut(gr, nt, a, 2, la); rr = pb200_ops_grad(o->parts[r], la.data(), lo.data()); }
+        else { team_cut(gr, nt, a, N, la); team_cut(gr, nt, b, N, lb); rr = pb200_ops_div(o->parts[r], la.data(), lb.data(), lo.data()); }
+        if (rr) return rr;
+        team_paste(gr, nt, lo, what == 2 ? 1 : N, out);
+        return PB200_OK;
+    });
+}
+static int team_solver_create(pb200_ctx *tc, const pb200_solver_desc *d, pb200_solver **out)
+{
+    Team *T = tc->team;
+    if (d->ops1->parts.empty() || (d->ops2 && d->ops2->parts.empty())) return set_err(tc, PB200_EINVAL, "the operators do not belong to this team context");
+    pb200_solver *s = new pb200_solver();
+    s->ctx = tc; s->g = d->ops1->cap->g;
+    s->team_nblk = d->phase_type == PB200_DIPH ? 4 : 2;
+    s->parts.assign(T->n, nullptr);
+    int rc = team_run(tc, [&](int r) {
+        pb200_solver_desc dr = *d;
+        dr.ops1 = d->ops1->parts[r];
+        dr.ops2 = d->ops2 ? d->ops2->parts[r] : nullptr;
+        const Grid &gr = dr.ops1->cap->g;
+        const size_t off = (size_t)gr.k0 * gr.plane;
+        if (d->D1_arr) dr.D1_arr = d->D1_arr + off;
+        if (d->D2_arr) dr.D2_arr = d->D2_arr + off;
+        return pb200_solver_create(T->ctx[r], &dr, &s->parts[r]);
+    });
+    if (rc) { pb200_solver_destroy(s); return rc; }
+    *out = s;
+    return PB200_OK;
+}
+static int team_solver_state(pb200_solver *s, const double *in, double *out)
+{
+    pb200_ctx *tc = s->ctx;
+    const int64_t nt = s->g.ntot;
+    return team_run(tc, [&](int r) {
+        const Grid &gr = s->parts[r]->g;
+        std::vector<double> loc;
+        if (in) { team_cut(gr, nt, in, s->team_nblk, loc); return pb200_solver_set_state(s->parts[r], loc.data()); }
+        loc.resize((size_t)s->team_nblk * gr.nown);
+        int rr = pb200_solver_get_state(s->parts[r], loc.data());
+        if (!rr) team_paste(gr, nt, loc, s->team_nblk, out);
+        return rr;
+    });
+}
+static int team_solver_step(pb200_solver *s, const pb200_step_in *in, const pb200_krylov_opts *opts, pb200_step_stats *stats)
+{
+    pb200_ctx *tc = s->ctx;
+    const int n = tc->team->n;
+    std::vector<pb200_step_stats> st(n);
+    std::vector<int> rcs(n, 0);
+    int rc = team_run(tc, [&](int r) {
+        const Grid &gr = s->parts[r]->g;
+        const size_t off = (size_t)gr.k0 * gr.plane;
+        pb200_step_in ir = *in;
+        for (int p = 0; p < 2; ++p) for (int w = 0; w < 2; ++w) if (in->f_arr[p][w]) ir.f_arr[p][w] = in->f_arr[p][w] + off;
+        for (int w = 0; w < 2; ++w) if (in->g_arr[w]) ir.g_arr[w] = in->g_arr[w] + off;
+        memset(&st[r], 0, sizeof(st[r]));
+        rcs[r] = pb200_solver_step(s->parts[r], &ir, opts, &st[r]);
+        return rcs[r] == PB200_ENOTCONV ? PB200_OK : rcs[r];     // (every rank takes the same decision; reported below)
+    });
+    if (rc) return rc;
+    if (stats) {
+        *stats = st[0];      // iteration counts, norms, global DOF counts are identical on every rank
+        for (int r = 1; r < n; ++r) {
+            if (st[r].solve_ms > stats->solve_ms) stats->solve_ms = st[r].solve_ms;
+            if (st[r].setup_ms > stats->setup_ms) stats->setup_ms = st[r].setup_ms;
+            stats->launches += st[r].launches; stats->apply_launches += st[r].apply_launches;
+            stats->apply_cells_uniform += st[r].apply_cells_uniform; stats->apply_cells_general += st[r].apply_cells_general;
+            stats->apply_cells_fast += st[r].apply_cells_fast; stats->band_cells += st[r].band_cells; stats->band_rows += st[r].band_rows;
+        }
+    }
+    if (rcs[0] == PB200_ENOTCONV) return set_err(tc, PB200_ENOTCONV, "Krylov solve did not reach the tolerance within maxit iterations");
+    return PB200_OK;
+}
+static int team_solver_norms(pb200_solver *s, int phase, const double *u_ana, double p, int relative, double *out)
+{
+    pb200_ctx *tc = s->ctx;
+    std::vector<double> o((size_t)4 * tc->team->n);
+    int rc = team_run(tc, [&](int r) {
+        const Grid &gr = s->parts[r]->g;
+        return pb200_solver_error_norms(s->parts[r], phase, u_ana + (size_t)gr.k0 * gr.plane, p, relative, o.data() + 4 * r);
+    });
+    if (!rc) memcpy(out, o.data(), 4 * sizeof(double));      // (reduced over the ranks inside the library: every rank holds the same numbers)
+    return rc;
 }

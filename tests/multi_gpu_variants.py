@@ -76,8 +76,29 @@ def main():
     ap.add_argument("--single", default=None)
     ap.add_argument("--ref", default=None)
     ap.add_argument("--cases", default="diph3d,mono3d,diph2d")
+    ap.add_argument("--team", type=int, default=0, help="ONE process driving this many GPUs (pb200_init_multi): global host arrays, compared with --ref")
     args = ap.parse_args()
     cases = args.cases.split(",")
+    if args.team:
+        import faulthandler
+        faulthandler.enable()
+        import torch  # noqa: F401  (loads the NCCL build that ships with torch before the library dlopens libnccl.so.2)
+        print("init_multi ...", flush=True)
+        pb.init_multi(list(range(args.team)))
+        print("init_multi done", flush=True)
+        ref = np.load(args.ref)
+        worst = 0.0
+        for case in cases:
+            dims, nblk, s = run_case(case, 0, 1)          # the team handle takes and returns GLOBAL arrays
+            for k, x in enumerate(s.states):
+                r = ref[f"{case}_{k}"]
+                err = np.linalg.norm(x - r) / np.linalg.norm(r)
+                worst = max(worst, err)
+                print(f"{case} [one process, {args.team} GPUs] state {k}: rel L2 vs one GPU = {err:.3e}  iterations {s.ch[k]['iters']} (one GPU {int(ref[case + '_iters'][k])})", flush=True)
+                assert err < 1e-9, err
+        print("SINGLE_PROCESS_MULTI_GPU_OK worst", worst)
+        pb.finalize()
+        return
     if args.single:
         pb.init(0)
         out = {}

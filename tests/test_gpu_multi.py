@@ -44,3 +44,16 @@ def test_ranks_agree_with_one_gpu(tmp_path, nccl_only):
         out = _torchrun(n, "multi_gpu_variants.py", ["--ref", ref, "--cases", cases], env={"PB200_NO_P2P": "1"} if nccl_only else None)
         assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
         assert "MULTI_GPU_VARIANTS_OK" in out.stdout
+
+
+def test_one_process_drives_two_gpus(tmp_path):
+    """pb200_init_multi: an unchanged single-process script (global host arrays) on 2 GPUs vs the same script on one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ref = str(tmp_path / "ref.npz")
+    script = os.path.join(ROOT, "tests", "multi_gpu_variants.py")
+    out = subprocess.run([sys.executable, script, "--single", ref, "--cases", "diph3d,mono3d"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    out = subprocess.run([sys.executable, script, "--team", "2", "--ref", ref, "--cases", "diph3d,mono3d"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "SINGLE_PROCESS_MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
