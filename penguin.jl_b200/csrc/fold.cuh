@@ -50,6 +50,11 @@ struct FoldDev {
     int *EnbrB;      // [2N][nEp]        (SoA: one THREAD works on one band / fringe cell, consecutive threads on consecutive cells)
     double *Eblk;    // [(1+2N)*9][nEp]  block 0: self, 1+2d: lower neighbour in d, 2+2d: upper; each 3x3 row-major
     unsigned char *Efix;   // [nE] bit k: gathered cell k (0 self, 1 + kk neighbours) lies in a tile of the fused kernel (its p lacks the band correction dz)
+    // band work folded into the two streaming kernels of the fused CG iteration (fold2.cuh "band heads", one rank):
+    const int *eord;       // [nloc] index of a cell in the E list (band + fringe cells), -1 elsewhere
+    const int *EofB;       // [nB]   E index of band cell k
+    const int *EnbrE;      // [2N][nEp] E index of the face neighbours that are band cells (-1: not a band cell), beside EnbrB
+    double *ya;            // [2][nEp] band-coupling part of v = M^ p on the bulk rows of the E cells (the tile kernel writes the dense part to v)
     int nEp;         // nE rounded up to a multiple of 32
     // Krylov vectors (FVec bulk fields) live in a RE-PITCHED copy of the local grid: x rows padded from ld0 (the reference's odd n+1) to P0,
     // a multiple of 32 doubles, so that every 32-cell tile row is 256-byte aligned and the arrays can be described to TMA (global
@@ -99,7 +104,7 @@ struct Items {
     int sd, lz;                    // slab dimension and its local extent (first / last plane of it are ghosts)
     int glo, ghi;                  // a neighbour rank exists below / above (its data fills that ghost plane)
     int wlo, whi;
-    const unsigned char *uni;      // [n] bit 0: the tile's coefficients are constants (ucoef); bit 1: the tile holds band cells (kf_tile_meta)
+    const unsigned char *uni;      // [n] bit 0: the tile's coefficients are constants (ucoef); bit 1: the tile holds band cells; bit 3: holds E cells (kf_tile_meta)
     const double *ucoef;           // [n][PB_MAXD]
 };
 // cell k (0..FU-1) of this thread inside tile R: linear index (reference pitch), index in the re-pitched Krylov vectors, validity
@@ -278,6 +283,27 @@ __global__ void kf_mark_band(long long nloc, const unsigned char *__restrict__ m
 __global__ void kf_bord_fill(int nB, const long long *__restrict__ Bcell, int *__restrict__ bord)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nB; k += gridDim.x * blockDim.x) bord[Bcell[k]] = k;
+}
+__global__ void kf_eord_fill(int nE, const long long *__restrict__ Ecell, const int *__restrict__ bord, int *__restrict__ eord, int *__restrict__ EofB)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const long long l = Ecell[e];
+        eord[l] = e;
+        const int bo = bord[l];
+        if (bo >= 0) EofB[bo] = e;
+    }
+}
+// (after kf_blocks: EnbrB is known) E index of the band neighbours
+__global__ void kf_enbre_fill(Grid g, int nE, int nEp, const long long *__restrict__ Ecell, const int *__restrict__ EnbrB, const int *__restrict__ eord, int *__restrict__ EnbrE)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const long long l = Ecell[e];
+        for (int kk = 0; kk < 2 * g.N; ++kk) {
+            const int nb = EnbrB[(size_t)kk * nEp + e];
+            const long long ln = (kk & 1) ? l + g.stride[kk >> 1] : l - g.stride[kk >> 1];
+            EnbrE[(size_t)kk * nEp + e] = nb >= 0 ? eord[ln] : -1;
+        }
+    }
 }
 
 template <int N>
@@ -494,7 +520,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
         const TileRec R = I.rec[it];
         if (R.f >= 2) { if (threadIdx.x == 0) uni[it] = 0; continue; }   // uniform over the block
         double mn[PB_MAXD], mx[PB_MAXD];
-        int nok = 0, hasb = 0;
+        int nok = 0, hasb = 0, hase = 0;
 #pragma unroll
         for (int d = 0; d < N; ++d) { mn[d] = 1e300; mx[d] = -1e300; }
 #pragma unroll
@@ -503,6 +529,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
             if (!tile_cell(I, R, k, l)) continue;
             ++nok;
             if (fd.bord && fd.bord[l] >= 0) hasb = 1;
+            if (fd.eord && fd.eord[l] >= 0) hase = 1;
 #pragma unroll
             for (int d = 0; d < N; ++d) {
                 const double *__restrict__ of = R.f == 0 ? fd.off[0][d] : fd.off[1][d];
@@ -517,6 +544,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
             if ((threadIdx.x & 31) == 0) { smn[d][threadIdx.x >> 5] = mn[d]; smx[d][threadIdx.x >> 5] = mx[d]; }
         }
         const int anyb = __syncthreads_or(hasb);
+        const int anye = __syncthreads_or(hase);
         if (threadIdx.x == 0) {
             bool u = true;
             for (int d = 0; d < N; ++d) {
@@ -528,7 +556,7 @@ __global__ void __launch_bounds__(FCH) kf_tile_meta(Grid g, FoldDev fd, Items I,
                 u = u && (b - a <= utol * fmax(fabs(a), fabs(b)));
                 ucoef[(size_t)it * PB_MAXD + d] = 0.5 * (a + b);
             }
-            uni[it] = (unsigned char)((u ? 1 : 0) | (anyb ? 2 : 0));   // bit 0: constant coefficients, bit 1: holds band cells
+            uni[it] = (unsigned char)((u ? 1 : 0) | (anyb ? 2 : 0) | (anye ? 8 : 0));   // bit 0: constant coefficients, bit 1: holds band cells, bit 3: holds band or fringe cells (E list)
             s_uni = u ? 1 : 0;
         }
         __syncthreads();
@@ -1168,6 +1196,8 @@ struct FoldSys {
     int *bord = nullptr, *EB = nullptr, *EnbrB = nullptr, *items = nullptr;
     double *Linv = nullptr, *Eblk = nullptr;
     unsigned char *Efix = nullptr;
+    int *eord = nullptr, *EofB = nullptr, *EnbrE = nullptr;   // band heads of the fused iteration (fold2.cuh)
+    double *ya = nullptr;
     int nitems = 0;
     unsigned char *uni = nullptr;
     double *ucoef = nullptr;
@@ -1190,7 +1220,8 @@ struct FoldSys {
     std::vector<void *> list_mem;           // device arrays behind the sub-lists
     FVec x, b, r, p, v, r0, s, t, z;
     FVec p2 = {}, zz = {};                  // fused iteration: second search-direction buffer, preconditioned residual (polynomial)
-    bool have_p2 = false, have_zz = false;
+    FVec r2 = {};                           // band heads: second residual buffer (r is double-buffered by iteration parity)
+    bool have_p2 = false, have_zz = false, have_r2 = false;
     bool tma_ok = false;                    // the Krylov vectors are describable to TMA (fold2.cuh)
     bool pipe = false;                      // ... and the interior constant-coefficient tiles go through the pipelined kernel (kf3_apply)
     Items IAi_all;                          // interior class, every kind of tile (fused iteration without the pipelined kernel)
@@ -1214,13 +1245,14 @@ static void fold_free(FoldSys &F)
     if (F.uni) cudaFree(F.uni); if (F.ucoef) cudaFree(F.ucoef); if (F.rec) cudaFree(F.rec); if (F.dz) cudaFree(F.dz); F.dz = nullptr; F.prec = false; F.uni = nullptr; F.ucoef = nullptr; F.rec = nullptr;
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
     if (F.Efix) cudaFree(F.Efix); F.Efix = nullptr;
+    if (F.eord) cudaFree(F.eord); if (F.EofB) cudaFree(F.EofB); if (F.ya) cudaFree(F.ya); if (F.EnbrE) cudaFree(F.EnbrE); F.eord = F.EofB = F.EnbrE = nullptr; F.ya = nullptr;
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
     for (void *m : F.list_mem) cudaFree(m);
     F.list_mem.clear();
     F.tmaps.clear();
-    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t, &F.z, &F.p2, &F.zz};
+    FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t, &F.z, &F.p2, &F.zz, &F.r2};
     for (FVec *a : vs) fold_free_vec(*a);
-    F.built = false; F.have_bicg = false; F.have_z = false; F.have_p2 = false; F.have_zz = false; F.tma_ok = false;
+    F.built = false; F.have_bicg = false; F.have_z = false; F.have_p2 = false; F.have_zz = false; F.have_r2 = false; F.tma_ok = false;
 }
 
 static const int PB_NCCL_UINT8 = 1;

@@ -63,8 +63,29 @@ template <int N> struct F2Box {
 };
 struct alignas(64) F2Maps { CUtensorMap a[2]; CUtensorMap b[2]; };   // per bulk field: a = the staged vector (x, or z in MODE 5), b = p_{k-1} (MODE 5)
 
+// Band heads (one rank).  The interface-band part of an iteration used to be two launches of its own between the streaming kernels
+// (kf_apply_band after the apply, kf_band_poly after the residual update): O(band) work, ~13 us of latency each, a third of an iteration at
+// 2048^2.  Both are folded into the streaming kernels as a HEAD that every block runs on its share of the band / fringe cells before it starts
+// on its tiles -- possible because neither needs anything the same launch produces:
+//   * apply head: gathers p_k on a band cell and its neighbours as z + beta p_{k-1} (+ dz on band cells) from the INPUTS of the launch, writes
+//     the band couplings of the bulk rows to the compact array ya (the tile part writes the dense part to v: no read-modify-write between blocks),
+//     the w rows of v, p_k and x on the interface unknowns (kf2_pupd is gone), and adds its share of (p_k, v) to the block's partial sum;
+//   * update head: r is double-buffered by iteration parity, so the head forms r_k = r_{k-1} - alpha (v + ya) on a band cell and its band
+//     neighbours from the OLD residual while other blocks write the new one, applies the band polynomial (dz, rho_band) and adds the previous dz
+//     to p_k on the band cells (the tile kernel formed p_k without it).
+struct BandHead {
+    int on, nE, nEp, nB, nbulk;
+    const long long *Ecell; const int *EB, *EnbrB, *EnbrE, *EofB, *eord;
+    const double *Eblk;
+    double *ya, *dzw;
+    long long ld0, dP, sq[PB_MAXD];
+    double ca, cb;          // band polynomial: dz = ca r_B + cb M^_BB r_B
+};
+__device__ __forceinline__ long long bh_q(const BandHead &b, long long l) { return b.dP ? l + (l / b.ld0) * b.dP : l; }
+
 struct F2Args {
     FVec a, pold, y, pnew, xs, aux;
+    BandHead bh;
     const double *dz; const int *bord; int nB;    // band preconditioner correction z_B - r_B (MODE 5, kf2_pupd); nullptr: none
     int sl_old, sl_cur;                           // rho groups of the previous / the current iteration
     StopCrit stop;
@@ -301,6 +322,112 @@ __global__ void __launch_bounds__(FCH) kf2_update(Items I, double *res, int sl_r
     v[1] = v[0];
     block_reduce_publish<2>(v, partials, res + sl_new, counter);
 }
+// Residual update of the fused iteration WITH the update head (see BandHead): reads r_{k-1} from `rold`, writes r_k to `r` (two buffers, by
+// iteration parity), v = qv + ya on the E cells; publishes (rho, rr, rho_band).
+// HB > 0: the first HB blocks of the grid run the head (one thread per band cell) and nothing else, the others stream the tiles meanwhile -- with
+// every block running its share of the head first, nothing streamed during the head's dependent gathers (2048^2: 23 -> 33 us).  HB = 0: every block does both.
+template <int N, int LPC>
+__global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int sl_rho, int sl_new, FVec qv, FVec rold, FVec r, FVec pnew, BandHead b, int HB,
+                                                       double *partials, unsigned *counter, StopCrit stop)
+{
+    if (fold_done(res, stop)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; res[sl_new + 3] = res[sl_rho + 3]; }
+        return;
+    }
+    const double alpha = safe_div(rho_at(res, sl_rho), res[FS_SIG_D] + res[FS_SIG_B] + res[FS_SIG_G]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { res[FS_ITERS] += 1.0; res[FS_ALPHA] = alpha; res[FS_XPEND] = 1.0; }
+    double v[3] = {0.0, 0.0, 0.0};
+    const size_t ES = (size_t)b.nEp;
+    const bool two = b.nbulk > 1;
+    const bool head_block = HB == 0 || (int)blockIdx.x < HB;
+    if (b.nB > 0 && head_block) {
+        // ---- head: band polynomial on r_k, formed from r_{k-1}, v and ya; LPC lanes per band cell (lane `sub` takes the blocks k = sub, sub + LPC, ...) ----
+        const int nhb = HB == 0 ? (int)gridDim.x : HB;
+        const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x), sub = gtid % LPC, gid = gtid / LPC, ngroups = nhb * (int)blockDim.x / LPC;
+        const int rounds = (b.nB + ngroups - 1) / ngroups;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int bo_raw = rd * ngroups + gid;
+            const bool live = bo_raw < b.nB;
+            const int bo = live ? bo_raw : b.nB - 1;        // (groups past the end redo the last cell: the shuffles are warp-wide)
+            const int e = b.EofB[bo];
+            const long long lq = bh_q(b, b.Ecell[e]);
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0, x0 = 0.0, x1 = 0.0, xw = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < 1 + 2 * N; k0 += LPC) {
+                const int k = k0 + sub;
+                if (LPC > 1 && k >= 1 + 2 * N) break;
+                long long ln = lq;
+                int nb = bo, en = e;
+                if (k > 0) {
+                    const int kk = k - 1, d = kk >> 1;
+                    ln = (kk & 1) ? lq + b.sq[d] : lq - b.sq[d];
+                    nb = b.EnbrB[(size_t)kk * ES + e];
+                    en = b.EnbrE[(size_t)kk * ES + e];
+                }
+                // branch-free: a neighbour that is no band cell reads this cell's entries and counts with weight 0 (all loads of a lane are in flight together)
+                const double wgt = nb >= 0 ? 1.0 : 0.0;
+                if (nb < 0) { nb = bo; en = e; ln = lq; }
+                const double *__restrict__ c = b.Eblk + (size_t)(k * 9) * ES + e;
+                const double c0 = c[0], c1 = c[ES], c2 = c[2 * ES], c3 = c[3 * ES], c4 = c[4 * ES], c5 = c[5 * ES], c6 = c[6 * ES], c7 = c[7 * ES], c8 = c[8 * ES];
+                const double v0 = wgt * fma(-alpha, qv.f[0][ln] + b.ya[en], rold.f[0][ln]);
+                const double v1 = two ? wgt * fma(-alpha, qv.f[1][ln] + b.ya[ES + en], rold.f[1][ln]) : 0.0;
+                const double v2 = wgt * fma(-alpha, qv.f[2][nb], rold.f[2][nb]);
+                if (k == 0) { x0 = v0; x1 = v1; xw = v2; }
+                r0 += c0 * v0 + c1 * v1 + c2 * v2;
+                r1 += c3 * v0 + c4 * v1 + c5 * v2;
+                r2 += c6 * v0 + c7 * v1 + c8 * v2;
+            }
+            if (LPC > 1) {
+#pragma unroll
+                for (int o = LPC / 2; o > 0; o >>= 1) {
+                    r0 += __shfl_xor_sync(0xffffffffu, r0, o, LPC); r1 += __shfl_xor_sync(0xffffffffu, r1, o, LPC); r2 += __shfl_xor_sync(0xffffffffu, r2, o, LPC);
+                }
+            }
+            if (sub != 0 || !live) continue;                              // (lane 0 of the group took k = 0: it holds x0, x1, xw)
+            const double a0 = r0 + x0, a1 = r1 + x1, a2 = r2 + xw;        // (I + band block) r_B
+            // p_k on the band cell lacks the band correction the tile kernel could not see: add the one it was formed with, then replace it
+            pnew.f[0][lq] += b.dzw[bo];
+            if (two) pnew.f[1][lq] += b.dzw[(size_t)b.nB + bo];
+            const double o0 = b.ca * x0 + b.cb * a0, o1 = b.ca * x1 + b.cb * a1, o2 = b.ca * xw + b.cb * a2;
+            b.dzw[bo] = o0;
+            b.dzw[(size_t)b.nB + bo] = o1;
+            b.dzw[2 * (size_t)b.nB + bo] = o2;
+            v[2] += x0 * o0 + x1 * o1 + xw * o2;
+        }
+    }
+    const int tb = HB == 0 ? (int)blockIdx.x : (int)blockIdx.x - HB, nt = HB == 0 ? (int)gridDim.x : (int)gridDim.x - HB;
+    for (int it = tb; it >= 0 && it < I.n; it += nt) {
+        const TileRec R = I.rec[it];
+        const int f = R.f;
+        const bool hasE = f < 2 && (I.uni[it] & 8) != 0;
+        const double *__restrict__ qf = f == 0 ? qv.f[0] : (f == 1 ? qv.f[1] : qv.f[2]);
+        const double *__restrict__ ro = f == 0 ? rold.f[0] : (f == 1 ? rold.f[1] : rold.f[2]);
+        double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
+        long long i[FU], iq[FU]; bool ok[FU]; double vv[FU], rv[FU];
+#pragma unroll
+        for (int k = 0; k < FU; ++k) {
+            ok[k] = tile_cell(I, R, k, i[k], iq[k]);
+            if (ok[k]) { vv[k] = qf[iq[k]]; rv[k] = ro[iq[k]]; }
+        }
+        if (hasE) {
+#pragma unroll
+            for (int k = 0; k < FU; ++k)
+                if (ok[k]) {
+                    const int e = b.eord[i[k]];
+                    if (e >= 0) vv[k] += b.ya[(size_t)f * ES + e];
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < FU; ++k)
+            if (ok[k]) {
+                const double rn = fma(-alpha, vv[k], rv[k]);
+                rf[iq[k]] = rn;
+                v[0] += rn * rn;
+            }
+    }
+    v[1] = v[0];
+    block_reduce_publish<3>(v, partials, res + sl_new, counter);
+}
 // skipped iteration: carry the whole (rho, rr, rho_band, rho_poly_band) group forward (the fused iteration has no kf_cg_p to do it)
 __global__ void kf2_carry(double *res, int sl_old, int sl_new, StopCrit stop)
 {
@@ -337,6 +464,78 @@ __global__ void __launch_bounds__(FCH) kf2_xflush(Items I, const double *res, FV
 //     is formed on the fly for the cell and its neighbours (a column of FU + 2 values per thread is shared along the k direction).
 // General tiles (interface band, border ring, partial tiles) keep kf2_apply; they run beside this kernel on the second stream.
 // =================================================================================================================================
+// apply head (see BandHead): groups of LPC lanes walk the E list; `gtid` / `nthr` = index / number of the threads of the whole grid that run heads
+template <int N, int LPC>
+__device__ __forceinline__ void f3_band_head(const F2Args &A, double alpha, double beta, double &sig, int gtid, int nthr)
+{
+    const BandHead &b = A.bh;
+    if (b.nE <= 0) return;
+    const size_t ES = (size_t)b.nEp;
+    const bool two = b.nbulk > 1;
+    const int sub = gtid % LPC, gid = gtid / LPC, ngroups = nthr / LPC;
+    const int rounds = (b.nE + ngroups - 1) / ngroups;
+    const double *__restrict__ z0 = A.a.f[0], *__restrict__ z1 = A.a.f[1], *__restrict__ zw = A.a.f[2];
+    const double *__restrict__ q0 = A.pold.f[0], *__restrict__ q1 = A.pold.f[1], *__restrict__ qw = A.pold.f[2];
+    const double *__restrict__ dz = b.dzw;
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int e_raw = rd * ngroups + gid;
+        const bool live = e_raw < b.nE;
+        const int e = live ? e_raw : b.nE - 1;      // (groups past the end redo the last cell: the shuffles are warp-wide)
+        const long long lq = bh_q(b, b.Ecell[e]);
+        const int bo = b.EB[e];
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, x0 = 0.0, x1 = 0.0, xw = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < 1 + 2 * N; k0 += LPC) {
+            const int k = k0 + sub;
+            if (LPC > 1 && k >= 1 + 2 * N) break;
+            long long ln = lq;
+            int nb = bo;
+            if (k > 0) {
+                const int kk = k - 1, d = kk >> 1;
+                ln = (kk & 1) ? lq + b.sq[d] : lq - b.sq[d];
+                nb = b.EnbrB[(size_t)kk * ES + e];
+            }
+            const bool nonzero = k == 0 ? bo >= 0 : (bo >= 0 || nb >= 0);     // (kf_blocks: other blocks are exactly zero)
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (nonzero || k == 0) {
+                v0 = fma(beta, q0[ln], z0[ln]);
+                if (two) v1 = fma(beta, q1[ln], z1[ln]);
+                if (nb >= 0) {
+                    const double e0 = dz[nb], e1 = two ? dz[(size_t)b.nB + nb] : 0.0;
+                    v0 += e0; v1 += e1;
+                    v2 = fma(beta, qw[nb], zw[nb] + dz[2 * (size_t)b.nB + nb]);
+                    if (k == 0) { d0 = e0; d1 = e1; }
+                }
+            }
+            if (k == 0) { x0 = v0; x1 = v1; xw = v2; }
+            if (nonzero) {
+                const double *__restrict__ c = b.Eblk + (size_t)(k * 9) * ES + e;
+                r0 += c[0] * v0 + c[ES] * v1 + c[2 * ES] * v2;
+                r1 += c[3 * ES] * v0 + c[4 * ES] * v1 + c[5 * ES] * v2;
+                r2 += c[6 * ES] * v0 + c[7 * ES] * v1 + c[8 * ES] * v2;
+            }
+        }
+        if (LPC > 1) {
+#pragma unroll
+            for (int o = LPC / 2; o > 0; o >>= 1) {
+                r0 += __shfl_xor_sync(0xffffffffu, r0, o, LPC); r1 += __shfl_xor_sync(0xffffffffu, r1, o, LPC); r2 += __shfl_xor_sync(0xffffffffu, r2, o, LPC);
+            }
+        }
+        if (sub != 0 || !live) continue;       // (lane 0 of the group took k = 0: it holds x0, x1, xw, d0, d1)
+        // bulk rows: the tile kernel writes v = p' (band cell: its dense couplings are zero, p' = p_k - dz) or the dense stencil (fringe cell)
+        b.ya[e] = d0 + r0;
+        if (two) b.ya[ES + e] = d1 + r1;
+        sig += d0 * (x0 - d0) + d1 * (x1 - d1) + x0 * (d0 + r0) + x1 * (d1 + r1);
+        if (bo >= 0) {
+            const double yw = xw + r2;
+            A.y.f[2][bo] = yw;
+            A.pnew.f[2][bo] = xw;
+            A.xs.f[2][bo] += alpha * qw[bo];
+            sig += xw * yw;
+        }
+    }
+}
+
 struct alignas(64) F3Maps { CUtensorMap a[2], b[2], t[2]; };   // boxes of the staged vector and of p_{k-1}; tile (no halo) of x (MODE 5) / aux (MODE 2, 4)
 struct F3Hdr {
     long long baseq, base;            // tile origin in the re-pitched Krylov vectors / in the reference-pitch arrays (coefficients, band map)
@@ -350,7 +549,8 @@ template <int N> struct F3Tile { static constexpr int BYTES = FTILE * 8; };
 __device__ __forceinline__ void f3_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 // has_t: the third map is valid (MODE 5 always; MODE 2 / 4: aux is a vector of its own -- otherwise aux == the staged vector)
-template <int N, int MODE, int S>
+// BH: 0 no band head; 1, 2: apply head with that many lanes per band / fringe cell (MODE 5, one rank)
+template <int N, int MODE, int S, int BH = 0>
 __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__ F3Maps maps, Items I, F2Args A, int has_t, int dbg)
 {
     using B = F2Box<N>;
@@ -411,6 +611,7 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
             alpha = A.res[FS_XPEND] != 0.0 ? A.res[FS_ALPHA] : 0.0;
             beta = safe_div(rho_at(A.res, A.sl_cur), rho_at(A.res, A.sl_old));
         }
+        if (BH > 0 && MODE == 5) f3_band_head<N, BH>(A, alpha, beta, v[0], (int)blockIdx.x * FCH + tid, (int)gridDim.x * FCH);   // (the producer is already prefetching tiles)
         constexpr int TYM = N == 2 ? FU : 1, SY = B::BX, SZ = B::BX * B::BY;
         constexpr int SK = N == 2 ? SY : SZ;                  // box stride of the k direction (the FU cells of a thread)
         const int ty = wid;

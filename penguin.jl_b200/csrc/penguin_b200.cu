@@ -946,6 +946,16 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         CUDA_TRY(ctx, cudaMalloc((void **)&F.Eblk, sizeof(double) * (1 + 2 * g.N) * 9 * nE));
         CUDA_TRY(ctx, cudaMalloc((void **)&F.Efix, nE));
         d.EB = F.EB; d.EnbrB = F.EnbrB; d.Eblk = F.Eblk; d.Efix = F.Efix;
+        if (ctx->nranks == 1) {   // band heads of the fused iteration (fold2.cuh): cell -> E index, band cell -> E index, band couplings of the bulk rows
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.eord, sizeof(int) * (size_t)g.nloc));
+            CUDA_TRY(ctx, cudaMemsetAsync(F.eord, 0xFF, sizeof(int) * (size_t)g.nloc, ctx->stream));
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.EofB, sizeof(int) * (size_t)(d.nB > 0 ? d.nB : 1)));
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.EnbrE, sizeof(int) * 2 * g.N * nE));
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.ya, sizeof(double) * 2 * nE));
+            CUDA_TRY(ctx, cudaMemsetAsync(F.ya, 0, sizeof(double) * 2 * nE, ctx->stream));
+            if (d.nE) { kf_eord_fill<<<(d.nE + 255) / 256, 256, 0, ctx->stream>>>(d.nE, F.Ecell, F.bord, F.eord, F.EofB); LAUNCH_CHECK(ctx); }
+            d.eord = F.eord; d.EofB = F.EofB; d.ya = F.ya; d.EnbrE = F.EnbrE;
+        }
         if (d.nEp == 0) d.nEp = 32;
         {   // local planes of the slab dimension whose tiles are interior class (fused kernel): see kf_tile_records (ghost flag)
             const int Tsd = g.N == 1 ? FTILE : (g.N == 2 ? 32 : 4);
@@ -964,6 +974,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
     if (d.has_w && d.nE > 0) {
         DISPATCH_N(g.N, (kf_blocks<N><<<(d.nE + 127) / 128, 128, 0, ctx->stream>>>(g, d)));
         LAUNCH_CHECK(ctx);
+        if (F.EnbrE) { kf_enbre_fill<<<(d.nE + 255) / 256, 256, 0, ctx->stream>>>(g, d.nE, d.nEp, F.Ecell, F.EnbrB, F.eord, F.EnbrE); LAUNCH_CHECK(ctx); }
     }
     // active tile list + per-tile coefficient census
     {
@@ -1308,6 +1319,33 @@ static int fold_maps3(pb200_solver *s, const FVec &a, const FVec *b, const FVec 
     if (s->F.d.nbulk == 1) { out->a[1] = out->a[0]; out->b[1] = out->b[0]; out->t[1] = out->t[0]; }
     return PB200_OK;
 }
+// one-wave grid of the pipelined kernel (MODE 5) on list L
+template <int N>
+static int fold3_grid5(pb200_solver *s, const Items &L)
+{
+    constexpr int S = N == 2 ? 3 : 2;
+    constexpr int smem = S * (2 * F2Box<N>::SLOT + FTILE * 8) + 128;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf3_apply<N, 5, S>, FCH + 32, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    int grid = L.n < s->ctx->sm_count * nb ? L.n : s->ctx->sm_count * nb;
+    return grid < 1 ? 1 : grid;
+}
+template <int N, int BH>
+static int fold3_launch_bh(pb200_solver *s, const Items &L, const F3Maps &maps, const F2Args &A, cudaStream_t st)
+{
+    pb200_ctx *ctx = s->ctx;
+    constexpr int S = N == 2 ? 3 : 2;
+    constexpr int smem = S * (2 * F2Box<N>::SLOT + FTILE * 8) + 128;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<N, 5, S, BH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set[ctx->device & 63] = true; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf3_apply<N, 5, S, BH>, FCH + 32, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    int grid = L.n < ctx->sm_count * nb ? L.n : ctx->sm_count * nb;
+    if (grid < 1) grid = 1;
+    kf3_apply<N, 5, S, BH><<<grid, FCH + 32, smem, st>>>(maps, L, A, 1, 0);
+    LAUNCH_CHECK(ctx);
+    return PB200_OK;
+}
 template <int N, int MODE>
 static int fold3_launch(pb200_solver *s, const Items &L, const F3Maps &maps, const F2Args &A, int has_t, cudaStream_t st)
 {
@@ -1572,6 +1610,20 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         }
         // The kernels test the residual themselves (fold_done) and fall through once it is below the tolerance, so `check_every`
         // iterations are queued between two host looks; FS_ITERS counts the iterations that really ran.
+        // band heads (fold2.cuh): the two O(band) launches of the iteration folded into the streaming kernels -- one rank, pipelined kernel, band preconditioner,
+        // SMALL bands (2-D problems: the separate launches are pure latency there; on the large bands of 3-D problems they are bandwidth work and were
+        // measured equal either way -- 1024 x 1024 x 128 diphasic: 68.3 vs 68.2 ms per step)
+        const bool bandfuse = cg && fused && prec && ctx->nranks == 1 && F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED") && F.d.eord != nullptr && F.d.nE > 0 && (band_lpc(F.d.nE) == 8 || getenv("PB200_BANDFUSE_ALWAYS")) && !getenv("PB200_NO_BANDFUSE");
+        if (bandfuse && !F.have_r2) { if ((rc = fold_alloc_vec(s, &F.r2))) return rc; F.have_r2 = true; }
+        BandHead bhd;
+        memset(&bhd, 0, sizeof(bhd));
+        if (bandfuse) {
+            bhd.on = 1; bhd.nE = F.d.nE; bhd.nEp = F.d.nEp; bhd.nB = F.d.nB; bhd.nbulk = F.d.nbulk;
+            bhd.Ecell = F.d.Ecell; bhd.EB = F.d.EB; bhd.EnbrB = F.d.EnbrB; bhd.EnbrE = F.d.EnbrE; bhd.EofB = F.d.EofB; bhd.eord = F.d.eord; bhd.Eblk = F.d.Eblk;
+            bhd.ya = F.d.ya; bhd.dzw = F.dz; bhd.ld0 = F.d.ld0; bhd.dP = F.d.dP;
+            for (int dd = 0; dd < PB_MAXD; ++dd) bhd.sq[dd] = F.d.sq[dd];
+            bhd.ca = F.pa0 - 1.0; bhd.cb = F.pa1;
+        }
         auto enqueue = [&](int curp) -> int {   // one Krylov iteration reading pair `curp`, publishing pair curp ^ 1
             const int nxt = curp ^ 1;
             StopCrit st = {o.rtol * o.rtol, o.atol * o.atol, FS_TRIPLE(curp) + 1};
@@ -1580,13 +1632,15 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
             if (cg && fused) {
                 const bool multi = ctx->nranks > 1;
                 const FVec &pold = curp ? F.p2 : F.p, &pnew = curp ? F.p : F.p2;    // iteration j reads P[j & 1], writes P[(j + 1) & 1]
-                const FVec &zsrc = poly ? F.zz : F.r;
+                const FVec &rold = bandfuse && curp ? F.r2 : F.r, &rnew = bandfuse && !curp ? F.r2 : F.r;   // band heads: r double-buffered like p
+                const FVec &zsrc = poly ? F.zz : rold;
                 // The second stream exists to overlap the HALO EXCHANGE with the interior tiles.  On one rank the side work is the pointwise update of
                 // the interface unknowns only, and running it beside the staged kernel cost more than it hid (512^3 diphasic: 85 vs 65 ms per step).
                 cudaStream_t st2 = (ctx->profile || !multi || getenv("PB200_DBG_SERIAL")) && !getenv("PB200_DBG_FORK") ? ctx->stream : ctx->stream2;
-                const bool side = F.IG1.n > 0 || multi;
+                const bool side = (F.IG1.n > 0 || multi) && !bandfuse;
                 F2Args A;
                 memset(&A, 0, sizeof(A));
+                A.bh = bhd;
                 A.a = zsrc; A.pold = pold; A.y = F.v; A.pnew = pnew; A.xs = F.x; A.aux = F.v;
                 A.dz = prec ? F.dz : nullptr; A.bord = F.bord; A.nB = F.d.nB;
                 A.sl_old = FS_TRIPLE(nxt); A.sl_cur = FS_TRIPLE(curp); A.stop = st; A.res = res;
@@ -1608,7 +1662,16 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 const bool split = F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED");     // interior class: pipelined kernel on the constant-coefficient tiles + general kernel on the rest (beside it)
                 prof_mark(ctx, PB_PROF_APPLY);
                 ctx->apply_launches++;
-                if (split) {   // one pipelined launch: constant-coefficient interior tiles and general tiles alike
+                if (bandfuse) {   // the same launch with the apply head
+                    F3Maps m3;
+                    if ((rc2 = fold_maps3(s, zsrc, &pold, &F.x, &m3))) return rc2;
+                    const int N3 = s->g.N;
+                    const int g5 = N3 == 2 ? fold3_grid5<2>(s, F.IA) : fold3_grid5<3>(s, F.IA);
+                    const bool two_lanes = (long long)F.d.nE * 2 <= (long long)g5 * FCH;
+                    if (N3 == 2) rc2 = two_lanes ? fold3_launch_bh<2, 2>(s, F.IA, m3, A, ctx->stream) : fold3_launch_bh<2, 1>(s, F.IA, m3, A, ctx->stream);
+                    else rc2 = two_lanes ? fold3_launch_bh<3, 2>(s, F.IA, m3, A, ctx->stream) : fold3_launch_bh<3, 1>(s, F.IA, m3, A, ctx->stream);
+                    if (rc2) return rc2;
+                } else if (split) {   // one pipelined launch: constant-coefficient interior tiles and general tiles alike
                     F3Maps m3;
                     if ((rc2 = fold_maps3(s, zsrc, &pold, &F.x, &m3))) return rc2;
                     if ((rc2 = fold3_apply(s, multi ? F.IAi_all : F.IA, m3, A, 5, 1, ctx->stream))) return rc2;
@@ -1655,6 +1718,20 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                     CUDA_TRY(ctx, cudaMemcpy(dbg2, res + 29, sizeof(dbg2), cudaMemcpyDeviceToHost));
                     { double bad; CUDA_TRY(ctx, cudaMemcpy(&bad, res + 28, sizeof(double), cudaMemcpyDeviceToHost)); if (bad != 0.0) fprintf(stderr, "[pb200] BOUNDS violation code %g\n", bad); }
                     fprintf(stderr, "[pb200] check kf3: header mismatches %g, staged-box mismatches %g, v vs global recompute mismatches %g (cumulative)\n", dbg2[1], dbg2[2], dbg2[0]);
+                }
+                if (bandfuse) {
+                    prof_mark(ctx, PB_PROF_UPDATE);
+                    // head blocks (small bands only: see bandfuse): an eighth of the wave, 8 lanes per band cell
+                    const int gw = s->g.N == 2 ? wave_grid(s, kf2_update_b<2, 8>) : wave_grid(s, kf2_update_b<3, 8>);
+                    int HB = getenv("PB200_BANDFUSE_HB") ? atoi(getenv("PB200_BANDFUSE_HB")) : gw / 8;
+                    if (HB > gw / 2) HB = gw / 2;
+                    if (gw < 8) HB = 0;
+#define K2B(N_) kf2_update_b<N_, 8><<<gw, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, rold, rnew, pnew, bhd, HB, ctx->d_partials, ctx->d_counter, st)
+                    if (s->g.N == 2) K2B(2); else K2B(3);
+#undef K2B
+                    LAUNCH_CHECK(ctx);
+                    prof_mark(ctx, PB_PROF_UPDATE);
+                    return PB200_OK;
                 }
                 if (F.d.has_w) {     // band part of v = M^ p_k (needs p_k everywhere)
                     prof_mark(ctx, PB_PROF_BAPPLY);
@@ -1718,7 +1795,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         auto even_up = [](int v) { return v < 2 ? 2 : (v + 1) & ~1; };
         const int first_chunk = even_up(F.last_iters > 0 ? F.last_iters + 1 : o.check_every);
         const int later_chunk = even_up(o.check_every < 4 ? o.check_every : 4);
-        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen + 1024.0 * F.poly_m + (fused ? 4096.0 : 0.0), o.rtol + F.poly_lo, o.atol + F.poly_hi, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
+        const double gkey[5] = {(double)method + 16.0 * ctx->p2p_gen + 1024.0 * F.poly_m + (fused ? 4096.0 : 0.0) + (bandfuse ? 8192.0 : 0.0), o.rtol + F.poly_lo, o.atol + F.poly_hi, prec ? F.pa0 : 0.0, prec ? F.pa1 : 0.0};
         if (use_graph && memcmp(gkey, F.graph_key, sizeof(gkey)) != 0) {
             for (auto &kv : F.graphs) cudaGraphExecDestroy(kv.second.exec);
             F.graphs.clear();
