@@ -54,6 +54,11 @@ struct FoldDev {
     const int *eord;       // [nloc] index of a cell in the E list (band + fringe cells), -1 elsewhere
     const int *EofB;       // [nB]   E index of band cell k
     const int *EnbrE;      // [2N][nEp] E index of the face neighbours that are band cells (-1: not a band cell), beside EnbrB
+    // the same rows indexed by BAND cell (update head: one dependent load less per gather)
+    const long long *Bq;   // [nB] re-pitched index of band cell k
+    const int *Bidx;       // [(1 + 4N)][nBp]: row 0 E index of the cell, rows 1 + kk band index of neighbour kk, rows 1 + 2N + kk its E index
+    const double *Bblk;    // [(1+2N)*9][nBp] copy of the cell's Eblk rows
+    int nBp;
     double *ya;            // [2][nEp] band-coupling part of v = M^ p on the bulk rows of the E cells (the tile kernel writes the dense part to v)
     int nEp;         // nE rounded up to a multiple of 32
     // Krylov vectors (FVec bulk fields) live in a RE-PITCHED copy of the local grid: x rows padded from ld0 (the reference's odd n+1) to P0,
@@ -92,6 +97,7 @@ struct __align__(16) TileRec {
 };
 struct Items {
     const int *it; int n;
+    int run;                       // kf3_apply: items are handed to the blocks in runs of this many consecutive items (0 / 1: item by item), see f3_item
     const TileRec *rec;            // [n]
     int shx;                       // log2 of the thread extent in x: 8 (1-D, w items use this layout too) or 5
     int kx, ky, kz;                // tile-relative coordinate advance per k: (256,0,0) 1-D, (0,1,0) 2-D, (0,0,1) 3-D
@@ -813,6 +819,22 @@ __global__ void __launch_bounds__(256) kf_apply_band(Grid g, FoldDev fd, FVec x,
     if (MODE == 3) block_reduce_publish<2>(v, partials, results, counter);
 }
 
+// band-indexed copies of the E arrays (update head of the fused iteration)
+__global__ void kf_band_index(Grid g, FoldDev fd, long long *Bq, int *Bidx, double *Bblk, int nBp)
+{
+    const int NK = 1 + 2 * g.N;
+    for (int bo = blockIdx.x * blockDim.x + threadIdx.x; bo < fd.nB; bo += gridDim.x * blockDim.x) {
+        const int e = fd.EofB[bo];
+        Bq[bo] = fd_q(fd, fd.Ecell[e]);
+        Bidx[bo] = e;
+        for (int kk = 0; kk < 2 * g.N; ++kk) {
+            Bidx[(size_t)(1 + kk) * nBp + bo] = fd.EnbrB[(size_t)kk * fd.nEp + e];
+            Bidx[(size_t)(1 + 2 * g.N + kk) * nBp + bo] = fd.EnbrE[(size_t)kk * fd.nEp + e];
+        }
+        for (int j = 0; j < NK * 9; ++j) Bblk[(size_t)j * nBp + bo] = fd.Eblk[(size_t)j * fd.nEp + e];
+    }
+}
+
 // ---- band preconditioner -------------------------------------------------------------------------------------------------------
 // The spectrum of M^ is the bulk interval [1/(1+2N theta dt/h^2 ...)] plus a few low modes localised on neighbouring cut cells (their w
 // unknowns are coupled across faces; tests/experiments/krylov_experiment3.py).  They are removed by a low-degree Chebyshev polynomial of the band
@@ -1196,7 +1218,9 @@ struct FoldSys {
     int *bord = nullptr, *EB = nullptr, *EnbrB = nullptr, *items = nullptr;
     double *Linv = nullptr, *Eblk = nullptr;
     unsigned char *Efix = nullptr;
-    int *eord = nullptr, *EofB = nullptr, *EnbrE = nullptr;   // band heads of the fused iteration (fold2.cuh)
+    int *eord = nullptr, *EofB = nullptr, *EnbrE = nullptr, *Bidx = nullptr;   // band heads of the fused iteration (fold2.cuh)
+    long long *Bq = nullptr;
+    double *Bblk = nullptr;
     double *ya = nullptr;
     int nitems = 0;
     unsigned char *uni = nullptr;
@@ -1220,7 +1244,8 @@ struct FoldSys {
     std::vector<void *> list_mem;           // device arrays behind the sub-lists
     FVec x, b, r, p, v, r0, s, t, z;
     FVec p2 = {}, zz = {};                  // fused iteration: second search-direction buffer, preconditioned residual (polynomial)
-    FVec r2 = {};                           // band heads: second residual buffer (r is double-buffered by iteration parity)
+    FVec r2 = {};                           // band heads: r2.f[2] is the second buffer of the interface part of r; r2.f[0], r2.f[1] alias r (never freed through r2)
+    double *rE = nullptr;                   // band heads: [2 parities][2][nEp] compact copy of r on the E cells
     bool have_p2 = false, have_zz = false, have_r2 = false;
     bool tma_ok = false;                    // the Krylov vectors are describable to TMA (fold2.cuh)
     bool pipe = false;                      // ... and the interior constant-coefficient tiles go through the pipelined kernel (kf3_apply)
@@ -1246,10 +1271,13 @@ static void fold_free(FoldSys &F)
     if (F.EnbrB) cudaFree(F.EnbrB); if (F.items) cudaFree(F.items); if (F.Linv) cudaFree(F.Linv); if (F.Eblk) cudaFree(F.Eblk);
     if (F.Efix) cudaFree(F.Efix); F.Efix = nullptr;
     if (F.eord) cudaFree(F.eord); if (F.EofB) cudaFree(F.EofB); if (F.ya) cudaFree(F.ya); if (F.EnbrE) cudaFree(F.EnbrE); F.eord = F.EofB = F.EnbrE = nullptr; F.ya = nullptr;
+    if (F.Bidx) cudaFree(F.Bidx); if (F.Bq) cudaFree(F.Bq); if (F.Bblk) cudaFree(F.Bblk); F.Bidx = nullptr; F.Bq = nullptr; F.Bblk = nullptr;
     F.Bcell = F.Ecell = nullptr; F.bord = F.EB = F.EnbrB = F.items = nullptr; F.Linv = F.Eblk = nullptr;
     for (void *m : F.list_mem) cudaFree(m);
     F.list_mem.clear();
     F.tmaps.clear();
+    F.r2.f[0] = F.r2.f[1] = nullptr;        // (aliases of r)
+    if (F.rE) cudaFree(F.rE); F.rE = nullptr;
     FVec *vs[] = {&F.x, &F.b, &F.r, &F.p, &F.v, &F.r0, &F.s, &F.t, &F.z, &F.p2, &F.zz, &F.r2};
     for (FVec *a : vs) fold_free_vec(*a);
     F.built = false; F.have_bicg = false; F.have_z = false; F.have_p2 = false; F.have_zz = false; F.have_r2 = false; F.tma_ok = false;

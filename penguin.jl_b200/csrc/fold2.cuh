@@ -53,6 +53,23 @@ __device__ __forceinline__ void f2_tma_load_3d(uint32_t dst, const CUtensorMap *
                  : "memory");
 }
 
+// the same copies with an L2 eviction policy (createpolicy) attached
+__device__ __forceinline__ void f2_tma_load_2d_h(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+                 "l"((unsigned long long)m), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void f2_tma_load_3d_h(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+                 "l"((unsigned long long)m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long f2_policy_evict_last() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ unsigned long long f2_policy_evict_first() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void f2_st_hint(double *a, double v, unsigned long long pol) { asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory"); }
+
 template <int N> struct F2Box {
     // x extent 36 = tile 32 + TWO cells on either side: the innermost TMA coordinate must be 16-byte aligned (measured on B200: a box of
     // doubles starting at an odd x raises "illegal instruction", tests/experiments/tma_box_probe.cu), so the box starts at x0 - 2
@@ -70,13 +87,14 @@ struct alignas(64) F2Maps { CUtensorMap a[2]; CUtensorMap b[2]; };   // per bulk
 //   * apply head: gathers p_k on a band cell and its neighbours as z + beta p_{k-1} (+ dz on band cells) from the INPUTS of the launch, writes
 //     the band couplings of the bulk rows to the compact array ya (the tile part writes the dense part to v: no read-modify-write between blocks),
 //     the w rows of v, p_k and x on the interface unknowns (kf2_pupd is gone), and adds its share of (p_k, v) to the block's partial sum;
-//   * update head: r is double-buffered by iteration parity, so the head forms r_k = r_{k-1} - alpha (v + ya) on a band cell and its band
-//     neighbours from the OLD residual while other blocks write the new one, applies the band polynomial (dz, rho_band) and adds the previous dz
-//     to p_k on the band cells (the tile kernel formed p_k without it).
+//   * update head: the residual on the E cells and on the interface unknowns is kept in compact arrays with two buffers by iteration parity, so
+//     the head forms r_k = r_{k-1} - alpha (v + ya) on a band cell and its band neighbours from the OLD values while other blocks write the new
+//     ones, applies the band polynomial (dz, rho_band) and adds the previous dz to p_k on the band cells (the tile kernel formed p_k without it).
 struct BandHead {
     int on, nE, nEp, nB, nbulk;
     const long long *Ecell; const int *EB, *EnbrB, *EnbrE, *EofB, *eord;
     const double *Eblk;
+    const long long *Bq; const int *Bidx; const double *Bblk; int nBp;      // band-indexed copies (update head)
     double *ya, *dzw;
     long long ld0, dP, sq[PB_MAXD];
     double ca, cb;          // band polynomial: dz = ca r_B + cb M^_BB r_B
@@ -94,6 +112,7 @@ struct F2Args {
     const double *res;
     int accumulate;                               // the published dot product is ADDED to the slot (a second launch of the same apply)
     int dbg;                                      // debugging switches (PB200_DBG_F3)
+    int l2hint;                                   // L2 eviction hints of the pipelined kernel: 1 boxes evict_last, 2 x tile evict_first, 4 stores evict_first
     const double *off[2][PB_MAXD];                // coefficient arrays of the tiles without constants (reference pitch)
 };
 // debugging: record an out-of-range index (code = kernel * 100 + site) in res[28] and SKIP the access
@@ -322,13 +341,23 @@ __global__ void __launch_bounds__(FCH) kf2_update(Items I, double *res, int sl_r
     v[1] = v[0];
     block_reduce_publish<2>(v, partials, res + sl_new, counter);
 }
-// Residual update of the fused iteration WITH the update head (see BandHead): reads r_{k-1} from `rold`, writes r_k to `r` (two buffers, by
-// iteration parity), v = qv + ya on the E cells; publishes (rho, rr, rho_band).
+// compact copy of the residual on the E cells (both parity buffers), once per solve
+__global__ void kf2_gather_rE(BandHead b, FVec r, double *rE0, double *rE1)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < b.nE; e += gridDim.x * blockDim.x) {
+        const long long lq = bh_q(b, b.Ecell[e]);
+        for (int f = 0; f < b.nbulk; ++f) { const double v = r.f[f][lq]; rE0[(size_t)f * b.nEp + e] = v; rE1[(size_t)f * b.nEp + e] = v; }
+    }
+}
+// Residual update of the fused iteration WITH the update head (see BandHead).  The dense residual is updated IN PLACE (a second dense buffer
+// pushed the iteration's working set at 2048^2 from 170 to 204 MB against 126 MB of L2: 23 -> 32 us); what the head reads of r_{k-1} while other
+// blocks overwrite it -- the bulk entries of the E cells and the interface unknowns -- lives in compact arrays with two buffers by iteration
+// parity (rEold / rEnew, rold.f[2] / r.f[2]).  v = qv + ya on the E cells; publishes (rho, rr, rho_band).
 // HB > 0: the first HB blocks of the grid run the head (one thread per band cell) and nothing else, the others stream the tiles meanwhile -- with
 // every block running its share of the head first, nothing streamed during the head's dependent gathers (2048^2: 23 -> 33 us).  HB = 0: every block does both.
 template <int N, int LPC>
-__global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int sl_rho, int sl_new, FVec qv, FVec rold, FVec r, FVec pnew, BandHead b, int HB,
-                                                       double *partials, unsigned *counter, StopCrit stop)
+__global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int sl_rho, int sl_new, FVec qv, FVec rold, FVec r, const double *__restrict__ rEold,
+                                                       double *__restrict__ rEnew, FVec pnew, BandHead b, int HB, double *partials, unsigned *counter, StopCrit stop)
 {
     if (fold_done(res, stop)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; res[sl_new + 3] = res[sl_rho + 3]; }
@@ -349,8 +378,10 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
             const int bo_raw = rd * ngroups + gid;
             const bool live = bo_raw < b.nB;
             const int bo = live ? bo_raw : b.nB - 1;        // (groups past the end redo the last cell: the shuffles are warp-wide)
-            const int e = b.EofB[bo];
-            const long long lq = bh_q(b, b.Ecell[e]);
+            const size_t BS = (size_t)b.nBp;
+            const int e = b.Bidx[bo];
+            const long long lq = b.Bq[bo];
+            const double dz0 = b.dzw[bo], dz1 = two ? b.dzw[(size_t)b.nB + bo] : 0.0;      // (lane 0 needs them after the reduction: in flight with the rest)
             double r0 = 0.0, r1 = 0.0, r2 = 0.0, x0 = 0.0, x1 = 0.0, xw = 0.0;
 #pragma unroll
             for (int k0 = 0; k0 < 1 + 2 * N; k0 += LPC) {
@@ -361,16 +392,16 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
                 if (k > 0) {
                     const int kk = k - 1, d = kk >> 1;
                     ln = (kk & 1) ? lq + b.sq[d] : lq - b.sq[d];
-                    nb = b.EnbrB[(size_t)kk * ES + e];
-                    en = b.EnbrE[(size_t)kk * ES + e];
+                    nb = b.Bidx[(size_t)(1 + kk) * BS + bo];
+                    en = b.Bidx[(size_t)(1 + 2 * N + kk) * BS + bo];
                 }
                 // branch-free: a neighbour that is no band cell reads this cell's entries and counts with weight 0 (all loads of a lane are in flight together)
                 const double wgt = nb >= 0 ? 1.0 : 0.0;
                 if (nb < 0) { nb = bo; en = e; ln = lq; }
-                const double *__restrict__ c = b.Eblk + (size_t)(k * 9) * ES + e;
-                const double c0 = c[0], c1 = c[ES], c2 = c[2 * ES], c3 = c[3 * ES], c4 = c[4 * ES], c5 = c[5 * ES], c6 = c[6 * ES], c7 = c[7 * ES], c8 = c[8 * ES];
-                const double v0 = wgt * fma(-alpha, qv.f[0][ln] + b.ya[en], rold.f[0][ln]);
-                const double v1 = two ? wgt * fma(-alpha, qv.f[1][ln] + b.ya[ES + en], rold.f[1][ln]) : 0.0;
+                const double *__restrict__ c = b.Bblk + (size_t)(k * 9) * BS + bo;
+                const double c0 = c[0], c1 = c[BS], c2 = c[2 * BS], c3 = c[3 * BS], c4 = c[4 * BS], c5 = c[5 * BS], c6 = c[6 * BS], c7 = c[7 * BS], c8 = c[8 * BS];
+                const double v0 = wgt * fma(-alpha, qv.f[0][ln] + b.ya[en], rEold[en]);
+                const double v1 = two ? wgt * fma(-alpha, qv.f[1][ln] + b.ya[ES + en], rEold[ES + en]) : 0.0;
                 const double v2 = wgt * fma(-alpha, qv.f[2][nb], rold.f[2][nb]);
                 if (k == 0) { x0 = v0; x1 = v1; xw = v2; }
                 r0 += c0 * v0 + c1 * v1 + c2 * v2;
@@ -386,8 +417,8 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
             if (sub != 0 || !live) continue;                              // (lane 0 of the group took k = 0: it holds x0, x1, xw)
             const double a0 = r0 + x0, a1 = r1 + x1, a2 = r2 + xw;        // (I + band block) r_B
             // p_k on the band cell lacks the band correction the tile kernel could not see: add the one it was formed with, then replace it
-            pnew.f[0][lq] += b.dzw[bo];
-            if (two) pnew.f[1][lq] += b.dzw[(size_t)b.nB + bo];
+            pnew.f[0][lq] += dz0;
+            if (two) pnew.f[1][lq] += dz1;
             const double o0 = b.ca * x0 + b.cb * a0, o1 = b.ca * x1 + b.cb * a1, o2 = b.ca * xw + b.cb * a2;
             b.dzw[bo] = o0;
             b.dzw[(size_t)b.nB + bo] = o1;
@@ -403,18 +434,19 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
         const double *__restrict__ qf = f == 0 ? qv.f[0] : (f == 1 ? qv.f[1] : qv.f[2]);
         const double *__restrict__ ro = f == 0 ? rold.f[0] : (f == 1 ? rold.f[1] : rold.f[2]);
         double *__restrict__ rf = f == 0 ? r.f[0] : (f == 1 ? r.f[1] : r.f[2]);
-        long long i[FU], iq[FU]; bool ok[FU]; double vv[FU], rv[FU];
+        long long i[FU], iq[FU]; bool ok[FU]; double vv[FU], rv[FU]; int ee[FU];
 #pragma unroll
         for (int k = 0; k < FU; ++k) {
             ok[k] = tile_cell(I, R, k, i[k], iq[k]);
+            ee[k] = -1;
             if (ok[k]) { vv[k] = qf[iq[k]]; rv[k] = ro[iq[k]]; }
         }
         if (hasE) {
 #pragma unroll
             for (int k = 0; k < FU; ++k)
                 if (ok[k]) {
-                    const int e = b.eord[i[k]];
-                    if (e >= 0) vv[k] += b.ya[(size_t)f * ES + e];
+                    ee[k] = b.eord[i[k]];
+                    if (ee[k] >= 0) vv[k] += b.ya[(size_t)f * ES + ee[k]];
                 }
         }
 #pragma unroll
@@ -422,6 +454,7 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
             if (ok[k]) {
                 const double rn = fma(-alpha, vv[k], rv[k]);
                 rf[iq[k]] = rn;
+                if (hasE && ee[k] >= 0) rEnew[(size_t)f * ES + ee[k]] = rn;      // the compact copy the NEXT update head reads (two buffers by parity)
                 v[0] += rn * rn;
             }
     }
@@ -536,6 +569,12 @@ __device__ __forceinline__ void f3_band_head(const F2Args &A, double alpha, doub
     }
 }
 
+// Which list item a block works on in its n-th round.  run == 1: item n * grid + block (neighbouring items on neighbouring blocks at the same time).
+// run > 1 (3-D lists, sorted so that consecutive items are z / y neighbours): the list is cut into runs of `run` items, run j goes to block j mod grid,
+// so a block walks spatial neighbours back to back and the halo planes its next box shares with the last one are still in L2.  (ncu, 1024 x 1024 x 128:
+// with item-wise striding the boxes were fetched from DRAM 2.1 times over -- blocks drift apart, and a neighbour's box comes tens of microseconds later.)
+__device__ __forceinline__ int f3_item(int n, int run, int grid, int block) { return run <= 1 ? n * grid + block : ((n / run) * grid + block) * run + n % run; }
+
 struct alignas(64) F3Maps { CUtensorMap a[2], b[2], t[2]; };   // boxes of the staged vector and of p_{k-1}; tile (no halo) of x (MODE 5) / aux (MODE 2, 4)
 struct F3Hdr {
     long long baseq, base;            // tile origin in the re-pitched Krylov vectors / in the reference-pitch arrays (coefficients, band map)
@@ -576,13 +615,15 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
         if (lane == 0) {
             const bool use_t = TT && (MODE == 5 || has_t);
             const uint32_t bytes = NBX * B::BYTES + (use_t ? F3Tile<N>::BYTES : 0);
+            const unsigned long long pol_last = f2_policy_evict_last(), pol_first = f2_policy_evict_first();
             int n = 0;
             TileRec Rn;
-            if ((int)blockIdx.x < I.n) Rn = I.rec[blockIdx.x];
-            for (int it = blockIdx.x; it < I.n; it += gridDim.x, ++n) {
+            const int G = (int)gridDim.x, bk = (int)blockIdx.x;
+            if (f3_item(0, I.run, G, bk) < I.n) Rn = I.rec[f3_item(0, I.run, G, bk)];
+            for (int it = f3_item(0, I.run, G, bk); it < I.n; it = f3_item(++n, I.run, G, bk)) {
                 const TileRec R = Rn;
                 const double c0 = I.ucoef[(size_t)it * PB_MAXD], c1 = I.ucoef[(size_t)it * PB_MAXD + 1], c2 = I.ucoef[(size_t)it * PB_MAXD + 2];
-                if (it + (int)gridDim.x < I.n) Rn = I.rec[it + gridDim.x];      // next record: in flight while this tile is issued
+                { const int nx = f3_item(n + 1, I.run, G, bk); if (nx < I.n) Rn = I.rec[nx]; }      // next record: in flight while this tile is issued
                 const int s = n % S, k = n / S;
                 if (k > 0) f2_mbar_wait(eb + 8 * s, (uint32_t)((k - 1) & 1));      // the consumers have released the stage's previous tile
                 F3Hdr h;
@@ -594,13 +635,22 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 f2_mbar_expect_tx(bar, bytes);                                       // (release: the header is visible to whoever passes the barrier)
                 const int fi = R.f == 0 ? 0 : 1;
-                if (N == 2) f2_tma_load_2d(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1); else f2_tma_load_3d(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
-                if (MODE == 5) {
-                    if (N == 2) f2_tma_load_2d(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1);
-                    else f2_tma_load_3d(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
+                if (A.l2hint & 1) {
+                    if (N == 2) f2_tma_load_2d_h(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1, pol_last); else f2_tma_load_3d_h(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1, pol_last);
+                    if (MODE == 5) {
+                        if (N == 2) f2_tma_load_2d_h(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1, pol_last);
+                        else f2_tma_load_3d_h(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1, pol_last);
+                    }
+                } else {
+                    if (N == 2) f2_tma_load_2d(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1); else f2_tma_load_3d(dst, &maps.a[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
+                    if (MODE == 5) {
+                        if (N == 2) f2_tma_load_2d(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1);
+                        else f2_tma_load_3d(dst + B::SLOT, &maps.b[fi], bar, R.ox - B::HX, R.oy - 1, R.oz - 1);
+                    }
                 }
                 if (use_t) {
-                    if (N == 2) f2_tma_load_2d(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy); else f2_tma_load_3d(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy, R.oz);
+                    if (A.l2hint & 2) { if (N == 2) f2_tma_load_2d_h(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy, pol_first); else f2_tma_load_3d_h(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy, R.oz, pol_first); }
+                    else { if (N == 2) f2_tma_load_2d(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy); else f2_tma_load_3d(dst + NBX * B::SLOT, &maps.t[fi], bar, R.ox, R.oy, R.oz); }
                 }
             }
         }
@@ -616,8 +666,9 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
         constexpr int SK = N == 2 ? SY : SZ;                  // box stride of the k direction (the FU cells of a thread)
         const int ty = wid;
         const bool use_t = TT && (MODE == 5 || has_t);
+        const unsigned long long pol_st = f2_policy_evict_first();
         int n = 0;
-        for (int it = blockIdx.x; it < I.n; it += gridDim.x, ++n) {
+        for (int it = f3_item(0, I.run, (int)gridDim.x, (int)blockIdx.x); it < I.n; it = f3_item(++n, I.run, (int)gridDim.x, (int)blockIdx.x)) {
             const int s = n % S, k0 = n / S;
             f2_mbar_wait(fb + 8 * s, (uint32_t)(k0 & 1));
             const F3Hdr h = hdr[s];
@@ -732,9 +783,12 @@ __global__ void __launch_bounds__(FCH + 32, 2) kf3_apply(const __grid_constant__
                 for (int k = 0; k < FU; ++k) {
                     const long long q = q0 + (long long)k * I.ustrideq;
                     const double pold = sB[b0 + k * SK], xo = (dbg & 1) ? xf[q] : sT[t0 + k * TK];
-                    yf[q] = acc[k];
-                    pn[q] = col[k + 1];
-                    xf[q] = xo + alpha * pold;
+                    if (A.l2hint & 4) { f2_st_hint(yf + q, acc[k], pol_st); f2_st_hint(pn + q, col[k + 1], pol_st); f2_st_hint(xf + q, xo + alpha * pold, pol_st); }
+                    else {
+                        yf[q] = acc[k];
+                        pn[q] = col[k + 1];
+                        xf[q] = xo + alpha * pold;
+                    }
                     v[0] += col[k + 1] * acc[k];
                 }
             } else {

@@ -1,3 +1,4 @@
+#include <algorithm>
 // penguin_b200.cu -- C ABI of libpenguin_b200.so (see include/penguin_b200.h for the reference citations).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC penguin_b200.cu -o libpenguin_b200.so
 #include "common.cuh"
@@ -975,6 +976,14 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         DISPATCH_N(g.N, (kf_blocks<N><<<(d.nE + 127) / 128, 128, 0, ctx->stream>>>(g, d)));
         LAUNCH_CHECK(ctx);
         if (F.EnbrE) { kf_enbre_fill<<<(d.nE + 255) / 256, 256, 0, ctx->stream>>>(g, d.nE, d.nEp, F.Ecell, F.EnbrB, F.eord, F.EnbrE); LAUNCH_CHECK(ctx); }
+        if (F.EnbrE && d.nB > 0 && band_lpc(d.nE) == 8) {   // small band: band-indexed copies for the update head
+            d.nBp = (d.nB + 31) / 32 * 32;
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.Bq, sizeof(long long) * (size_t)d.nBp));
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.Bidx, sizeof(int) * (size_t)(1 + 4 * g.N) * d.nBp));
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.Bblk, sizeof(double) * (size_t)(1 + 2 * g.N) * 9 * d.nBp));
+            kf_band_index<<<(d.nB + 127) / 128, 128, 0, ctx->stream>>>(g, d, F.Bq, F.Bidx, F.Bblk, d.nBp); LAUNCH_CHECK(ctx);
+            d.Bq = F.Bq; d.Bidx = F.Bidx; d.Bblk = F.Bblk;
+        }
     }
     // active tile list + per-tile coefficient census
     {
@@ -1073,8 +1082,47 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
             // cost-class order of the bulk tiles (slow first): all / interior class / ghost class (box reaches a neighbour rank's ghost plane)
             const bool reorder = !getenv("PB200_NO_REORDER");
             std::vector<int> all, ghost, g1, fast_i, gen_i, fast_all, gen_all, inner_all;
+            // 3-D: the apply's lists walk the tiles BRICK by brick (8 x 8 x 8 tiles = 256 x 64 x 32 cells) instead of in index order, so that the tiles in
+            // flight at one time form a compact block whose halo planes are shared while they are in L2.  Measured with ncu at 1024 x 1024 x 128 (DRAM
+            // reads of one fused apply, 4.1 GB algorithmic): index order, 2 blocks per SM x 2 stages 6.8 GB; index order, 1 block per SM x 4 stages 5.5 GB;
+            // bricks, 1 block per SM 4.9 GB (tools/r2_ncu_*.sh).  PB200_ORDER=runs: consecutive z / y neighbours handed to ONE block in runs (Items.run,
+            // f3_item) -- measured worse (7.4 GB), kept as an experiment.  The order is fixed, so the reductions stay deterministic.
+            std::vector<int> perm(n);
+            for (int i = 0; i < n; ++i) perm[i] = i;
+            int run3 = 1;
+            const char *order = getenv("PB200_ORDER");
+            if (g.N == 3 && !getenv("PB200_NO_BRICKS") && !(order && !strcmp(order, "index"))) {
+                std::vector<long long> key(n);
+                if (order && !strcmp(order, "runs")) {
+                    int ry = 2, rz = 8;
+                    if (const char *e = getenv("PB200_RUN")) sscanf(e, "%d,%d", &ry, &rz);
+                    if (ry < 1) ry = 1;
+                    if (rz < 1) rz = 1;
+                    run3 = ry * rz;
+                    const long long nt2l = (I.ld2 + I.T2 - 1) / I.T2;
+                    for (int i = 0; i < n; ++i) {
+                        if (hr[i].f >= 2) { key[i] = (1ll << 62) + i; continue; }
+                        const long long t0 = hr[i].ox / I.T0, t1 = hr[i].oy / I.T1, t2 = hr[i].oz / I.T2;
+                        key[i] = ((long long)hr[i].f << 58) + ((((t0 * ((I.nt1 + ry - 1) / ry) + t1 / ry) * ((nt2l + rz - 1) / rz) + t2 / rz) * rz + t2 % rz) * ry + t1 % ry);
+                    }
+                } else {
+                    int bd[3] = {8, 8, 8};
+                    if (const char *e = getenv("PB200_BRICK")) sscanf(e, "%d,%d,%d", &bd[0], &bd[1], &bd[2]);
+                    for (int q = 0; q < 3; ++q) if (bd[q] < 1) bd[q] = 1;
+                    const long long nb0 = (I.nt0 + bd[0] - 1) / bd[0], nb1 = (I.nt1 + bd[1] - 1) / bd[1];
+                    for (int i = 0; i < n; ++i) {
+                        if (hr[i].f >= 2) { key[i] = (1ll << 62) + i; continue; }
+                        const long long t0 = hr[i].ox / I.T0, t1 = hr[i].oy / I.T1, t2 = hr[i].oz / I.T2;
+                        const long long brick = (t0 / bd[0]) + nb0 * ((t1 / bd[1]) + nb1 * (t2 / bd[2]));
+                        const long long inb = (t0 % bd[0]) + bd[0] * ((t1 % bd[1]) + bd[1] * (t2 % bd[2]));
+                        key[i] = ((long long)hr[i].f << 58) + brick * (long long)(bd[0] * bd[1] * bd[2]) + inb;
+                    }
+                }
+                std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+            }
             for (int cls = 0; cls < 2; ++cls)
-                for (int i = 0; i < n; ++i) {
+                for (int ii = 0; ii < n; ++ii) {
+                    const int i = perm[ii];
                     if (hr[i].f >= 2) continue;     // (w chunks are not the dense apply's business)
                     // every cell valid, one constant per direction, no band cell: the pipelined kernel (kf3_apply).  (A tile in which a field lives on
                     // cut cells only has all-zero coefficients -- "constant" -- and still holds band cells, whose z carries the band correction.)
@@ -1090,6 +1138,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
             for (int i = 0; i < n; ++i) if (hr[i].f >= 2 || hr[i].ghost) g1.push_back(hi[i]);
             if ((rc = make_list(all, F.IA)) || (rc = make_list(ghost, F.IAg)) || (rc = make_list(g1, F.IG1)) || (rc = make_list(fast_i, F.IAf)) ||
                 (rc = make_list(gen_i, F.IAgen)) || (rc = make_list(fast_all, F.IFall)) || (rc = make_list(gen_all, F.IGall)) || (rc = make_list(inner_all, F.IAi_all))) return rc;
+            F.IA.run = F.IAg.run = F.IAf.run = F.IAgen.run = F.IFall.run = F.IGall.run = F.IAi_all.run = run3;
             if (getenv("PB200_DBG_LISTS")) {   // debugging: every sub-list must carry the base list's records / flags / constants for its items
                 std::vector<double> hc((size_t)n * PB_MAXD);
                 CUDA_TRY(ctx, cudaMemcpy(hc.data(), F.ucoef, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
@@ -1256,9 +1305,11 @@ static int fold_tmap(pb200_solver *s, const double *ptr, CUtensorMap *out, int k
     cuuint32_t box2[2] = {(cuuint32_t)F2Box<2>::BX, (cuuint32_t)F2Box<2>::BY}, box3[3] = {(cuuint32_t)F2Box<3>::BX, (cuuint32_t)F2Box<3>::BY, (cuuint32_t)F2Box<3>::BZ};
     const cuuint32_t es[3] = {1, 1, 1};
     if (kind == 1) { box2[0] = 32; box2[1] = 32; box3[0] = 32; box3[1] = 8; box3[2] = 4; }
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char *e = getenv("PB200_TMA_PROMO")) { const int v = atoi(e); promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B)); }
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)N, (void *)ptr, dims, strides, N == 2 ? box2 : box3, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(s->ctx, PB200_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     F.tmaps[std::make_pair(ptr, kind)] = m;
     *out = m;
@@ -1362,6 +1413,42 @@ static int fold3_launch(pb200_solver *s, const Items &L, const F3Maps &maps, con
     const int dbg = getenv("PB200_DBG_F3") ? atoi(getenv("PB200_DBG_F3")) : 0;
     if ((dbg & 4) && grid > ctx->sm_count) grid = ctx->sm_count;
     if (grid < 1) grid = 1;
+    if (N == 3 && MODE == 5) {
+        // 3-D fused apply: ONE block per SM with a four-stage pipeline (171 KB of shared memory) instead of two blocks with two stages each -- the same
+        // bytes in flight, but the boxes of neighbouring tiles then share their halo planes in L2 (ncu, 1024 x 1024 x 128: 6.8 -> 5.5 GB of DRAM reads
+        // per launch, 1.53 -> 1.39 ms).  PB200_F3_S = 2 (two blocks per SM) .. 5.
+        const int sreq = getenv("PB200_F3_S") ? atoi(getenv("PB200_F3_S")) : 4;
+        auto go = [&](auto kern, int smemS) -> int {
+            static bool attrS[64][8] = {};
+            const int si = smemS / STAGE;
+            if (!attrS[ctx->device & 63][si & 7]) { CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemS)); attrS[ctx->device & 63][si & 7] = true; }
+            int nbS = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbS, kern, FCH + 32, smemS) != cudaSuccess || nbS < 1) { cudaGetLastError(); nbS = 1; }
+            int gS = L.n < ctx->sm_count * nbS ? L.n : ctx->sm_count * nbS;
+            if ((dbg & 4) && gS > ctx->sm_count) gS = ctx->sm_count;
+            if (gS < 1) gS = 1;
+            kern<<<gS, FCH + 32, smemS, st>>>(maps, L, A, has_t, dbg);
+            LAUNCH_CHECK(ctx);
+            return PB200_OK;
+        };
+        if (!(dbg & 8)) {
+            if (sreq == 3) return go(kf3_apply<3, 5, 3>, 3 * STAGE + 128);
+            if (sreq == 4) return go(kf3_apply<3, 5, 4>, 4 * STAGE + 128);
+            if (sreq == 5) return go(kf3_apply<3, 5, 5>, 5 * STAGE + 128);
+        }
+    }
+    if (N == 3 && MODE != 5 && getenv("PB200_F3_PLAIN_S6")) {   // experiment: plain 3-D applies with one block per SM, six stages -- measured WORSE (512^3 CN: 36.4 -> 42.7 ms per step)
+        static bool attr6[64] = {};
+        constexpr int smem6 = 6 * STAGE + 128;
+        if (!attr6[ctx->device & 63]) { CUDA_TRY(ctx, cudaFuncSetAttribute(kf3_apply<3, MODE, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6)); attr6[ctx->device & 63] = true; }
+        int nb6 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb6, kf3_apply<3, MODE, 6>, FCH + 32, smem6) != cudaSuccess || nb6 < 1) { cudaGetLastError(); nb6 = 1; }
+        int g6 = L.n < ctx->sm_count * nb6 ? L.n : ctx->sm_count * nb6;
+        if (g6 < 1) g6 = 1;
+        kf3_apply<3, MODE, 6><<<g6, FCH + 32, smem6, st>>>(maps, L, A, has_t, dbg);
+        LAUNCH_CHECK(ctx);
+        return PB200_OK;
+    }
     if ((dbg & 8) && MODE == 5) {   // one stage: no overlap, tests the pipeline logic
         constexpr int smem1 = STAGE + 128;
         static bool attr1[64] = {};
@@ -1613,8 +1700,13 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         // band heads (fold2.cuh): the two O(band) launches of the iteration folded into the streaming kernels -- one rank, pipelined kernel, band preconditioner,
         // SMALL bands (2-D problems: the separate launches are pure latency there; on the large bands of 3-D problems they are bandwidth work and were
         // measured equal either way -- 1024 x 1024 x 128 diphasic: 68.3 vs 68.2 ms per step)
-        const bool bandfuse = cg && fused && prec && ctx->nranks == 1 && F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED") && F.d.eord != nullptr && F.d.nE > 0 && (band_lpc(F.d.nE) == 8 || getenv("PB200_BANDFUSE_ALWAYS")) && !getenv("PB200_NO_BANDFUSE");
-        if (bandfuse && !F.have_r2) { if ((rc = fold_alloc_vec(s, &F.r2))) return rc; F.have_r2 = true; }
+        const bool bandfuse = cg && fused && prec && ctx->nranks == 1 && F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED") && F.d.eord != nullptr && F.d.nE > 0 && F.d.Bq != nullptr && !getenv("PB200_NO_BANDFUSE");
+        if (bandfuse && !F.have_r2) {
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.r2.f[2], sizeof(double) * (size_t)(F.d.nB > 0 ? F.d.nB : 1)));
+            CUDA_TRY(ctx, cudaMalloc((void **)&F.rE, sizeof(double) * 4 * (size_t)F.d.nEp));
+            F.have_r2 = true;
+        }
+        if (bandfuse) { F.r2.f[0] = F.r.f[0]; F.r2.f[1] = F.r.f[1]; }
         BandHead bhd;
         memset(&bhd, 0, sizeof(bhd));
         if (bandfuse) {
@@ -1623,6 +1715,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
             bhd.ya = F.d.ya; bhd.dzw = F.dz; bhd.ld0 = F.d.ld0; bhd.dP = F.d.dP;
             for (int dd = 0; dd < PB_MAXD; ++dd) bhd.sq[dd] = F.d.sq[dd];
             bhd.ca = F.pa0 - 1.0; bhd.cb = F.pa1;
+            bhd.Bq = F.d.Bq; bhd.Bidx = F.d.Bidx; bhd.Bblk = F.d.Bblk; bhd.nBp = F.d.nBp;
+            kf2_gather_rE<<<(F.d.nE + 255) / 256, 256, 0, ctx->stream>>>(bhd, F.r, F.rE, F.rE + 2 * (size_t)F.d.nEp); LAUNCH_CHECK(ctx);
         }
         auto enqueue = [&](int curp) -> int {   // one Krylov iteration reading pair `curp`, publishing pair curp ^ 1
             const int nxt = curp ^ 1;
@@ -1646,6 +1740,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 A.sl_old = FS_TRIPLE(nxt); A.sl_cur = FS_TRIPLE(curp); A.stop = st; A.res = res;
                 A.partials = ctx->d_partials; A.counter = ctx->d_counter; A.results = res + FS_SIG_D;
                 A.dbg = getenv("PB200_DBG_F3") ? atoi(getenv("PB200_DBG_F3")) : 0;
+                A.l2hint = getenv("PB200_L2HINT") ? atoi(getenv("PB200_L2HINT")) : 0;
                 for (int pp = 0; pp < 2; ++pp) for (int dd = 0; dd < PB_MAXD; ++dd) A.off[pp][dd] = F.d.off[pp][dd];
                 if (side) {
                     if (st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
@@ -1726,7 +1821,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                     int HB = getenv("PB200_BANDFUSE_HB") ? atoi(getenv("PB200_BANDFUSE_HB")) : gw / 8;
                     if (HB > gw / 2) HB = gw / 2;
                     if (gw < 8) HB = 0;
-#define K2B(N_) kf2_update_b<N_, 8><<<gw, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, rold, rnew, pnew, bhd, HB, ctx->d_partials, ctx->d_counter, st)
+#define K2B(N_) kf2_update_b<N_, 8><<<gw, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, rold, rnew, F.rE + (curp ? 2 : 0) * (size_t)F.d.nEp, F.rE + (curp ? 0 : 2) * (size_t)F.d.nEp, pnew, bhd, HB, ctx->d_partials, ctx->d_counter, st)
                     if (s->g.N == 2) K2B(2); else K2B(3);
 #undef K2B
                     LAUNCH_CHECK(ctx);

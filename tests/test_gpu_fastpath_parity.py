@@ -76,7 +76,9 @@ def diph256(pb):
 
 # implementations of the Krylov iteration on the folded system (csrc/fold2.cuh): the default is the fused, TMA-staged one; the switches
 # peel it back layer by layer so that a parity failure names its layer
-VARIANTS = {"fused_pipelined": {}, "fused_two_stage": {"PB200_NO_PIPE": "1"}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1"},
+# (fused_pipelined runs the band heads -- the interface-band work inside the two streaming kernels --, fused_band_launches the separate band kernels
+#  that several ranks and large 3-D bands use)
+VARIANTS = {"fused_pipelined": {}, "fused_band_launches": {"PB200_NO_BANDFUSE": "1"}, "fused_two_stage": {"PB200_NO_PIPE": "1"}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1"},
             "reference_pitch": {"PB200_NO_REPITCH": "1"}}
 
 

@@ -7,7 +7,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"fused_pipelined": {}, "fused_two_stage": {"PB200_NO_PIPE": "1"}, "unfused_tma": {"PB200_NO_FUSED": "1"}}
+VARIANTS = {"fused_pipelined": {}, "fused_band_launches": {"PB200_NO_BANDFUSE": "1"}, "fused_band_heads_all_blocks": {"PB200_BANDFUSE_HB": "0"},
+            "fused_two_stage": {"PB200_NO_PIPE": "1"}, "unfused_tma": {"PB200_NO_FUSED": "1"}}
 BASE = {"PB200_NO_TMA": "1", "PB200_NO_REPITCH": "1"}
 
 

@@ -25,12 +25,16 @@ def main():
     ap.add_argument("--diph", action="store_true", help="configs[3]: diphasic BE, sphere interface r = 1 centre (2,2,2), ScalarJump(1,2,0), FluxJump(1,1,0), "
                                                         "u0 = [1,1,0,0], dt = 0.5 h^2, empty borders (examples/3D/Diffusion/Heat_2ph.jl)")
     ap.add_argument("--warm", type=int, default=4)
+    ap.add_argument("--nz", type=int, default=0, help="--diph: planes in z (default nx); the box is [0,4]^2 x nz h centred on the sphere, as bench.py's configs[3] slab")
     args = ap.parse_args()
     import torch
     ctx = pb.init(0)
     lib = L.lib()
     nx = args.nx
     mesh = pb.Mesh((nx, nx, nx), (4.0, 4.0, 4.0))
+    if args.diph and args.nz:
+        Lz = args.nz * 4.0 / nx
+        mesh = pb.Mesh((nx, nx, args.nz), (4.0, 4.0, Lz), (0.0, 0.0, 2.0 - 0.5 * Lz))
     if args.diph:
         body = pb.Sphere((2.0, 2.0, 2.0), 1.0)
         t0 = time.perf_counter()
