@@ -825,8 +825,9 @@ __global__ void kf_band_index(Grid g, FoldDev fd, long long *Bq, int *Bidx, doub
     const int NK = 1 + 2 * g.N;
     for (int bo = blockIdx.x * blockDim.x + threadIdx.x; bo < fd.nB; bo += gridDim.x * blockDim.x) {
         const int e = fd.EofB[bo];
-        Bq[bo] = fd_q(fd, fd.Ecell[e]);
         Bidx[bo] = e;
+        if (e < 0) { Bq[bo] = 0; continue; }      // band cell of a ghost plane: no row on this rank
+        Bq[bo] = fd_q(fd, fd.Ecell[e]);
         for (int kk = 0; kk < 2 * g.N; ++kk) {
             Bidx[(size_t)(1 + kk) * nBp + bo] = fd.EnbrB[(size_t)kk * fd.nEp + e];
             Bidx[(size_t)(1 + 2 * g.N + kk) * nBp + bo] = fd.EnbrE[(size_t)kk * fd.nEp + e];
@@ -1241,6 +1242,8 @@ struct FoldSys {
     Items IAf, IAgen;                       // interior class: tiles of the pipelined kernel (all cells valid, constant coefficients) / the rest
     Items IFall, IGall;                     // the same split over both classes (plain applies with the halo already exchanged)
     Items IG1;                              // ghost-class tiles + compact interface unknowns: pointwise p / x update of the fused iteration
+    Items IG1nw;                            // ghost-class tiles only (band heads update the interface unknowns)
+    bool bandfuse_ok = false;               // band heads usable (collective: the same on every rank)
     std::vector<void *> list_mem;           // device arrays behind the sub-lists
     FVec x, b, r, p, v, r0, s, t, z;
     FVec p2 = {}, zz = {};                  // fused iteration: second search-direction buffer, preconditioned residual (polynomial)

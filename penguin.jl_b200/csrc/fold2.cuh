@@ -357,10 +357,10 @@ __global__ void kf2_gather_rE(BandHead b, FVec r, double *rE0, double *rE1)
 // every block running its share of the head first, nothing streamed during the head's dependent gathers (2048^2: 23 -> 33 us).  HB = 0: every block does both.
 template <int N, int LPC>
 __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int sl_rho, int sl_new, FVec qv, FVec rold, FVec r, const double *__restrict__ rEold,
-                                                       double *__restrict__ rEnew, FVec pnew, BandHead b, int HB, double *partials, unsigned *counter, StopCrit stop)
+                                                       double *__restrict__ rEnew, FVec pnew, BandHead b, int HB, int carry, double *partials, unsigned *counter, StopCrit stop)
 {
     if (fold_done(res, stop)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; res[sl_new + 3] = res[sl_rho + 3]; }
+        if (carry && blockIdx.x == 0 && threadIdx.x == 0) { res[sl_new] = res[sl_rho]; res[sl_new + 1] = res[sl_rho + 1]; res[sl_new + 2] = res[sl_rho + 2]; res[sl_new + 3] = res[sl_rho + 3]; }
         return;
     }
     const double alpha = safe_div(rho_at(res, sl_rho), res[FS_SIG_D] + res[FS_SIG_B] + res[FS_SIG_G]);
@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
             const bool live = bo_raw < b.nB;
             const int bo = live ? bo_raw : b.nB - 1;        // (groups past the end redo the last cell: the shuffles are warp-wide)
             const size_t BS = (size_t)b.nBp;
-            const int e = b.Bidx[bo];
+            const int e_raw2 = b.Bidx[bo];
+            const bool ghost_row = e_raw2 < 0;            // (band cell of a ghost plane: no row here; the lanes still run for the warp-wide shuffles)
+            const int e = ghost_row ? 0 : e_raw2;
             const long long lq = b.Bq[bo];
             const double dz0 = b.dzw[bo], dz1 = two ? b.dzw[(size_t)b.nB + bo] : 0.0;      // (lane 0 needs them after the reduction: in flight with the rest)
             double r0 = 0.0, r1 = 0.0, r2 = 0.0, x0 = 0.0, x1 = 0.0, xw = 0.0;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
                 if (k > 0) {
                     const int kk = k - 1, d = kk >> 1;
                     ln = (kk & 1) ? lq + b.sq[d] : lq - b.sq[d];
-                    nb = b.Bidx[(size_t)(1 + kk) * BS + bo];
+                    nb = ghost_row ? -1 : b.Bidx[(size_t)(1 + kk) * BS + bo];
                     en = b.Bidx[(size_t)(1 + 2 * N + kk) * BS + bo];
                 }
                 // branch-free: a neighbour that is no band cell reads this cell's entries and counts with weight 0 (all loads of a lane are in flight together)
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(FCH, 4) kf2_update_b(Items I, double *res, int
                     r0 += __shfl_xor_sync(0xffffffffu, r0, o, LPC); r1 += __shfl_xor_sync(0xffffffffu, r1, o, LPC); r2 += __shfl_xor_sync(0xffffffffu, r2, o, LPC);
                 }
             }
-            if (sub != 0 || !live) continue;                              // (lane 0 of the group took k = 0: it holds x0, x1, xw)
+            if (sub != 0 || !live || ghost_row) continue;                 // (lane 0 of the group took k = 0: it holds x0, x1, xw)
             const double a0 = r0 + x0, a1 = r1 + x1, a2 = r2 + xw;        // (I + band block) r_B
             // p_k on the band cell lacks the band correction the tile kernel could not see: add the one it was formed with, then replace it
             pnew.f[0][lq] += dz0;

@@ -947,10 +947,14 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         CUDA_TRY(ctx, cudaMalloc((void **)&F.Eblk, sizeof(double) * (1 + 2 * g.N) * 9 * nE));
         CUDA_TRY(ctx, cudaMalloc((void **)&F.Efix, nE));
         d.EB = F.EB; d.EnbrB = F.EnbrB; d.Eblk = F.Eblk; d.Efix = F.Efix;
-        if (ctx->nranks == 1) {   // band heads of the fused iteration (fold2.cuh): cell -> E index, band cell -> E index, band couplings of the bulk rows
+        // (small band) band heads of the fused iteration (fold2.cuh): cell -> E index, band cell -> E index, band couplings of the bulk rows.
+        // Several ranks: implemented (collective choice below) but OFF unless PB200_BANDFUSE_MULTI is set -- on 2 GPUs the graph-replayed iteration of the
+        // weak-scaled 2-D bench ran 2.3x SLOWER with the heads (335 vs 146 us) although every kernel timed alone was as fast or faster; not understood yet.
+        if (band_lpc(d.nE) == 8 && (ctx->nranks == 1 || getenv("PB200_BANDFUSE_MULTI"))) {
             CUDA_TRY(ctx, cudaMalloc((void **)&F.eord, sizeof(int) * (size_t)g.nloc));
             CUDA_TRY(ctx, cudaMemsetAsync(F.eord, 0xFF, sizeof(int) * (size_t)g.nloc, ctx->stream));
             CUDA_TRY(ctx, cudaMalloc((void **)&F.EofB, sizeof(int) * (size_t)(d.nB > 0 ? d.nB : 1)));
+            CUDA_TRY(ctx, cudaMemsetAsync(F.EofB, 0xFF, sizeof(int) * (size_t)(d.nB > 0 ? d.nB : 1), ctx->stream));   // (band cells in ghost planes have no E row)
             CUDA_TRY(ctx, cudaMalloc((void **)&F.EnbrE, sizeof(int) * 2 * g.N * nE));
             CUDA_TRY(ctx, cudaMalloc((void **)&F.ya, sizeof(double) * 2 * nE));
             CUDA_TRY(ctx, cudaMemsetAsync(F.ya, 0, sizeof(double) * 2 * nE, ctx->stream));
@@ -984,6 +988,26 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
             kf_band_index<<<(d.nB + 127) / 128, 128, 0, ctx->stream>>>(g, d, F.Bq, F.Bidx, F.Bblk, d.nBp); LAUNCH_CHECK(ctx);
             d.Bq = F.Bq; d.Bidx = F.Bidx; d.Bblk = F.Bblk;
         }
+    }
+    // Band heads (fold2.cuh) are a COLLECTIVE choice: every rank must hold a small band (or none) whose cells AND their face neighbours all lie in
+    // tiles of the fused kernel (interior class: Efix has every bit set) -- then no band row needs a ghost plane and the heads replace the band launches
+    // on every rank (bench.py's weak-scaled configs[1]: one interface per slab, away from the slab faces).
+    F.bandfuse_ok = false;
+    if (d.has_w) {
+        double bad = (d.nE > 0 && F.eord == nullptr) ? 1.0 : 0.0;
+        if (d.nE > 0 && bad == 0.0 && ctx->nranks > 1) {
+            std::vector<unsigned char> hfix((size_t)d.nE);
+            CUDA_TRY(ctx, cudaMemcpyAsync(hfix.data(), F.Efix, (size_t)d.nE, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            const unsigned full = (1u << (1 + 2 * g.N)) - 1u;
+            for (unsigned char v : hfix) if ((v & full) != full) { bad = 1.0; break; }
+        }
+        if (d.nE > 0 && d.nB > 0 && F.Bq == nullptr) bad = 1.0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_results + SL_TMP, &bad, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = allreduce_results(ctx, SL_TMP, 1))) return rc;
+        if ((rc = fetch_results(ctx, SL_TMP, 1, &bad))) return rc;
+        F.bandfuse_ok = bad == 0.0;
+        if (getenv("PB200_REPORT_HEADS") && ctx->rank == 0) fprintf(stderr, "[pb200] band heads: %s (%d rank%s, %d band / fringe rows on rank 0)\n", F.bandfuse_ok ? "on" : "off", ctx->nranks, ctx->nranks > 1 ? "s" : "", d.nE);
     }
     // active tile list + per-tile coefficient census
     {
@@ -1046,6 +1070,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
         // kernels keep the index-ordered list: all tiles cost them the same, and neighbouring blocks on neighbouring tiles share DRAM
         // pages (the class order cost them 25 % at 384^3).
         F.IA = I; F.IAg = I; F.IG1 = I; F.IAf = I; F.IAgen = I; F.IFall = I; F.IGall = I; F.IAi_all = I;
+        F.IG1nw = I; F.IG1nw.n = 0;
         F.IAg.n = 0; F.IG1.n = 0; F.IAf.n = 0; F.IAgen.n = 0; F.IFall.n = 0; F.IGall.n = 0; F.IAi_all.n = 0;
         if (F.nitems > 0) {
             const int n = F.nitems;
@@ -1136,6 +1161,9 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
                 }
             // pointwise p / x update of the fused iteration: ghost-class tiles + the compact interface unknowns (index order)
             for (int i = 0; i < n; ++i) if (hr[i].f >= 2 || hr[i].ghost) g1.push_back(hi[i]);
+            std::vector<int> g1nw;                                                                    // (band heads: the heads update the interface unknowns)
+            for (int i = 0; i < n; ++i) if (hr[i].f < 2 && hr[i].ghost) g1nw.push_back(hi[i]);
+            if ((rc = make_list(g1nw, F.IG1nw))) return rc;
             if ((rc = make_list(all, F.IA)) || (rc = make_list(ghost, F.IAg)) || (rc = make_list(g1, F.IG1)) || (rc = make_list(fast_i, F.IAf)) ||
                 (rc = make_list(gen_i, F.IAgen)) || (rc = make_list(fast_all, F.IFall)) || (rc = make_list(gen_all, F.IGall)) || (rc = make_list(inner_all, F.IAi_all))) return rc;
             F.IA.run = F.IAg.run = F.IAf.run = F.IAgen.run = F.IFall.run = F.IGall.run = F.IAi_all.run = run3;
@@ -1700,7 +1728,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
         // band heads (fold2.cuh): the two O(band) launches of the iteration folded into the streaming kernels -- one rank, pipelined kernel, band preconditioner,
         // SMALL bands (2-D problems: the separate launches are pure latency there; on the large bands of 3-D problems they are bandwidth work and were
         // measured equal either way -- 1024 x 1024 x 128 diphasic: 68.3 vs 68.2 ms per step)
-        const bool bandfuse = cg && fused && prec && ctx->nranks == 1 && F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED") && F.d.eord != nullptr && F.d.nE > 0 && F.d.Bq != nullptr && !getenv("PB200_NO_BANDFUSE");
+        const bool bandfuse = cg && fused && prec && F.bandfuse_ok && F.pipe && !getenv("PB200_DBG_NOPIPE_FUSED") && !getenv("PB200_NO_BANDFUSE");   // (the same on every rank)
         if (bandfuse && !F.have_r2) {
             CUDA_TRY(ctx, cudaMalloc((void **)&F.r2.f[2], sizeof(double) * (size_t)(F.d.nB > 0 ? F.d.nB : 1)));
             CUDA_TRY(ctx, cudaMalloc((void **)&F.rE, sizeof(double) * 4 * (size_t)F.d.nEp));
@@ -1716,7 +1744,7 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
             for (int dd = 0; dd < PB_MAXD; ++dd) bhd.sq[dd] = F.d.sq[dd];
             bhd.ca = F.pa0 - 1.0; bhd.cb = F.pa1;
             bhd.Bq = F.d.Bq; bhd.Bidx = F.d.Bidx; bhd.Bblk = F.d.Bblk; bhd.nBp = F.d.nBp;
-            kf2_gather_rE<<<(F.d.nE + 255) / 256, 256, 0, ctx->stream>>>(bhd, F.r, F.rE, F.rE + 2 * (size_t)F.d.nEp); LAUNCH_CHECK(ctx);
+            if (F.d.nE > 0) { kf2_gather_rE<<<(F.d.nE + 255) / 256, 256, 0, ctx->stream>>>(bhd, F.r, F.rE, F.rE + 2 * (size_t)F.d.nEp); LAUNCH_CHECK(ctx); }
         }
         auto enqueue = [&](int curp) -> int {   // one Krylov iteration reading pair `curp`, publishing pair curp ^ 1
             const int nxt = curp ^ 1;
@@ -1731,7 +1759,8 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 // The second stream exists to overlap the HALO EXCHANGE with the interior tiles.  On one rank the side work is the pointwise update of
                 // the interface unknowns only, and running it beside the staged kernel cost more than it hid (512^3 diphasic: 85 vs 65 ms per step).
                 cudaStream_t st2 = (ctx->profile || !multi || getenv("PB200_DBG_SERIAL")) && !getenv("PB200_DBG_FORK") ? ctx->stream : ctx->stream2;
-                const bool side = (F.IG1.n > 0 || multi) && !bandfuse;
+                const Items &Lpupd = bandfuse ? F.IG1nw : F.IG1;      // (band heads update the interface unknowns themselves)
+                const bool side = Lpupd.n > 0 || multi;
                 F2Args A;
                 memset(&A, 0, sizeof(A));
                 A.bh = bhd;
@@ -1744,10 +1773,10 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                 for (int pp = 0; pp < 2; ++pp) for (int dd = 0; dd < PB_MAXD; ++dd) A.off[pp][dd] = F.d.off[pp][dd];
                 if (side) {
                     if (st2 != ctx->stream) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0)); }
-                    if (F.IG1.n > 0) {   // ghost-class tiles and the compact interface unknowns: p_k and x pointwise
+                    if (Lpupd.n > 0) {   // ghost-class tiles and the compact interface unknowns: p_k and x pointwise
                         prof_mark(ctx, PB_PROF_PUPD);
-                        int g1 = F.IG1.n < ctx->sm_count * 4 ? F.IG1.n : ctx->sm_count * 4;
-                        kf2_pupd<<<g1, FCH, 0, st2>>>(F.IG1, A); LAUNCH_CHECK(ctx);
+                        int g1 = Lpupd.n < ctx->sm_count * 4 ? Lpupd.n : ctx->sm_count * 4;
+                        kf2_pupd<<<g1, FCH, 0, st2>>>(Lpupd, A); LAUNCH_CHECK(ctx);
                         prof_mark(ctx, PB_PROF_PUPD);
                     }
                     if (multi && (rc2 = fold_halo(s, pnew, st2))) return rc2;   // ghost planes of p_k: in flight while the interior class computes
@@ -1761,10 +1790,11 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                     F3Maps m3;
                     if ((rc2 = fold_maps3(s, zsrc, &pold, &F.x, &m3))) return rc2;
                     const int N3 = s->g.N;
-                    const int g5 = N3 == 2 ? fold3_grid5<2>(s, F.IA) : fold3_grid5<3>(s, F.IA);
+                    const Items &L5 = multi ? F.IAi_all : F.IA;
+                    const int g5 = N3 == 2 ? fold3_grid5<2>(s, L5) : fold3_grid5<3>(s, L5);
                     const bool two_lanes = (long long)F.d.nE * 2 <= (long long)g5 * FCH;
-                    if (N3 == 2) rc2 = two_lanes ? fold3_launch_bh<2, 2>(s, F.IA, m3, A, ctx->stream) : fold3_launch_bh<2, 1>(s, F.IA, m3, A, ctx->stream);
-                    else rc2 = two_lanes ? fold3_launch_bh<3, 2>(s, F.IA, m3, A, ctx->stream) : fold3_launch_bh<3, 1>(s, F.IA, m3, A, ctx->stream);
+                    if (N3 == 2) rc2 = two_lanes ? fold3_launch_bh<2, 2>(s, L5, m3, A, ctx->stream) : fold3_launch_bh<2, 1>(s, L5, m3, A, ctx->stream);
+                    else rc2 = two_lanes ? fold3_launch_bh<3, 2>(s, L5, m3, A, ctx->stream) : fold3_launch_bh<3, 1>(s, L5, m3, A, ctx->stream);
                     if (rc2) return rc2;
                 } else if (split) {   // one pipelined launch: constant-coefficient interior tiles and general tiles alike
                     F3Maps m3;
@@ -1815,17 +1845,22 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
                     fprintf(stderr, "[pb200] check kf3: header mismatches %g, staged-box mismatches %g, v vs global recompute mismatches %g (cumulative)\n", dbg2[1], dbg2[2], dbg2[0]);
                 }
                 if (bandfuse) {
+                    if (multi && (rc2 = allreduce_results(ctx, FS_SIG_D, 3))) return rc2;
                     prof_mark(ctx, PB_PROF_UPDATE);
                     // head blocks (small bands only: see bandfuse): an eighth of the wave, 8 lanes per band cell
                     const int gw = s->g.N == 2 ? wave_grid(s, kf2_update_b<2, 8>) : wave_grid(s, kf2_update_b<3, 8>);
                     int HB = getenv("PB200_BANDFUSE_HB") ? atoi(getenv("PB200_BANDFUSE_HB")) : gw / 8;
                     if (HB > gw / 2) HB = gw / 2;
                     if (gw < 8) HB = 0;
-#define K2B(N_) kf2_update_b<N_, 8><<<gw, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, rold, rnew, F.rE + (curp ? 2 : 0) * (size_t)F.d.nEp, F.rE + (curp ? 0 : 2) * (size_t)F.d.nEp, pnew, bhd, HB, ctx->d_partials, ctx->d_counter, st)
+#define K2B(N_) kf2_update_b<N_, 8><<<gw, FCH, 0, ctx->stream>>>(I, res, FS_TRIPLE(curp), FS_TRIPLE(nxt), F.v, rold, rnew, F.rE + (curp ? 2 : 0) * (size_t)F.d.nEp, F.rE + (curp ? 0 : 2) * (size_t)F.d.nEp, pnew, bhd, HB, multi ? 0 : 1, ctx->d_partials, ctx->d_counter, st)
                     if (s->g.N == 2) K2B(2); else K2B(3);
 #undef K2B
                     LAUNCH_CHECK(ctx);
                     prof_mark(ctx, PB_PROF_UPDATE);
+                    if (multi) {
+                        if ((rc2 = allreduce_results(ctx, FS_TRIPLE(nxt), 3))) return rc2;
+                        kf2_carry<<<1, 32, 0, ctx->stream>>>(res, FS_TRIPLE(curp), FS_TRIPLE(nxt), st); LAUNCH_CHECK(ctx);
+                    }
                     return PB200_OK;
                 }
                 if (F.d.has_w) {     // band part of v = M^ p_k (needs p_k everywhere)

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 import penguin_b200 as pb                      # noqa: E402
 from penguin_b200 import slab                  # noqa: E402
 
-VARIANTS = {"fused_pipelined": {}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1", "PB200_NO_REPITCH": "1"}}
+VARIANTS = {"fused_pipelined": {}, "fused_band_launches": {"PB200_NO_BANDFUSE": "1"}, "unfused_tma": {"PB200_NO_FUSED": "1"}, "register_kernels": {"PB200_NO_TMA": "1", "PB200_NO_REPITCH": "1"}}
 
 
 def run_case(case, rank, world):
@@ -28,6 +28,11 @@ def run_case(case, rank, world):
     elif case == "mono3d":
         dims, L = (136, 128, 64), (4.25, 4.0, 2.0)
         body = -pb.Sphere((2.1, 2.0, 1.0), 0.7)
+    elif case == "diph2d_heads":
+        # one interface per slab of a 2-rank split, away from the slab faces: the band lies in interior-class tiles on every rank, so the band
+        # heads (the band work inside the two streaming kernels) run with several ranks as well -- bench.py's weak-scaled configs[1] in small
+        dims, L = (128, 512), (4.0, 16.0)
+        body = pb.Balls([[2.0, 4.0], [2.0, 12.0]], [1.5, 1.5])
     else:
         dims, L = (512, 1024), (4.0, 8.0)
         body = pb.Balls([[2.0, 4.0]], [1.3])          # the interface crosses the slab boundary of a 2-rank split
@@ -75,7 +80,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--single", default=None)
     ap.add_argument("--ref", default=None)
-    ap.add_argument("--cases", default="diph3d,mono3d,diph2d")
+    ap.add_argument("--cases", default="diph3d,mono3d,diph2d,diph2d_heads")
     ap.add_argument("--team", type=int, default=0, help="ONE process driving this many GPUs (pb200_init_multi): global host arrays, compared with --ref")
     args = ap.parse_args()
     cases = args.cases.split(",")
@@ -126,7 +131,7 @@ def main():
     worst = 0.0
     for case in cases:
         for vname, env in VARIANTS.items():
-            for k in ("PB200_NO_FUSED", "PB200_NO_TMA", "PB200_NO_REPITCH", "PB200_NO_PIPE"):
+            for k in ("PB200_NO_FUSED", "PB200_NO_TMA", "PB200_NO_REPITCH", "PB200_NO_PIPE", "PB200_NO_BANDFUSE"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             dims, nblk, s = run_case(case, rank, world)

@@ -37,13 +37,17 @@ def test_ranks_agree_with_one_gpu(tmp_path, nccl_only):
     if ng < 2:
         pytest.skip("needs 2 GPUs")
     ref = str(tmp_path / "ref.npz")
-    cases = "diph3d" if nccl_only else "diph3d,mono3d,diph2d"
+    cases = "diph3d" if nccl_only else "diph3d,mono3d,diph2d,diph2d_heads"
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "multi_gpu_variants.py"), "--single", ref, "--cases", cases], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "SINGLE_GPU_REFERENCE_WRITTEN" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     for n in ([2, 4] if ng >= 4 and not nccl_only else [2]):
-        out = _torchrun(n, "multi_gpu_variants.py", ["--ref", ref, "--cases", cases], env={"PB200_NO_P2P": "1"} if nccl_only else None)
+        env = {"PB200_REPORT_HEADS": "1"}
+        if nccl_only:
+            env["PB200_NO_P2P"] = "1"
+        out = _torchrun(n, "multi_gpu_variants.py", ["--ref", ref, "--cases", cases], env=env)
         assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
         assert "MULTI_GPU_VARIANTS_OK" in out.stdout
+        # (diph2d_heads is the geometry for which the band heads could run with several ranks -- PB200_BANDFUSE_MULTI=1; off by default, see fold_build)
 
 
 def test_one_process_drives_two_gpus(tmp_path):
