@@ -95,6 +95,11 @@ int pb200_ops_create(pb200_capacity *cap, pb200_ops **ops);
 int pb200_ops_grad(pb200_ops *ops, const double *p, double *out);
 /* div(op, q_omega, q_gamma) = -(G'+H') q_omega + H' q_gamma -- src/operators.jl:30-34.  q_*: ndim*nloc   */
 int pb200_ops_div(pb200_ops *ops, const double *q_omega, const double *q_gamma, double *out);
+/* ConvectionOps(cap, u_omega, u_gamma) -- src/operators.jl:194-209: adds the advective operators C_d = D_p diag(S_m A_d u_omega_d) S_m and
+ * K_d = diag(S_p H' u_gamma) to an operator handle (coefficient arrays on the device, applied matrix-free).  u_omega, u_gamma: ndim*nloc each.
+ * A solver created on such operators is the reference's AdvectionDiffusion{Steady,Unsteady}{Mono,Diph} (src/solver/advectiondiffusion.jl:12-418):
+ * bulk rows gain (sum_d C_d + 0.5 sum_d K_d) T_omega + 0.5 sum_d K_d T_gamma; solved with BiCGSTAB on the reference's rows (one GPU).          */
+int pb200_ops_set_convection(pb200_ops *ops, const double *u_omega, const double *u_gamma);
 /* W! diagonal (1/W, 1.0 where W == 0 -- src/operators.jl:145-152), component-major ndim*nloc              */
 int pb200_ops_export_wdag(pb200_ops *ops, double *wdag);
 int pb200_ops_destroy(pb200_ops *ops);

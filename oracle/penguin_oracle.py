@@ -185,6 +185,136 @@ class DiffusionOps:
         self.V = sp.diags(cap.V, format="csr")
 
 
+def delta_p(n):
+    """Forward difference, last row zero (operators.jl:10)."""
+    D = sp.lil_matrix(sp.diags([-np.ones(n), np.ones(n - 1)], [0, 1]))
+    D[n - 1, n - 1] = 0.0
+    return sp.csr_matrix(D)
+
+
+def sigma_m(n):
+    """Backward average; ``D[n, n] = 0`` (operators.jl:11)."""
+    D = sp.lil_matrix(0.5 * sp.diags([np.ones(n), np.ones(n - 1)], [0, -1]))
+    D[n - 1, n - 1] = 0.0
+    return sp.csr_matrix(D)
+
+
+def sigma_p(n):
+    """Forward average, last row zero (operators.jl:12)."""
+    D = sp.lil_matrix(0.5 * sp.diags([np.ones(n), np.ones(n - 1)], [0, 1]))
+    D[n - 1, n - 1] = 0.0
+    return sp.csr_matrix(D)
+
+
+class ConvectionOps(DiffusionOps):
+    """``ConvectionOps(capacity, u_omega, u_gamma)`` (operators.jl:194-209): C_d = D_p diag(S_m A_d u_omega_d) S_m,  K_d = diag(S_p H' u_gamma).
+    ``uo``: N vectors of n bulk velocity components, ``ug``: one vector of N n interface velocity components."""
+
+    def __init__(self, cap: Capacity, uo, ug):
+        super().__init__(cap)
+        mesh = cap.mesh
+        N, pd = mesh.N, mesh.pdims
+
+        def lifted(fn, d):
+            ops = [fn(pd[i]) if i == d else sp.identity(pd[i], format="csr") for i in range(N)]
+            return lift(ops) if N > 1 else ops[0]
+        Dp = [lifted(delta_p, d) for d in range(N)]
+        Sm = [lifted(sigma_m, d) for d in range(N)]
+        Sp = [lifted(sigma_p, d) for d in range(N)]
+        ug = np.asarray(ug, float)
+        self.C = [Dp[d] @ sp.diags(Sm[d] @ (cap.A[d] * np.asarray(uo[d], float))) @ Sm[d] for d in range(N)]
+        q = self.H.T @ ug
+        self.K = [sp.diags(Sp[d] @ q) for d in range(N)]
+
+
+def _conv(op):
+    return sum(op.C[1:], op.C[0]), 0.5 * sum(op.K[1:], op.K[0])
+
+
+def A_mono_stead_advdiff(op, cap, D, bc):
+    """advectiondiffusion.jl:30-47"""
+    ia, ib = build_I_bc(op.n, bc)
+    Id = build_I_D(op, D, cap)
+    GG, GH, HG, HH = _blocks(op, Id)
+    Cb, Ki = _conv(op)
+    Ib, Ia, Ig = sp.diags(ib), sp.diags(ia), sp.diags(cap.Gamma)
+    return sp.bmat([[Cb + Ki + GG, Ki + GH], [Ib @ HG, Ib @ HH + Ia @ Ig]], format="csr")
+
+
+def A_mono_unstead_advdiff(op, cap, D, bc, dt, scheme):
+    """advectiondiffusion.jl:178-213"""
+    ia, ib = build_I_bc(op.n, bc)
+    Id = build_I_D(op, D, cap)
+    GG, GH, HG, HH = _blocks(op, Id)
+    Cb, Ki = _conv(op)
+    Ib, Ia, Ig = sp.diags(ib), sp.diags(ia), sp.diags(cap.Gamma)
+    tie = Ib @ HH + Ia @ Ig
+    if scheme == "CN":
+        return sp.bmat([[op.V + dt / 2 * (Cb + Ki + GG), dt / 2 * (Ki + GH)], [dt / 2 * (Ib @ HG), dt / 2 * tie]], format="csr")
+    return sp.bmat([[op.V + dt * (Cb + Ki + GG), dt * (Ki + GH)], [Ib @ HG, tie]], format="csr")
+
+
+def b_mono_unstead_advdiff(op, f, cap, D, bc, Ti, dt, t, scheme):
+    """advectiondiffusion.jl:215-252"""
+    n = op.n
+    fn, fn1 = build_source(op, f, cap, t), build_source(op, f, cap, t + dt)
+    gn, gn1 = build_g_g(op, bc, cap, t), build_g_g(op, bc, cap, t + dt)
+    ia, ib = build_I_bc(n, bc)
+    Id = build_I_D(op, D, cap)
+    To, Tg = Ti[:n], Ti[n:]
+    V, Gam = cap.V, cap.Gamma
+    if scheme == "CN":
+        GG, GH, HG, HH = _blocks(op, Id)
+        Cb, Ki = _conv(op)
+        b1 = V * To - dt / 2 * ((Cb + Ki + GG) @ To) - dt / 2 * ((Ki + GH) @ Tg) + dt / 2 * V * (fn + fn1)
+        b2 = dt / 2 * Gam * (gn + gn1) - dt / 2 * ib * (HG @ To) - dt / 2 * (ib * (HH @ Tg) + ia * Gam * Tg)
+    else:
+        b1 = V * To + dt * V * fn1
+        b2 = Gam * gn1
+    return np.concatenate([b1, b2])
+
+
+def AdvectionDiffusionSteadyMono(phase, bc_b, bc_i):
+    """advectiondiffusion.jl:12-28"""
+    s = Solver()
+    s.A = A_mono_stead_advdiff(phase.operator, phase.capacity, phase.D, bc_i)
+    s.b = b_mono_stead_diff(phase.operator, phase.source, phase.capacity, bc_i)      # (b_mono_stead_advdiff :49-63 is the same vector)
+    s.A, s.b = BC_border_mono(s.A, s.b, bc_b, phase.capacity.mesh)
+    return s
+
+
+def solve_AdvectionDiffusionSteadyMono(s):
+    s.x = solve_system(s.A, s.b)
+    return s
+
+
+def AdvectionDiffusionUnsteadyMono(phase, bc_b, bc_i, dt, Ti, scheme):
+    """advectiondiffusion.jl:163-176: NO border rows in the constructor's system (unlike the diffusion constructor)."""
+    s = Solver()
+    sch = "CN" if scheme == "CN" else "BE"
+    s.A = A_mono_unstead_advdiff(phase.operator, phase.capacity, phase.D, bc_i, dt, sch)
+    s.b = b_mono_unstead_advdiff(phase.operator, phase.source, phase.capacity, phase.D, bc_i, np.asarray(Ti, float), dt, 0.0, sch)
+    return s
+
+
+def solve_AdvectionDiffusionUnsteadyMono(s, phase, dt, Tend, bc_b, bc, scheme, max_steps=None):
+    """advectiondiffusion.jl:254-283.  The reference's loop calls b_mono_unstead_advdiff WITHOUT the diffusion coefficient (:272, a MethodError as
+    written); this restates the evident intent (the 9-argument call of the constructor, :175)."""
+    t = 0.0
+    s.x = solve_system(s.A, s.b)
+    s.states.append(s.x)
+    k = 0
+    while t < Tend and (max_steps is None or k < max_steps):
+        t += dt
+        s.A = A_mono_unstead_advdiff(phase.operator, phase.capacity, phase.D, bc, dt, scheme)
+        s.b = b_mono_unstead_advdiff(phase.operator, phase.source, phase.capacity, phase.D, bc, s.x, dt, t, scheme)
+        s.A, s.b = BC_border_mono(s.A, s.b, bc_b, phase.capacity.mesh, t=t)
+        s.x = solve_system(s.A, s.b)
+        s.states.append(s.x)
+        k += 1
+    return s
+
+
 def grad(op: DiffusionOps, p):
     """operators.jl:20-23"""
     n = op.n

@@ -27,11 +27,14 @@ __all__ = [
     "DiffusionSteadyDiph", "solve_DiffusionSteadyDiph_", "DiffusionUnsteadyMono", "solve_DiffusionUnsteadyMono_",
     "DiffusionUnsteadyDiph", "solve_DiffusionUnsteadyDiph_", "Steady", "Unsteady", "Monophasic", "Diphasic", "Diffusion",
     "DarcyFlow", "solve_DarcyFlow_", "DarcyFlowUnsteady", "solve_DarcyFlowUnsteady_", "solve_darcy_velocity", "check_convergence",
+    "ConvectionOps", "DiffusionAdvection", "AdvectionDiffusionSteadyMono", "solve_AdvectionDiffusionSteadyMono_",
+    "AdvectionDiffusionUnsteadyMono", "solve_AdvectionDiffusionUnsteadyMono_",
 ]
 
 Steady, Unsteady = "Steady", "Unsteady"
 Monophasic, Diphasic = "Monophasic", "Diphasic"
 Diffusion = "Diffusion"
+DiffusionAdvection = "DiffusionAdvection"
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -348,6 +351,21 @@ class DiffusionOps:
                 L.lib().pb200_ops_destroy(self._h)
         except Exception:
             pass
+
+
+class ConvectionOps(DiffusionOps):
+    """``ConvectionOps(capacity, uₒ, uᵧ)`` (src/operators.jl:194-209): the diffusion operators plus the advective ones, C_d = D_p diag(S_m A_d uₒ_d) S_m
+    and K_d = diag(S_p H' uᵧ), as coefficient arrays on the device (``pb200_ops_set_convection``).  ``uₒ``: N arrays of n bulk velocity components,
+    ``uᵧ``: N n interface velocity components."""
+
+    def __init__(self, capacity, uₒ, uᵧ):
+        super().__init__(capacity)
+        n, N = capacity.nloc, capacity.N
+        uo = np.ascontiguousarray(np.concatenate([np.asarray(u, float).reshape(-1) for u in uₒ]))
+        ug = np.ascontiguousarray(np.asarray(uᵧ, float).reshape(-1))
+        if uo.shape != (N * n,) or ug.shape != (N * n,):
+            raise ValueError("ConvectionOps: uₒ must hold N arrays of n values and uᵧ N n values")
+        L.check(L.lib().pb200_ops_set_convection(self._h, _dp(uo), _dp(ug)), self._ctx.h)
 
 
 def grad(operator, p):
@@ -705,6 +723,57 @@ def solve_DiffusionUnsteadyDiph_(s, phase1, phase2, Δt, Tₑ, bc_b, ic, scheme,
 
 
 # ---- Darcy (src/solver/darcy.jl:1-89): the diffusion systems under another name + the velocity u = -∇p ---------------------------
+# ---- advection-diffusion (src/solver/advectiondiffusion.jl) -- the same solver objects on ConvectionOps -------------------------------------
+def AdvectionDiffusionSteadyMono(phase, bc_b, bc_i):
+    """src/solver/advectiondiffusion.jl:12-28"""
+    if not isinstance(phase.operator, ConvectionOps):
+        raise TypeError("AdvectionDiffusionSteadyMono needs a phase built on ConvectionOps")
+    s = Solver(Steady, Monophasic, DiffusionAdvection)
+    _make_solver(s, phase, None, bc_i, None)
+    _set_borders(s, phase.capacity.mesh, bc_b, None)
+    s._args = (bc_i, None)
+    return s
+
+
+def solve_AdvectionDiffusionSteadyMono_(s, method="gmres", algorithm=None, **kw):
+    """src/solver/advectiondiffusion.jl:65-71 (``gmres`` in the reference; the device solves the same rows with BiCGSTAB)"""
+    if s._h is None:
+        raise RuntimeError("Solver is not initialized. Call a solver constructor first.")
+    _step(s, "BE", None, None, s._args[0], None, _krylov_opts(method, kw))
+    return s
+
+
+def AdvectionDiffusionUnsteadyMono(phase, bc_b, bc_i, Δt, Tᵢ, scheme):
+    """src/solver/advectiondiffusion.jl:163-176: the constructor's system carries NO border rows (they enter in the loop, :273)."""
+    if not isinstance(phase.operator, ConvectionOps):
+        raise TypeError("AdvectionDiffusionUnsteadyMono needs a phase built on ConvectionOps")
+    s = Solver(Unsteady, Monophasic, DiffusionAdvection)
+    _make_solver(s, phase, None, bc_i, None)
+    _set_state(s, Tᵢ)
+    s._first = ("CN" if scheme == "CN" else "BE", float(Δt), bc_i)
+    return s
+
+
+def solve_AdvectionDiffusionUnsteadyMono_(s, phase, Δt, Tₑ, bc_b, bc, scheme, method="gmres", algorithm=None, states_stride=1, **kw):
+    """src/solver/advectiondiffusion.jl:254-283 (the loop's RHS call with the diffusion coefficient the reference's text omits at :272)."""
+    if s._h is None:
+        raise RuntimeError("Solver is not initialized. Call a solver constructor first.")
+    opts = _krylov_opts(method, kw)
+    sch0, dt0, bc0 = s._first
+    t = 0.0
+    _step(s, sch0, dt0, 0.0, bc0, None, opts)
+    s.states.append(s.x)
+    k = 0
+    while t < Tₑ:
+        t += Δt
+        _set_borders(s, phase.capacity.mesh, bc_b, t)
+        _step(s, scheme, Δt, t, bc, None, opts)
+        k += 1
+        if k % states_stride == 0:
+            s.states.append(s.x)
+    return s
+
+
 def DarcyFlow(phase, bc_b, bc_i):
     """src/solver/darcy.jl:1-15 -- the steady monophasic diffusion system (A_mono_stead_diff / b_mono_stead_diff + border rows)."""
     return DiffusionSteadyMono(phase, bc_b, bc_i)

@@ -53,14 +53,16 @@ __global__ void k_rhs_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, const 
         double Rbk = 0.0, Rik = 0.0, Rbe = 0.0, Rie = 0.0;
         GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
         // zero for every other row: nothing known is within reach; skip_known: k_rhs_known_mono adds it for the listed rows afterwards
-        if (!skip_known && (wi || (mb & MB_KNBR))) phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
+        double Cvk = 0.0, Cve = 0.0;   // advective parts (conv_row, operators.cuh): known values / explicit CN part
+        if (!skip_known && (wi || (mb & MB_KNBR))) { phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik); Cvk = conv_row<N>(p, g, l, c, ufix, gk); }
         if (sc.cn) {
             GamSpec ge = {Tg, 1.0, nullptr, 0.0, 0.0};
             phase_rows<N>(p, g, l, c, Tw, ge, Rbe, Rie);
+            Cve = conv_row<N>(p, g, l, c, Tw, ge);
         }
         if (wb) {
-            double v = sc.cV * V * Tw[l] + V * (sc.wf0 * src_at(f0, l) + sc.wf1 * src_at(f1, l)) - sc.ce * D * Rbe
-                       - sc.c * D * Rbk;   // (ufix is zero on a free row)
+            double v = sc.cV * V * Tw[l] + V * (sc.wf0 * src_at(f0, l) + sc.wf1 * src_at(f1, l)) - sc.ce * (D * Rbe + Cve)
+                       - sc.c * (D * Rbk + Cvk);   // (ufix is zero on a free row)
             if (sc.sym) v /= D;
             bb[l] = v;
         } else bb[l] = 0.0;
@@ -98,21 +100,22 @@ __global__ void k_rhs_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, StepC
         GamSpec gk2 = {nullptr, 0.0, nullptr, 0.0, 0.0};
         double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0, Rbe1 = 0, Rie1 = 0, Rbe2 = 0, Rie2 = 0;
         // the known part is zero unless something known is within the row's reach (MB_KNBR) -- or the row is an interface row
+        double Ck1 = 0, Ck2 = 0, Ce1 = 0, Ce2 = 0;   // advective parts (conv_row, operators.cuh)
         if (!skip_known) {
-            if ((w1 && (a & MB_KNBR)) || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
-            if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
+            if ((w1 && (a & MB_KNBR)) || ww) { phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1); if (w1) Ck1 = conv_row<N>(p1, g, l, c, ufix1, gk1); }
+            if ((w2 && (b & MB_KNBR)) || ww) { phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2); if (w2) Ck2 = conv_row<N>(p2, g, l, c, ufix2, gk2); }
         }
         if (sc.cn) {
             GamSpec ge1 = {Tg1, 1.0, nullptr, 0.0, 0.0}, ge2 = {Tg2, 1.0, nullptr, 0.0, 0.0};
-            if (w1) phase_rows<N>(p1, g, l, c, Tw1, ge1, Rbe1, Rie1);
-            if (w2) phase_rows<N>(p2, g, l, c, Tw2, ge2, Rbe2, Rie2);
+            if (w1) { phase_rows<N>(p1, g, l, c, Tw1, ge1, Rbe1, Rie1); Ce1 = conv_row<N>(p1, g, l, c, Tw1, ge1); }
+            if (w2) { phase_rows<N>(p2, g, l, c, Tw2, ge2, Rbe2, Rie2); Ce2 = conv_row<N>(p2, g, l, c, Tw2, ge2); }
         }
         const double V1 = p1.V[l], V2 = p2.V[l];
-        b1[l] = w1 ? sc.cV * V1 * Tw1[l] + V1 * (sc.wf0 * src_at(f10, l) + sc.wf1 * src_at(f11, l)) - sc.ce * D_at(p1, l) * Rbe1
-                         - sc.c * D_at(p1, l) * Rbk1       /* (ufix is zero on a free row) */
+        b1[l] = w1 ? sc.cV * V1 * Tw1[l] + V1 * (sc.wf0 * src_at(f10, l) + sc.wf1 * src_at(f11, l)) - sc.ce * (D_at(p1, l) * Rbe1 + Ce1)
+                         - sc.c * (D_at(p1, l) * Rbk1 + Ck1)       /* (ufix is zero on a free row) */
                    : 0.0;
-        b2[l] = w2 ? sc.cV * V2 * Tw2[l] + V2 * (sc.wf0 * src_at(f20, l) + sc.wf1 * src_at(f21, l)) - sc.ce * D_at(p2, l) * Rbe2
-                         - sc.c * D_at(p2, l) * Rbk2
+        b2[l] = w2 ? sc.cV * V2 * Tw2[l] + V2 * (sc.wf0 * src_at(f20, l) + sc.wf1 * src_at(f21, l)) - sc.ce * (D_at(p2, l) * Rbe2 + Ce2)
+                         - sc.c * (D_at(p2, l) * Rbk2 + Ck2)
                    : 0.0;
         bw[l] = ww ? p2.Gam[l] * src_at(hj, l) - (sp.b1 * Rik1 + sp.b2 * Rik2) : 0.0;
     }

@@ -16,6 +16,9 @@ struct PhaseDev {
     const double *A[PB_MAXD], *B[PB_MAXD], *Wd[PB_MAXD];
     const double *Darr;  // per-cell D or nullptr
     double Dc;           // constant D when Darr == nullptr
+    // advection (ConvectionOps, /root/reference/src/operators.jl:194-209): nullptr without it
+    const double *cf[PB_MAXD];   // cf_d = S_m (A_d u_d): the face flux coefficient of C_d = D_p diag(cf_d) S_m
+    const double *kd;            // 0.5 sum_d S_p^(d) (H' u_gamma): the diagonal of 0.5 sum_d K_d
 };
 
 // gamma "spec": value(l) = scale * (ptr ? ptr[l] : 0) + (off_ptr ? off_scale * off_ptr[l] : 0) + cst
@@ -64,6 +67,62 @@ __device__ __forceinline__ void phase_rows(const PhaseDev &ph, const Grid &g, in
         }
         Rb += bi * (ei * qL - qU);
         Ri += ei * (ai - bi) * qL - hpU * qU;
+    }
+}
+
+// advective part of a bulk row (A_mono_unstead_advdiff, /root/reference/src/solver/advectiondiffusion.jl:178-210):
+//   [(sum_d C_d + 0.5 sum_d K_d) u + 0.5 sum_d K_d gamma]_l,   (C_d u)_l = w_{l+s} - w_l  (0 on the last padded index),
+//   w_j = cf_j (S_m u)_j,  (S_m u)_j = (u_j + u_{j-1}) / 2  below the last index,  u_{j-1} / 2  on it  (delta_p, Sigma_m of src/operators.jl:8-12)
+template <int N>
+__device__ __forceinline__ double conv_row(const PhaseDev &ph, const Grid &g, int64_t l, const int c[PB_MAXD], const double *__restrict__ u, const GamSpec &gs)
+{
+    if (!ph.kd) return 0.0;
+    const double ui = u ? u[l] : 0.0;
+    double r = ph.kd[l] * (ui + gam_at(gs, l));
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int64_t s = g.stride[d];
+        const int id = c[d], last = g.pd[d] - 1;
+        if (id >= last) continue;                               // delta_p: the last row is zero
+        const double um = (id > 0 && u) ? u[l - s] : 0.0, up = u ? u[l + s] : 0.0;
+        const double wl = ph.cf[d][l] * 0.5 * (ui + um);        // (id < last: the regular Sigma_m row)
+        const double wu = ph.cf[d][l + s] * 0.5 * (id + 1 < last ? up + ui : ui);
+        r += wu - wl;
+    }
+    return r;
+}
+template <int N>
+__device__ __forceinline__ double conv_diag(const PhaseDev &ph, const Grid &g, int64_t l, const int c[PB_MAXD])
+{
+    if (!ph.kd) return 0.0;
+    double r = ph.kd[l];
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int id = c[d], last = g.pd[d] - 1;
+        if (id < last) r += 0.5 * (ph.cf[d][l + g.stride[d]] - ph.cf[d][l]);
+    }
+    return r;
+}
+// ConvectionOps set-up: cf_d = S_m (A_d u_d), kd = 0.5 sum_d S_p^(d) q with q = H' u_gamma (computed by k_div)
+template <int N>
+__global__ void k_conv_coef(Grid g, PhaseDev ph, const double *__restrict__ uo, const double *__restrict__ q, double *__restrict__ cf, double *__restrict__ kd)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < g.nown; t += (int64_t)gridDim.x * blockDim.x) {
+        int c[PB_MAXD];
+        cell_coords(g, t, c);
+        const int64_t l = t + g.plane;
+        double k = 0.0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            const int64_t s = g.stride[d];
+            const int id = c[d], last = g.pd[d] - 1;
+            const double *__restrict__ A = ph.A[d];
+            const double *__restrict__ ud = uo + (int64_t)d * g.nloc;
+            const double am = id > 0 ? A[l - s] * ud[l - s] : 0.0;
+            cf[(int64_t)d * g.nloc + l] = id < last ? 0.5 * (A[l] * ud[l] + am) : 0.5 * am;      // Sigma_m: [n, n] = 0
+            if (id < last) k += 0.5 * (q[l] + q[l + s]);                                           // Sigma_p: last row zero
+        }
+        kd[l] = 0.5 * k;
     }
 }
 
@@ -301,7 +360,7 @@ __global__ void k_apply_mono(Grid g, PhaseDev p, SysParams sp, ApplyCoef ac, con
         if (wb || wi) phase_rows<N>(p, g, l, c, u, gs, Rb, Ri);
         const double D = D_at(p, l);
         if (wb) {
-            double v = ac.cV * p.V[l] * (u ? u[l] : 0.0) + ac.c * D * Rb;
+            double v = ac.cV * p.V[l] * (u ? u[l] : 0.0) + ac.c * (D * Rb + conv_row<N>(p, g, l, c, u, gs));
             if (ac.sym) v /= D;
             yb[l] = v;
         } else yb[l] = 0.0;
@@ -330,8 +389,8 @@ __global__ void k_apply_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, App
         double Rb1 = 0.0, Ri1 = 0.0, Rb2 = 0.0, Ri2 = 0.0;
         if (w1 || ww) phase_rows<N>(p1, g, l, c, u1, g1, Rb1, Ri1);
         if (w2 || ww) phase_rows<N>(p2, g, l, c, u2, g2, Rb2, Ri2);
-        y1[l] = w1 ? ac.cV * p1.V[l] * (u1 ? u1[l] : 0.0) + ac.c * D_at(p1, l) * Rb1 : 0.0;
-        y2[l] = w2 ? ac.cV * p2.V[l] * (u2 ? u2[l] : 0.0) + ac.c * D_at(p2, l) * Rb2 : 0.0;
+        y1[l] = w1 ? ac.cV * p1.V[l] * (u1 ? u1[l] : 0.0) + ac.c * (D_at(p1, l) * Rb1 + conv_row<N>(p1, g, l, c, u1, g1)) : 0.0;
+        y2[l] = w2 ? ac.cV * p2.V[l] * (u2 ? u2[l] : 0.0) + ac.c * (D_at(p2, l) * Rb2 + conv_row<N>(p2, g, l, c, u2, g2)) : 0.0;
         yw[l] = ww ? sp.b1 * Ri1 + sp.b2 * Ri2 : 0.0;
     }
 }
@@ -348,7 +407,7 @@ __global__ void k_diag_mono(Grid g, PhaseDev p, SysParams sp, ApplyCoef ac, cons
         double GG, HH; bool r, h;
         phase_diag<N>(p, g, l, c, GG, HH, r, h);
         const double D = D_at(p, l);
-        double vb = ac.cV * p.V[l] + ac.c * D * GG;
+        double vb = ac.cV * p.V[l] + ac.c * (D * GG + conv_diag<N>(p, g, l, c));
         if (ac.sym) vb /= D;
         db[l] = (m[l] & MB_FREE) ? vb : 1.0;
         if (di) {
@@ -369,8 +428,8 @@ __global__ void k_diag_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp, Appl
         double GG1, HH1, GG2, HH2; bool r, h;
         phase_diag<N>(p1, g, l, c, GG1, HH1, r, h);
         phase_diag<N>(p2, g, l, c, GG2, HH2, r, h);
-        d1[l] = (m1[l] & MB_FREE) ? ac.cV * p1.V[l] + ac.c * D_at(p1, l) * GG1 : 1.0;
-        d2[l] = (m2[l] & MB_FREE) ? ac.cV * p2.V[l] + ac.c * D_at(p2, l) * GG2 : 1.0;
+        d1[l] = (m1[l] & MB_FREE) ? ac.cV * p1.V[l] + ac.c * (D_at(p1, l) * GG1 + conv_diag<N>(p1, g, l, c)) : 1.0;
+        d2[l] = (m2[l] & MB_FREE) ? ac.cV * p2.V[l] + ac.c * (D_at(p2, l) * GG2 + conv_diag<N>(p2, g, l, c)) : 1.0;
         dw[l] = (m2[l] & MB_IFREE) ? sp.b1 * (sp.a2 / sp.a1) * HH1 + sp.b2 * HH2 : 1.0;
     }
 }

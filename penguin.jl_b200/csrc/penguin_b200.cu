@@ -309,6 +309,7 @@ struct pb200_ops {
     pb200_ctx *ctx;          // (kept here: the destroy path must not reach through `cap`, which a garbage-collected host may have released first)
     pb200_capacity *cap;
     double *Wd[PB_MAXD] = {};
+    double *cf = nullptr, *kd = nullptr;   // ConvectionOps (pb200_ops_set_convection): [N][nloc] face flux coefficients, [nloc] interface-velocity diagonal
 };
 static PhaseDev phase_dev(const pb200_ops *o, const double *Darr, double Dc)
 {
@@ -316,6 +317,8 @@ static PhaseDev phase_dev(const pb200_ops *o, const double *Darr, double Dc)
     p.V = o->cap->V; p.Gam = o->cap->Gam;
     for (int d = 0; d < PB_MAXD; ++d) { p.A[d] = o->cap->A[d]; p.B[d] = o->cap->B[d]; p.Wd[d] = o->Wd[d]; }
     p.Darr = Darr; p.Dc = Dc;
+    for (int d = 0; d < PB_MAXD; ++d) p.cf[d] = o->cf ? o->cf + (int64_t)d * o->cap->g.nloc : nullptr;
+    p.kd = o->kd;
     return p;
 }
 static inline int sgrid(pb200_ctx *ctx, int64_t n) { return red_grid(ctx, n); }
@@ -347,7 +350,36 @@ extern "C" int pb200_ops_destroy(pb200_ops *o)
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     for (int d = 0; d < PB_MAXD; ++d) dev_free(o->Wd[d]);
+    dev_free(o->cf); dev_free(o->kd);
     delete o;
+    return PB200_OK;
+}
+// ConvectionOps(capacity, u_omega, u_gamma) (/root/reference/src/operators.jl:194-209): the operators gain the advective terms
+//   C_d = D_p diag(S_m A_d u_omega_d) S_m   and   K_d = diag(S_p H' u_gamma)
+// as two coefficient sets on the device -- cf_d = S_m (A_d u_omega_d) per direction and kd = 0.5 sum_d S_p^(d) (H' u_gamma) -- that the
+// matrix-free rows read (conv_row, operators.cuh).  u_omega: N blocks of n values, u_gamma: N blocks of n values (host, padded grid).
+extern "C" int pb200_ops_set_convection(pb200_ops *o, const double *u_omega, const double *u_gamma)
+{
+    if (!o || !u_omega || !u_gamma) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!o->parts.empty() || o->cap->ctx->nranks > 1) return set_err(o->ctx, PB200_EUNSUPPORTED, "advection-diffusion runs on one GPU so far");
+    pb200_ctx *ctx = o->cap->ctx;
+    const Grid &g = o->cap->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    double *uo = nullptr, *ug = nullptr, *zero = nullptr, *q = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &uo, g.nloc * g.N)) || (rc = dev_alloc(ctx, &ug, g.nloc * g.N)) || (rc = dev_alloc(ctx, &zero, g.nloc * g.N)) || (rc = dev_alloc(ctx, &q, g.nloc))) return rc;
+    for (int d = 0; d < g.N; ++d) {
+        if ((rc = upload_owned(ctx, g, uo + (int64_t)d * g.nloc, u_omega + (int64_t)d * g.nown))) return rc;
+        if ((rc = upload_owned(ctx, g, ug + (int64_t)d * g.nloc, u_gamma + (int64_t)d * g.nown))) return rc;
+    }
+    if (!o->cf && ((rc = dev_alloc(ctx, &o->cf, g.nloc * g.N)) || (rc = dev_alloc(ctx, &o->kd, g.nloc)))) return rc;
+    PhaseDev ph = phase_dev(o, nullptr, 1.0);
+    DISPATCH_N(g.N, (k_div<N><<<sgrid(ctx, g.nown), RED_THREADS, 0, ctx->stream>>>(g, ph, zero, ug, q)));      // q = H' u_gamma  (-(G' + H') 0 + H' u_gamma)
+    LAUNCH_CHECK(ctx);
+    DISPATCH_N(g.N, (k_conv_coef<N><<<sgrid(ctx, g.nown), RED_THREADS, 0, ctx->stream>>>(g, ph, uo, q, o->cf, o->kd)));
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(uo); dev_free(ug); dev_free(zero); dev_free(q);
     return PB200_OK;
 }
 extern "C" int pb200_ops_export_wdag(pb200_ops *o, double *wdag)
@@ -739,6 +771,7 @@ static int apply_op(pb200_solver *s, const ApplyCoef &ac, const MVec &in, const 
 static bool fold_eligible(const pb200_solver *s)
 {
     const SysParams &sp = s->sp;
+    if (s->p1.kd || s->p2.kd) return false;   // advection: the system is not symmetric -- reference rows, BiCGSTAB
     if (has_slave_rows(s)) return false;   // 1-D Neumann border rows: eliminated unknowns that follow a neighbour -- generic path only
     if (sp.phase_type == PB200_MONO) {
         if (sp.beta == 0.0) return true;                       // Dirichlet interface: T_gamma known, SPD bulk system
@@ -2067,7 +2100,9 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     const bool use_fold = o.path != PB200_PATH_GENERIC && fold_eligible(s);
     // AUTO: the folded system is symmetric positive definite for mono AND diphasic problems, so CG (one operator apply per
     // iteration) is the cheaper choice there; the reference's rows of the diphasic system are not symmetric => BiCGSTAB.
-    if (method == PB200_KRYLOV_AUTO) method = (use_fold || !diph) ? PB200_KRYLOV_CG : PB200_KRYLOV_BICGSTAB;
+    const bool advect = s->p1.kd || s->p2.kd;   // ConvectionOps: non-symmetric rows (gmres in the reference, src/solver/advectiondiffusion.jl:61) -> BiCGSTAB
+    if (method == PB200_KRYLOV_AUTO) method = ((use_fold || !diph) && !advect) ? PB200_KRYLOV_CG : PB200_KRYLOV_BICGSTAB;
+    if (method == PB200_KRYLOV_CG && advect) return set_err(ctx, PB200_EUNSUPPORTED, "CG on an advection-diffusion system (not symmetric); use BiCGSTAB");
     if (method == PB200_KRYLOV_CG && diph && !use_fold)
         return set_err(ctx, PB200_EUNSUPPORTED, "CG on the diphasic system needs the folded (symmetrised) path; use BiCGSTAB");
     (void)nonconstD;
