@@ -100,6 +100,8 @@ int pb200_ops_div(pb200_ops *ops, const double *q_omega, const double *q_gamma, 
  * A solver created on such operators is the reference's AdvectionDiffusion{Steady,Unsteady}{Mono,Diph} (src/solver/advectiondiffusion.jl:12-418):
  * bulk rows gain (sum_d C_d + 0.5 sum_d K_d) T_omega + 0.5 sum_d K_d T_gamma; solved with BiCGSTAB on the reference's rows (one GPU).          */
 int pb200_ops_set_convection(pb200_ops *ops, const double *u_omega, const double *u_gamma);
+/* the coefficient arrays behind it: cf (ndim*nloc: S_m A_d u_omega_d, so that C_d = D_p diag(cf_d) S_m) and kd (nloc: diag of 0.5 sum_d K_d); NULL = skip */
+int pb200_ops_export_convection(pb200_ops *ops, double *cf, double *kd);
 /* W! diagonal (1/W, 1.0 where W == 0 -- src/operators.jl:145-152), component-major ndim*nloc              */
 int pb200_ops_export_wdag(pb200_ops *ops, double *wdag);
 int pb200_ops_destroy(pb200_ops *ops);

@@ -374,6 +374,56 @@ function solve_DiffusionUnsteadyDiph!(s::Solver, ph1::Phase, ph2::Phase, Δt::Fl
     s
 end
 
+# ---- advection-diffusion (src/operators.jl:194-209, src/solver/advectiondiffusion.jl:12-283): ConvectionOps + the monophasic solvers ------
+# ConvectionOps(cap, uₒ, uᵧ): the diffusion operator handle gains the advective coefficient arrays on the device; C and K are never assembled
+# (the struct keeps empty matrices, `size` and `V` stay as in the reference).
+function ConvectionOps(cap::Capacity{N}, uₒ, uᵧ) where {N}
+    haskey(B200_HANDLES, cap) || return invoke(ConvectionOps, Tuple{AbstractCapacity,Any,Any}, cap, uₒ, uᵧ)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    pbcheck(ccall((:pb200_ops_create, libpb), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), b200_handle(cap), h))
+    uo = Float64.(vcat((vec(u) for u in uₒ)...)); ug = Float64.(vec(uᵧ))
+    pbcheck(ccall((:pb200_ops_set_convection, libpb), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], uo, ug))
+    n = prod(length.(cap.mesh.nodes)); Z = spzeros(n, n)
+    op = ConvectionOps{N}(ntuple(_ -> Z, N), ntuple(_ -> Z, N), spzeros(N * n, n), spzeros(N * n, n), spzeros(N * n, N * n), cap.V, ntuple(i -> length(cap.mesh.nodes[i]), N))
+    b200_register!(op, h[], :pb200_ops_destroy); op
+end
+function AdvectionDiffusionSteadyMono(phase::Phase, bc_b::BorderConditions, bc_i::AbstractBoundary)              # advectiondiffusion.jl:12-28
+    b200_on_device(phase) || return invoke(AdvectionDiffusionSteadyMono, Tuple{Any,Any,Any}, phase, bc_b, bc_i)
+    s = Solver(Steady, Monophasic, DiffusionAdvection, nothing, nothing, nothing, [], [])
+    b200_register!(s, b200_make_solver(0, Monophasic, phase, nothing, bc_i, nothing), :pb200_solver_destroy)
+    set_borders!(b200_handle(s), phase.capacity.mesh, bc_b, nothing)
+    B200_FIRST[s] = (phase, nothing, bc_i, nothing); s
+end
+function solve_AdvectionDiffusionSteadyMono!(s::Solver; method = nothing, algorithm = nothing, kwargs...)          # :65-71 (gmres there, BiCGSTAB on the device)
+    haskey(B200_HANDLES, s) || return invoke(solve_AdvectionDiffusionSteadyMono!, Tuple{Any}, s; method = method, algorithm = algorithm, kwargs...)
+    ph, _, bc_i, _ = B200_FIRST[s]
+    b200_step!(s, ph, nothing, bc_i, nothing, "BE", 0.0, nothing, krylov_opts(nothing, kwargs), false); s
+end
+function AdvectionDiffusionUnsteadyMono(phase::Phase, bc_b::BorderConditions, bc_i::AbstractBoundary, Δt::Float64, Tᵢ::Vector{Float64}, scheme::String)   # :163-176
+    b200_on_device(phase) || return invoke(AdvectionDiffusionUnsteadyMono, Tuple{Any,Any,Any,Any,Any,Any}, phase, bc_b, bc_i, Δt, Tᵢ, scheme)
+    s = Solver(Unsteady, Monophasic, DiffusionAdvection, nothing, nothing, nothing, [], [])
+    b200_register!(s, b200_make_solver(1, Monophasic, phase, nothing, bc_i, nothing), :pb200_solver_destroy)
+    pbcheck(ccall((:pb200_solver_set_state, libpb), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), b200_handle(s), Tᵢ))
+    B200_FIRST[s] = (scheme == "CN" ? "CN" : "BE", Δt, bc_i); s                   # NO border rows in the constructor's system (the reference applies none, :172-176)
+end
+function solve_AdvectionDiffusionUnsteadyMono!(s::Solver, phase::Phase, Δt::Float64, Tₑ, bc_b::BorderConditions, bc::AbstractBoundary, scheme::String;
+                                               method = nothing, algorithm = nothing, kwargs...)                                                       # :254-283
+    haskey(B200_HANDLES, s) || return invoke(solve_AdvectionDiffusionUnsteadyMono!, Tuple{Any,Any,Any,Any,Any,Any,Any}, s, phase, Δt, Tₑ, bc_b, bc, scheme;
+                                             method = method, algorithm = algorithm, kwargs...)
+    opts = krylov_opts(nothing, kwargs)
+    sch0, dt0, bc0 = B200_FIRST[s]
+    b200_step!(s, phase, nothing, bc0, nothing, sch0, dt0, 0.0, opts, true)
+    push!(s.states, s.x); println("Time: 0.0"); println("Solver Extremum: ", maximum(abs.(s.x)))
+    t = 0.0
+    while t < Tₑ
+        t += Δt
+        set_borders!(b200_handle(s), phase.capacity.mesh, bc_b, t)               # BC_border_mono!(…; t = t) (:273)
+        b200_step!(s, phase, nothing, bc, nothing, scheme, Δt, t, opts, true)   # (the reference's RHS call at :272 drops the diffusion coefficient: a MethodError as written)
+        push!(s.states, s.x); println("Time: ", t); println("Solver Extremum: ", maximum(abs.(s.x)))
+    end
+    s
+end
+
 # ---- Darcy (src/solver/darcy.jl:1-89): the diffusion systems under another name + the velocity u = -∇p -------------------------------
 DarcyFlow(phase::Phase, bc_b::BorderConditions, bc_i::AbstractBoundary) = DiffusionSteadyMono(phase, bc_b, bc_i)
 solve_DarcyFlow!(s::Solver; kw...) = (solve_DiffusionSteadyMono!(s; kw...); push!(s.states, s.x); s)

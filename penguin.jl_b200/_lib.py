@@ -60,6 +60,7 @@ SYMBOLS = {
     "pb200_ops_create": ([C.c_void_p, C.POINTER(C.c_void_p)], C.c_int),
     "pb200_ops_grad": ([C.c_void_p, dp, dp], C.c_int),
     "pb200_ops_set_convection": ([C.c_void_p, dp, dp], C.c_int),
+    "pb200_ops_export_convection": ([C.c_void_p, dp, dp], C.c_int),
     "pb200_ops_div": ([C.c_void_p, dp, dp, dp], C.c_int),
     "pb200_ops_export_wdag": ([C.c_void_p, dp], C.c_int),
     "pb200_ops_destroy": ([C.c_void_p], C.c_int),

@@ -367,6 +367,13 @@ class ConvectionOps(DiffusionOps):
             raise ValueError("ConvectionOps: uₒ must hold N arrays of n values and uᵧ N n values")
         L.check(L.lib().pb200_ops_set_convection(self._h, _dp(uo), _dp(ug)), self._ctx.h)
 
+    def coefficients(self):
+        """(cf, kd): cf[d] = S_m A_d uₒ_d (C_d = D_p diag(cf[d]) S_m), kd = diag(0.5 Σ_d K_d) -- what the device rows read"""
+        n, N = self.capacity.nloc, self.capacity.N
+        cf, kd = np.empty(N * n), np.empty(n)
+        L.check(L.lib().pb200_ops_export_convection(self._h, _dp(cf), _dp(kd)), self._ctx.h)
+        return [cf[d * n:(d + 1) * n] for d in range(N)], kd
+
 
 def grad(operator, p):
     """``∇(operator, p) = Wꜝ (G p_ω + H p_γ)`` (src/operators.jl:20-23)."""

@@ -140,7 +140,7 @@ __global__ void k_rhs_known_mono(Grid g, PhaseDev p, SysParams sp, StepCoef sc, 
         double Rbk, Rik;
         GamSpec gk = {gK, 1.0, nullptr, 0.0, 0.0};
         phase_rows<N>(p, g, l, c, ufix, gk, Rbk, Rik);
-        if (wb) { double v = sc.c * D_at(p, l) * Rbk; if (sc.sym) v /= D_at(p, l); bb[l] -= v; }
+        if (wb) { double v = sc.c * (D_at(p, l) * Rbk + conv_row<N>(p, g, l, c, ufix, gk)); if (sc.sym) v /= D_at(p, l); bb[l] -= v; }
         if (wi) {
             double v = sc.c2 * sp.beta * Rik;
             if (sc.sym) v *= sc.c / (sc.c2 * sp.beta);
@@ -168,8 +168,8 @@ __global__ void k_rhs_known_diph(Grid g, PhaseDev p1, PhaseDev p2, SysParams sp,
         double Rbk1 = 0, Rik1 = 0, Rbk2 = 0, Rik2 = 0;
         if ((w1 && (a & MB_KNBR)) || ww) phase_rows<N>(p1, g, l, c, ufix1, gk1, Rbk1, Rik1);
         if ((w2 && (b & MB_KNBR)) || ww) phase_rows<N>(p2, g, l, c, ufix2, gk2, Rbk2, Rik2);
-        if (w1) b1[l] -= sc.c * D_at(p1, l) * Rbk1;
-        if (w2) b2[l] -= sc.c * D_at(p2, l) * Rbk2;
+        if (w1) b1[l] -= sc.c * (D_at(p1, l) * Rbk1 + ((a & MB_KNBR) ? conv_row<N>(p1, g, l, c, ufix1, gk1) : 0.0));
+        if (w2) b2[l] -= sc.c * (D_at(p2, l) * Rbk2 + ((b & MB_KNBR) ? conv_row<N>(p2, g, l, c, ufix2, gk2) : 0.0));
         if (ww) bw[l] = (set_ifc ? p2.Gam[l] * src_at(hj, l) : bw[l]) - (sp.b1 * Rik1 + sp.b2 * Rik2);
     }
 }

@@ -103,6 +103,32 @@ __device__ __forceinline__ double conv_diag(const PhaseDev &ph, const Grid &g, i
     }
     return r;
 }
+// remove_zero_rows_cols! (src/solver.jl:59-78) keeps an unknown whose row AND column of the assembled matrix are non-zero.  The advective operators are
+// not symmetric and reach one cell further than the capacities of a cell say: cf_j = (a_j + a_{j-1}) / 2 is non-zero on a SOLID cell j whose lower
+// neighbour is fluid, so the reference keeps T_j of that solid cell as an unknown (row: -w_j = 0, i.e. T_j = -T_{j-1}).  This predicate reproduces it.
+template <int N>
+__device__ __forceinline__ bool conv_keeps(const PhaseDev &ph, const Grid &g, int64_t l, const int c[PB_MAXD])
+{
+    if (!ph.kd) return false;
+    double rs = 0.0, cs = 0.0, dg = ph.kd[l];
+    rs += fabs(ph.kd[l]);                       // (the T_gamma column of the row; counted although that column may be trimmed: kd != 0 only beside the interface)
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int64_t s = g.stride[d];
+        const int id = c[d], last = g.pd[d] - 1;
+        if (id < last) {
+            const double cl = ph.cf[d][l], cu = ph.cf[d][l + s];
+            dg += 0.5 * (cu - cl);
+            if (id + 1 < last) rs += fabs(0.5 * cu);      // coefficient of u[l + s] in row l
+            if (id > 0) rs += fabs(0.5 * cl);             // coefficient of u[l - s] in row l
+            // column l: rows l + s (exists below the last index) and l - s
+            if (id + 1 < last) cs += fabs(0.5 * cu);      // u[l] in w_{l+s}, row l + s:  -w_{l+s}
+            if (id > 0) cs += fabs(0.5 * cl);             // u[l] in w_l, row l - s:  +w_l
+        }
+    }
+    rs += fabs(dg); cs += fabs(dg);
+    return rs != 0.0 && cs != 0.0;
+}
 // ConvectionOps set-up: cf_d = S_m (A_d u_d), kd = 0.5 sum_d S_p^(d) q with q = H' u_gamma (computed by k_div)
 template <int N>
 __global__ void k_conv_coef(Grid g, PhaseDev ph, const double *__restrict__ uo, const double *__restrict__ q, double *__restrict__ cf, double *__restrict__ kd)
@@ -285,7 +311,7 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
         bool rowG, hrow1, hrow2 = false;
         phase_diag<N>(p1, g, l, c, GG, HH, rowG, hrow1);
         unsigned char b1 = 0, b2 = 0;
-        bool kept1 = (unsteady && p1.V[l] != 0.0) || rowG;
+        bool kept1 = (unsteady && p1.V[l] != 0.0) || rowG || conv_keeps<N>(p1, g, l, c);
         if (sp.phase_type == PB200_MONO) {
             if (dirichlet) { b1 |= MB_FIXED; ufix1[l] = bval; }
             else if (slave) { b1 |= MB_SLAVE; ufix1[l] = bval; }
@@ -297,7 +323,7 @@ __global__ void k_build_masks(Grid g, PhaseDev p1, PhaseDev p2, const double *__
         } else {
             bool rowG2;
             phase_diag<N>(p2, g, l, c, GG, HH, rowG2, hrow2);
-            bool kept2 = (unsteady && p2.V[l] != 0.0) || rowG2;
+            bool kept2 = (unsteady && p2.V[l] != 0.0) || rowG2 || conv_keeps<N>(p2, g, l, c);
             bool d1 = dirichlet && ct1[l] != 0.0, d2 = dirichlet && ct2[l] != 0.0;   // src/solver.jl:573-576
             const bool s1 = slave && ct1[l] != 0.0, s2 = slave && ct2[l] != 0.0;
             if (d1) { b1 |= MB_FIXED; ufix1[l] = bval; } else if (s1) { b1 |= MB_SLAVE; ufix1[l] = bval; } else { if (kept1) b1 |= MB_FREE; ufix1[l] = 0.0; }
@@ -408,6 +434,7 @@ __global__ void k_diag_mono(Grid g, PhaseDev p, SysParams sp, ApplyCoef ac, cons
         phase_diag<N>(p, g, l, c, GG, HH, r, h);
         const double D = D_at(p, l);
         double vb = ac.cV * p.V[l] + ac.c * (D * GG + conv_diag<N>(p, g, l, c));
+        if (vb == 0.0) vb = 1.0;       // (advection: a kept solid cell may have an empty diagonal; Jacobi then leaves the row alone)
         if (ac.sym) vb /= D;
         db[l] = (m[l] & MB_FREE) ? vb : 1.0;
         if (di) {

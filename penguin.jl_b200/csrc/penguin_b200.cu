@@ -443,6 +443,22 @@ extern "C" int pb200_ops_div(pb200_ops *o, const double *qo, const double *qg, d
     return PB200_OK;
 }
 
+/* the two coefficient sets of pb200_ops_set_convection back on the host: cf (ndim * n: S_m A_d u_omega_d) and kd (n: the diagonal of 0.5 sum_d K_d) */
+extern "C" int pb200_ops_export_convection(pb200_ops *o, double *cf, double *kd)
+{
+    if (!o) return set_err(nullptr, PB200_EINVAL, "NULL argument");
+    if (!o->parts.empty() || !o->cf) return set_err(o->ctx, PB200_EINVAL, "no convection on this operator handle");
+    pb200_ctx *ctx = o->cap->ctx;
+    const Grid &g = o->cap->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    for (int d = 0; d < g.N && cf; ++d)
+        if ((rc = download_owned(ctx, g, cf + (int64_t)d * g.nown, o->cf + (int64_t)d * g.nloc))) return rc;
+    if (kd && (rc = download_owned(ctx, g, kd, o->kd))) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+
 // =================================================================================================================
 // Solver
 // =================================================================================================================
@@ -2103,6 +2119,8 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     const bool advect = s->p1.kd || s->p2.kd;   // ConvectionOps: non-symmetric rows (gmres in the reference, src/solver/advectiondiffusion.jl:61) -> BiCGSTAB
     if (method == PB200_KRYLOV_AUTO) method = ((use_fold || !diph) && !advect) ? PB200_KRYLOV_CG : PB200_KRYLOV_BICGSTAB;
     if (method == PB200_KRYLOV_CG && advect) return set_err(ctx, PB200_EUNSUPPORTED, "CG on an advection-diffusion system (not symmetric); use BiCGSTAB");
+    if (advect && diph && in->scheme == PB200_CN)   // the reference's diphasic CN right-hand side drops the explicit diffusion part (advectiondiffusion.jl:372-376): not reproduced
+        return set_err(ctx, PB200_EUNSUPPORTED, "diphasic advection-diffusion with Crank-Nicolson is not supported (BE is)");
     if (method == PB200_KRYLOV_CG && diph && !use_fold)
         return set_err(ctx, PB200_EUNSUPPORTED, "CG on the diphasic system needs the folded (symmetrised) path; use BiCGSTAB");
     (void)nonconstD;
