@@ -187,6 +187,12 @@ typedef struct {
 #define PB200_PATH_AUTO 0
 #define PB200_PATH_GENERIC 1
 #define PB200_PATH_FOLDED 2
+/* PB200_PRECOND_DEFAULT: what DESIGN.md section 4 describes (block-Jacobi scaling + interface-band / Chebyshev polynomial preconditioners).
+ * PB200_PRECOND_MG: geometric multigrid V-cycle (csrc/mg.cuh: capacities rebuilt on the meshes n/2, n/4, ..., cell-aggregation transfers,
+ * Chebyshev smoothers) for systems whose condition number grows like n^2 -- the steady problems of src/solver/diffusion.jl:14-72.  Monophasic,
+ * Dirichlet interface, constant D, capacities built by pb200_capacity_create, one rank; PB200_EUNSUPPORTED otherwise.                         */
+#define PB200_PRECOND_DEFAULT 0
+#define PB200_PRECOND_MG 1
 typedef struct {
     int method;
     double rtol; /* stop when ||r|| <= max(rtol ||b||, atol)  (IterativeSolvers convention) */
@@ -195,6 +201,7 @@ typedef struct {
     int warm_start; /* 0: zero initial guess like the reference; 1: previous state; m >= 2: polynomial extrapolation through the last m states (m <= 5) */
     int check_every; /* convergence is tested on the host every this many iterations (>= 1) */
     int path;        /* PB200_PATH_*: which implementation of the solve runs */
+    int precond;     /* PB200_PRECOND_*: preconditioner of the CG on the folded path */
 } pb200_krylov_opts;
 
 typedef struct {

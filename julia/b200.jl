@@ -214,7 +214,7 @@ struct pb200_step_in
     g_arr::NTuple{2,Ptr{Cdouble}}
 end
 struct pb200_krylov_opts
-    method::Cint; rtol::Cdouble; atol::Cdouble; maxit::Cint; warm_start::Cint; check_every::Cint; path::Cint
+    method::Cint; rtol::Cdouble; atol::Cdouble; maxit::Cint; warm_start::Cint; check_every::Cint; path::Cint; precond::Cint
 end
 struct pb200_step_stats
     iters::Cint; converged::Cint; rnorm::Cdouble; bnorm::Cdouble; solve_ms::Cdouble; setup_ms::Cdouble
@@ -233,7 +233,7 @@ function krylov_opts(method, kwargs)
     m = name == "cg" ? 1 : startswith(name, "bicgstab") ? 2 : 0
     direct = method === nothing || name == "\\"
     rtol = Float64(get(kw, :reltol, direct ? 1e-13 : sqrt(eps(Float64))))        # IterativeSolvers default reltol = sqrt(eps) (SURVEY B.3)
-    pb200_krylov_opts(m, rtol, Float64(get(kw, :abstol, 0.0)), Int(get(kw, :maxiter, 20000)), Int(get(kw, :warm_start, 0)), 4, 0)
+    pb200_krylov_opts(m, rtol, Float64(get(kw, :abstol, 0.0)), Int(get(kw, :maxiter, 20000)), Int(get(kw, :warm_start, 0)), 4, 0, get(kw, :precond, :default) == :mg ? 1 : 0)
 end
 
 # ---- solver construction shared by the four constructors (src/solver/diffusion.jl:14-28, 88-102, 192-210, 319-332) -------------------

@@ -29,7 +29,7 @@ class StepIn(C.Structure):
 
 class KrylovOpts(C.Structure):
     _fields_ = [("method", C.c_int), ("rtol", C.c_double), ("atol", C.c_double), ("maxit", C.c_int),
-                ("warm_start", C.c_int), ("check_every", C.c_int), ("path", C.c_int)]
+                ("warm_start", C.c_int), ("check_every", C.c_int), ("path", C.c_int), ("precond", C.c_int)]
 
 
 class StepStats(C.Structure):

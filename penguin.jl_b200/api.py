@@ -570,6 +570,7 @@ def _krylov_opts(method, kw):
     o.warm_start = int(kw.get("warm_start", 1))
     o.check_every = int(kw.get("check_every", 4))
     o.path = {"auto": 0, "generic": 1, "folded": 2}[kw.get("path", "auto")]
+    o.precond = {"default": 0, "mg": 1, "multigrid": 1}[kw.get("precond", "default")]
     return o
 
 

@@ -173,6 +173,11 @@ struct pb200_capacity {
     double *V = nullptr, *Gam = nullptr, *ct = nullptr;
     double *A[PB_MAXD] = {}, *B[PB_MAXD] = {}, *W[PB_MAXD] = {}, *Co[PB_MAXD] = {}, *Cg[PB_MAXD] = {};
     bool has_cg = false;
+    // the level set the capacities were built from (pb200_capacity_create): the multigrid preconditioner rebuilds them on coarser meshes (mg.cuh)
+    bool has_ls = false;
+    int ls_kind = 0, ls_inside = 1, ls_hsdim = 0;
+    double ls_hsc = 0.0;
+    std::vector<double> ls_c, ls_r;
 };
 
 static int cap_alloc(pb200_ctx *ctx, pb200_capacity *c)
@@ -249,6 +254,8 @@ extern "C" int pb200_capacity_create(pb200_ctx *ctx, int ndim, const int *n, con
         go.V = c->V; go.Gam = c->Gam; go.ct = c->ct;
         for (int d = 0; d < PB_MAXD; ++d) { go.A[d] = c->A[d]; go.B[d] = c->B[d]; go.W[d] = c->W[d]; go.Co[d] = c->Co[d]; go.Cg[d] = c->Cg[d]; }
         if ((rc = geometry_build(ctx, c->g, ls, compute_centroids, go))) return rc;
+        c->has_ls = true; c->ls_kind = ls->kind; c->ls_inside = ls->fluid_inside; c->ls_hsdim = ls->hs_dim; c->ls_hsc = ls->hs_c;
+        if (ls->kind == PB200_LS_BALLS) { c->ls_c.assign(ls->centers, ls->centers + (size_t)ls->nballs * c->g.N); c->ls_r.assign(ls->radii, ls->radii + ls->nballs); }
         if ((rc = cap_halo(c))) return rc;
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return PB200_OK;
@@ -462,8 +469,12 @@ extern "C" int pb200_ops_export_convection(pb200_ops *o, double *cf, double *kd)
 // =================================================================================================================
 // Solver
 // =================================================================================================================
+struct MgHier;
+struct pb200_solver;
+static void mg_free(pb200_solver *s);
 struct pb200_solver {
     pb200_ctx *ctx;
+    MgHier *mg = nullptr;                  // multigrid hierarchy of the folded system (mg.cuh), built on first use
     std::vector<pb200_solver *> parts;     // team handle
     int team_nblk = 0;                     // blocks of the state vector (2 mono, 4 diph)
     Grid g;
@@ -578,6 +589,7 @@ extern "C" int pb200_solver_destroy(pb200_solver *s)
     }
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    mg_free(s);
     for (double *p : s->owned) cudaFree(p);
     fold_free(s->F);
     if (s->Kcell) cudaFree(s->Kcell);
@@ -909,6 +921,7 @@ static int fold_build(pb200_solver *s, const ApplyCoef &ac)
     pb200_ctx *ctx = s->ctx;
     const Grid &g = s->g;
     FoldSys &F = s->F;
+    mg_free(s);          // (the coarse levels mirror this system)
     fold_free(F);
     FoldDev &d = F.d;
     memset(&d, 0, sizeof(d));
@@ -1707,6 +1720,8 @@ static int fold_poly_setup(pb200_solver *s)
     return PB200_OK;
 }
 
+#include "mg.cuh"
+
 // Krylov solve of the folded system.  In: s->b (reference rows, known parts eliminated), s->x (initial guess on the free sets).
 // Out: s->x.  The stopping test ||r^|| <= max(rtol ||b^||, atol) is on the block-Jacobi-scaled residual.
 static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, const GuessSpec gsp[3], bool dense_done, int *iters, int *conv, double *rnorm_out,
@@ -1733,6 +1748,19 @@ static int fold_solve(pb200_solver *s, int method, const pb200_krylov_opts &o, c
     if (band) { kf_to_scaled_band<<<gb, 128, 0, ctx->stream>>>(F.d, s->b, F.b); LAUNCH_CHECK(ctx); }
     const bool cg = method == PB200_KRYLOV_CG;
     static_assert(FS_RR0 == FS_BB + 1, "kf_resid publishes the pair (bb, rr0)");
+    if (o.precond == PB200_PRECOND_MG) {   // multigrid-preconditioned CG (mg.cuh), zero initial guess
+        if (!cg) return set_err(ctx, PB200_EUNSUPPORTED, "the multigrid preconditioner is a CG preconditioner");
+        const ApplyCoef acm = {F.key[0], F.key[1], F.key[2], 0, 1};
+        if ((!s->mg || !s->mg->ready) && (rc = mg_setup(s, acm))) { mg_free(s); return rc; }
+        int itm = 0, cvm = 0;
+        double rn = 0.0, bn = 0.0;
+        if ((rc = mg_pcg(s, o, &itm, &cvm, &rn, &bn))) return rc;
+        prof_mark(ctx, PB_PROF_EPILOGUE);
+        kf_from_scaled_dense<<<wave_grid(s, kf_from_scaled_dense), FCH, 0, ctx->stream>>>(F.d, I, F.x, s->x); LAUNCH_CHECK(ctx);
+        prof_mark(ctx, PB_PROF_EPILOGUE);
+        *iters = itm; *conv = cvm; *rnorm_out = rn; *bnorm_out = bn;
+        return PB200_OK;
+    }
     // fused CG iteration (fold2.cuh): p update + apply in one TMA-staged kernel, ghost-class tiles and the halo exchange on a second stream
     const bool fused = cg && F.tma_ok && !getenv("PB200_NO_FUSED");
     if (fused && !F.have_p2) { if ((rc = fold_alloc_vec(s, &F.p2))) return rc; F.have_p2 = true; }

@@ -69,7 +69,7 @@ int main(int argc, char **argv)
     pb200_step_in si;
     memset(&si, 0, sizeof(si));
     si.scheme = PB200_BE; si.dt = 0.5 * h * h;
-    pb200_krylov_opts ko = {PB200_KRYLOV_AUTO, 1e-12, 0.0, 20000, 1, 4, PB200_PATH_AUTO};
+    pb200_krylov_opts ko = {PB200_KRYLOV_AUTO, 1e-12, 0.0, 20000, 1, 4, PB200_PATH_AUTO, PB200_PRECOND_DEFAULT};
     pb200_step_stats st;
     for (int k = 0; k < 3; ++k) {
         memset(&st, 0, sizeof(st));

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--repeat", type=int, default=2, help="solves (a steady solve always starts from a zero guess, penguin_b200.cu fold step); the first one builds the folded system and captures the graphs, the last one is timed")
     ap.add_argument("--path", default="auto", choices=["auto", "folded", "generic"])
+    ap.add_argument("--precond", default="default", choices=["default", "mg"], help="mg: geometric multigrid V-cycle as the CG preconditioner (csrc/mg.cuh, one GPU)")
     args = ap.parse_args()
     H = bench.Harness(args)
     pb, torch = H.pb, H.torch
@@ -65,7 +66,7 @@ def main():
     bc_b = pb.BorderConditions({k: pb.Dirichlet(0.0) for k in keys})
     s = pb.DiffusionSteadyMono(phase, bc_b, pb.Dirichlet(0.0))
     n = cap.nloc
-    kw = dict(reltol=args.rtol, maxiter=args.maxit, check_every=args.check_every, path=args.path)
+    kw = dict(reltol=args.rtol, maxiter=args.maxit, check_every=args.check_every, path=args.path, precond=args.precond)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = 0.0
     for k in range(max(1, args.repeat)):
@@ -82,11 +83,11 @@ def main():
     cells = cu + cg
     # per iteration of the fused CG: apply 6 passes + N coefficient arrays on the general tiles, update 3 passes
     it_bytes = H.allsum(8.0 * (9 * cells + 3 * cg))
-    agg = it_bytes * it / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    agg = it_bytes * it / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 and args.precond != "mg" else 0.0      # (the byte model is the plain CG iteration's)
     T = s.x[:n]
     out = {"workload": "steady Poisson 3-D, union of random disjoint spheres (fluid outside), f = 1, Dirichlet 0 on interface and borders (BASELINE.json configs[4])",
            "grid": [nx, nx, nx], "spheres": int(args.spheres), "seed": SEED, "n_gpus": N, "dof": dof, "rtol": args.rtol,
-           "krylov": "CG on the folded (block-Jacobi-scaled) system, no multigrid", "iterations": it, "converged": bool(ch["converged"]),
+           "krylov": "CG on the folded (block-Jacobi-scaled) system, " + ("multigrid V-cycle preconditioner (rediscretised levels, Chebyshev smoothers)" if args.precond == "mg" else "no multigrid"), "iterations": it, "converged": bool(ch["converged"]),
            "final_rel_residual": ch["rnorm"] / ch["bnorm"] if ch["bnorm"] else 0.0,
            "time_to_tolerance_ms": ms, "krylov_loop_ms": solve_ms, "prologue_ms": H.allmax(float(ch["setup_ms"])), "capacity_build_s": cap_s,
            "ms_per_iteration": solve_ms / max(it, 1), "dof_iterations_per_s": dof * it / (solve_ms * 1e-3) if solve_ms > 0 else 0.0,
