@@ -345,6 +345,78 @@ def run_heat3d(H, args, kind):
     return out
 
 
+POISSON_SEED = 20261018
+
+
+def random_spheres(K=64, L=4.0, seed=POISSON_SEED, rmin=0.1, rmax=0.3, margin=0.5, gap=0.11):
+    """BASELINE.json configs[4] geometry: K spheres, centres U[margin, L - margin]^3, radii U[rmin, rmax], rejection-sampled so that any two
+    surfaces are at least `gap` apart (two cell diagonals at 128^3: no cell, and no staggered volume between two barycentres, meets two spheres)."""
+    rng = np.random.default_rng(seed)
+    cen, rad = [], []
+    while len(cen) < K:
+        c = rng.uniform(margin, L - margin, 3)
+        r = rng.uniform(rmin, rmax)
+        if all(np.linalg.norm(c - c2) >= r + r2 + gap for c2, r2 in zip(cen, rad)):
+            cen.append(c)
+            rad.append(r)
+    return np.array(cen), np.array(rad)
+
+
+def run_poisson3d(H, nx, precond="default", spheres=64, rtol=1e-10, maxit=40000, check_every=16, repeat=2, path="auto"):
+    """BASELINE.json configs[4]: steady cut-cell Poisson (src/solver/diffusion.jl:14-72) around `spheres` random disjoint spheres (fluid outside), f = 1, D = 1,
+    Dirichlet 0 on the interface and on the six recognised border keys, CG to ||r|| <= rtol ||b|| through the public API (solve_DiffusionSteadyMono_, the D2H read
+    of solver.x included in time_to_tolerance_ms).  A "step" of this workload is one Krylov iteration: the system has no V / dt shift, kappa = O(n^2).
+    precond = "mg": geometric multigrid V-cycle (csrc/mg.cuh, one GPU).  `repeat` solves: the first builds the folded system (and the hierarchy), the last is timed."""
+    pb, torch = H.pb, H.torch
+    N = H.world
+    peak, peak_src = peaks()
+    mesh = pb.Mesh((nx, nx, nx), (4.0, 4.0, 4.0))
+    cen, rad = random_spheres(spheres)
+    body = pb.Balls(cen, rad, fluid_inside=False)
+    t0 = time.perf_counter()
+    cap = pb.Capacity(body, mesh, compute_centroids=False)
+    H.ctx.sync()
+    cap_s = time.perf_counter() - t0
+    phase = pb.Phase(cap, pb.DiffusionOps(cap), 1.0, 1.0)
+    keys = ("left", "right", "top", "bottom", "forward", "backward")
+    bc_b = pb.BorderConditions({k: pb.Dirichlet(0.0) for k in keys})
+    s = pb.DiffusionSteadyMono(phase, bc_b, pb.Dirichlet(0.0))
+    n = cap.nloc
+    kw = dict(reltol=rtol, maxiter=maxit, check_every=check_every, path=path, precond=precond)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, first_ms = 0.0, 0.0
+    for k in range(max(1, repeat)):
+        H.barrier()
+        e0.record(H.ext)
+        pb.solve_DiffusionSteadyMono_(s, method="cg", **kw)
+        e1.record(H.ext)
+        H.barrier()
+        ms = H.allmax(e0.elapsed_time(e1))
+        if k == 0:
+            first_ms = ms
+    ch = s.ch[-1]
+    it, dof = int(ch["iters"]), int(ch["dof_bulk"])
+    solve_ms = H.allmax(float(ch["solve_ms"]))
+    cu, cg = int(ch["apply_cells_uniform"]), int(ch["apply_cells_general"])
+    cells = cu + cg
+    # per iteration of the fused CG (DESIGN.md section 5): apply 6 passes + N coefficient arrays on the general tiles, update 3 passes (the byte model of the PLAIN iteration)
+    it_bytes = H.allsum(8.0 * (9 * cells + 3 * cg))
+    agg = it_bytes * it / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 and precond != "mg" else None
+    T = s.x[:n]
+    out = {"workload": "steady Poisson 3-D, union of random disjoint spheres (fluid outside), f = 1, Dirichlet 0 on interface and borders (BASELINE.json configs[4])",
+           "grid": [nx, nx, nx], "spheres": int(spheres), "seed": POISSON_SEED, "n_gpus": N, "dof": dof, "rtol": rtol,
+           "krylov": "CG on the folded (block-Jacobi-scaled) system, " + ("multigrid V-cycle preconditioner (levels rediscretised by the capacity kernels, cell-aggregation transfers, "
+                                                                         "Chebyshev smoothers)" if precond == "mg" else "no multigrid"),
+           "iterations": it, "converged": bool(ch["converged"]), "final_rel_residual": ch["rnorm"] / ch["bnorm"] if ch["bnorm"] else 0.0,
+           "time_to_tolerance_ms": ms, "first_solve_ms_incl_setup": first_ms, "krylov_loop_ms": solve_ms, "prologue_ms": H.allmax(float(ch["setup_ms"])), "capacity_build_s": cap_s,
+           "ms_per_iteration": solve_ms / max(it, 1), "dof_iterations_per_s": dof * it / (solve_ms * 1e-3) if solve_ms > 0 else 0.0,
+           "plain_iteration_algorithmic_bytes_all_ranks": it_bytes, "aggregate_gbs": agg, "frac_of_measured_hbm": agg / (N * peak) if agg else None, "peak_source": peak_src,
+           "cells_constant_coef_tiles_rank0": cu, "cells_streamed_coef_tiles_rank0": cg, "launches": int(ch["launches"]),
+           "max_T_rank0": float(T.max()), "min_T_rank0": float(T.min())}
+    del s, phase, cap
+    return out
+
+
 def run_gpu(args):
     H = Harness(args)
     torch, pb, L, lib, ctx = H.torch, H.pb, H.L, H.lib, H.ctx
@@ -495,6 +567,17 @@ def run_gpu(args):
                 extra[key] = {"error": repr(e)[:300]}
                 barrier()
             gc.collect()
+    if not args.no_3d and not args.no_poisson:
+        # configs[4] at a single-GPU size: the plain folded CG and the multigrid-preconditioned one on the same problem (one rank: csrc/mg.cuh)
+        if world == 1:
+            for pre, key in (("default", "poisson3d_steady_cg"), ("mg", "poisson3d_steady_mgcg")):
+                try:
+                    extra[key] = run_poisson3d(H, args.nxpoisson, pre)
+                except Exception as e:
+                    extra[key] = {"error": repr(e)[:300]}
+                gc.collect()
+        else:
+            extra["poisson3d_steady_mgcg"] = {"skipped": "the multigrid preconditioner runs on one rank (the slab decomposition does not coarsen with the grid); tools/run_poisson3d.py --gpus N runs the plain CG on N ranks"}
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
@@ -556,6 +639,8 @@ def main():
     ap.add_argument("--nx3d", type=int, default=1024, help="configs[3]: cells in x and y")
     ap.add_argument("--nz3d", type=int, default=128, help="configs[3]: planes per GPU (128 x 8 GPUs = the 1024^3 north-star problem)")
     ap.add_argument("--nxmono", type=int, default=512, help="configs[2]: cells per direction (strong-scaled)")
+    ap.add_argument("--no-poisson", action="store_true", help="skip the configs[4] workload (steady Poisson around 64 spheres, plain and multigrid-preconditioned CG; N = 1 only)")
+    ap.add_argument("--nxpoisson", type=int, default=384, help="configs[4]: cells per direction")
     ap.add_argument("--steps3d", type=int, default=10)
     ap.add_argument("--warmup3d", type=int, default=3)
     args = ap.parse_args()

@@ -23,16 +23,20 @@ struct MgXfer {
     int ncc[3];                 // real coarse cells per dimension
 };
 
+// local array coordinates of cell k of this thread in bulk tile R (the arithmetic of tile_cell, without the linear index)
+__device__ __forceinline__ void mg_cell_coords(const Items &I, const TileRec &R, int k, int c[3])
+{
+    const int tx = (int)threadIdx.x & ((1 << I.shx) - 1), ty = (int)threadIdx.x >> I.shx;
+    c[0] = R.ox + tx + I.kx * k; c[1] = R.oy + ty * I.tym + I.ky * k; c[2] = R.oz + I.kz * k;
+}
 // r^_c = S_c sum_children r^_f / S_f over the coarse items (inactive cells carry sc = 0 and contribute / receive nothing)
 __global__ void __launch_bounds__(FCH) kf_mg_restrict(Items Ic, MgXfer X, const double *__restrict__ scf, const double *__restrict__ scc, const double *__restrict__ rf,
                                                       double *__restrict__ rc)
 {
     FV_LOOP(Ic) {
         if (f != 0) continue;
-        long long t = i;
         int c[3];
-        c[0] = (int)(t % X.ldc[0]); t /= X.ldc[0];
-        c[1] = (int)(t % X.ldc[1]); c[2] = (int)(t / X.ldc[1]);
+        mg_cell_coords(Ic, R__, k__, c);
         const double sc = scc[i];
         bool real = sc > 0.0;
         for (int d = 0; d < X.N; ++d) { if (d == X.sd) c[d] -= 1; if (c[d] < 0 || c[d] >= X.ncc[d]) real = false; }
@@ -61,10 +65,8 @@ __global__ void __launch_bounds__(FCH) kf_mg_prolong(Items If, MgXfer X, const d
         if (f != 0) continue;
         const double s = scf[i];
         if (!(s > 0.0)) continue;
-        long long t = i;
         int c[3];
-        c[0] = (int)(t % X.ldf[0]); t /= X.ldf[0];
-        c[1] = (int)(t % X.ldf[1]); c[2] = (int)(t / X.ldf[1]);
+        mg_cell_coords(If, R__, k__, c);
         bool real = true;
         for (int d = 0; d < X.N; ++d) { if (d == X.sd) c[d] -= 1; c[d] >>= 1; if (c[d] < 0 || c[d] >= X.ncc[d]) real = false; }
         if (!real) continue;
@@ -107,8 +109,11 @@ struct MgLevel {
 struct MgHier {
     std::vector<MgLevel> lev;
     bool ready = false;
+    cudaGraphExec_t exec = nullptr;    // one MG-PCG iteration (mg_pcg)
+    int64_t graph_launches = 0, graph_applies = 0;
     int deg = 2, coarse_sweeps = 12;
-    double alpha = 8.0, alpha_c = 40.0;
+    double alpha = 3.0, alpha_c = 40.0;
+    double min_res = 1.0;              // coarsen while the smallest ball radius spans at least this many coarse cells (384^3: 1.0 -> 43 iterations, 1.5 -> 55)
 };
 
 static void mg_free(pb200_solver *s)
@@ -121,6 +126,7 @@ static void mg_free(pb200_solver *s)
         for (FVec *v : vs) fold_free_vec(*v);
         if (l > 0) { pb200_solver_destroy(L.s); pb200_ops_destroy(L.ops); pb200_capacity_destroy(L.cap); }
     }
+    if (H->exec) cudaGraphExecDestroy(H->exec);
     delete H;
     s->mg = nullptr;
 }
@@ -181,7 +187,9 @@ static int mg_setup(pb200_solver *s, const ApplyCoef &ac)
     if (getenv("PB200_MG_DEG")) H->deg = atoi(getenv("PB200_MG_DEG")) >= 2 ? 2 : 1;
     if (getenv("PB200_MG_ALPHA")) H->alpha = atof(getenv("PB200_MG_ALPHA"));
     if (getenv("PB200_MG_SWEEPS")) H->coarse_sweeps = atoi(getenv("PB200_MG_SWEEPS"));
-    if (!(H->alpha > 1.5)) H->alpha = 8.0;
+    if (getenv("PB200_MG_ALPHAC")) H->alpha_c = atof(getenv("PB200_MG_ALPHAC"));
+    if (!(H->alpha > 1.5)) H->alpha = 3.0;
+    if (getenv("PB200_MG_RES")) H->min_res = atof(getenv("PB200_MG_RES"));
     int maxlev = getenv("PB200_MG_LEVELS") ? atoi(getenv("PB200_MG_LEVELS")) : 12;
     H->lev.emplace_back();
     H->lev[0].s = s;
@@ -193,7 +201,11 @@ static int mg_setup(pb200_solver *s, const ApplyCoef &ac)
         const Grid &gf = H->lev.back().s->g;
         bool ok = true;
         int n[3] = {1, 1, 1};
-        for (int d = 0; d < gf.N; ++d) { if (gf.nc[d] % 2 || gf.nc[d] / 2 < 4) ok = false; n[d] = gf.nc[d] / 2; }
+        double hc = 0.0;
+        for (int d = 0; d < gf.N; ++d) { if (gf.nc[d] % 2 || gf.nc[d] / 2 < 4) ok = false; n[d] = gf.nc[d] / 2; hc = fmax(hc, 2.0 * gf.h[d]); }
+        // A level whose cells are larger than the bodies misrepresents their Dirichlet condition and HURTS the cycle (measured, 256^3 around 64 spheres of
+        // radius 0.1-0.3: 3 levels 31 iterations, 4 levels 45, 5 levels 62, 7 levels 75): stop while the smallest ball still spans min_res coarse cells.
+        if (ls.kind == PB200_LS_BALLS && !c0->ls_r.empty() && *std::min_element(c0->ls_r.begin(), c0->ls_r.end()) < H->min_res * hc) ok = false;
         if (!ok) break;
         MgLevel L;
         if ((rc = pb200_capacity_create(ctx, gf.N, n, gf.x0, gf.L, &ls, 0, &L.cap))) return rc;
@@ -288,22 +300,47 @@ static int mg_pcg(pb200_solver *s, const pb200_krylov_opts &o, int *iters, int *
     const double tol = fmax(o.rtol * bnorm, o.atol);
     int it = 0, converged = rnorm <= tol ? 1 : 0;
     if (!converged) {
-        if ((rc = mg_vcycle(H, 0, F.r, L0.e))) return rc;
-        kf_dot<<<wave_grid(s, kf_dot), FCH, 0, ctx->stream>>>(I, F.r, L0.e, ctx->d_partials, res + MG_RHO, ctx->d_counter); LAUNCH_CHECK(ctx);
-        kf_mg_p<<<wave_grid(s, kf_mg_p), FCH, 0, ctx->stream>>>(I, res, MG_RHON, MG_RHO, 1, L0.e, F.p); LAUNCH_CHECK(ctx);
-        while (it < o.maxit) {
-            if ((rc = fold_apply(s, F.p, F.v, F.v, 1))) return rc;                          // v = M^ p, (p, v) -> FS_SIG_D
+        // one iteration = z = V(r); rho' = (r, z); p = z + (rho' / rho) p; rho = rho'; v = M^ p; alpha = rho / (p, v); x += alpha p; r -= alpha v; (r, r).
+        // kf_resid has set p = 0 and rho starts at 1, so the first pass forms p = z without a special case: the body is the same every time and
+        // is replayed as ONE CUDA graph from the second iteration on (~100 launches, most of them on tiny coarse levels: pure launch latency).
+        const double one = 1.0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(res + MG_RHO, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        auto body = [&]() -> int {
+            int rc2;
+            if ((rc2 = mg_vcycle(H, 0, F.r, L0.e))) return rc2;
+            kf_dot<<<wave_grid(s, kf_dot), FCH, 0, ctx->stream>>>(I, F.r, L0.e, ctx->d_partials, res + MG_RHON, ctx->d_counter); LAUNCH_CHECK(ctx);
+            kf_mg_p<<<wave_grid(s, kf_mg_p), FCH, 0, ctx->stream>>>(I, res, MG_RHON, MG_RHO, 0, L0.e, F.p); LAUNCH_CHECK(ctx);
+            CUDA_TRY(ctx, cudaMemcpyAsync(res + MG_RHO, res + MG_RHON, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            if ((rc2 = fold_apply(s, F.p, F.v, F.v, 1))) return rc2;                         // v = M^ p, (p, v) -> FS_SIG_D
             kf_mg_xr<<<wave_grid(s, kf_mg_xr), FCH, 0, ctx->stream>>>(I, res, MG_RHO, FS_SIG_D, F.p, F.v, F.x, F.r, ctx->d_partials, res + MG_RR, ctx->d_counter); LAUNCH_CHECK(ctx);
+            return PB200_OK;
+        };
+        const bool use_graph = !ctx->profile && !getenv("PB200_NO_GRAPH");
+        while (it < o.maxit) {
+            if (it == 0 || !use_graph) { if ((rc = body())) return rc; }
+            else {
+                if (!H.exec) {
+                    cudaGraph_t gr = nullptr;
+                    const int64_t l0 = ctx->launches, a0 = ctx->apply_launches;
+                    CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                    const int rcc = body();
+                    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &gr);
+                    if (rcc) { if (gr) cudaGraphDestroy(gr); return rcc; }
+                    CUDA_TRY(ctx, ce);
+                    CUDA_TRY(ctx, cudaGraphInstantiate(&H.exec, gr, 0));
+                    cudaGraphDestroy(gr);
+                    H.graph_launches = ctx->launches - l0; H.graph_applies = ctx->apply_launches - a0;
+                    ctx->launches = l0; ctx->apply_launches = a0;   // capturing launches nothing
+                }
+                CUDA_TRY(ctx, cudaGraphLaunch(H.exec, ctx->stream));
+                ctx->launches += H.graph_launches; ctx->apply_launches += H.graph_applies;
+            }
             ++it;
             if ((rc = fetch_results(ctx, MG_RR, 1, h))) return rc;
             rnorm = sqrt(h[0]);
             if (getenv("PB200_DEBUG")) fprintf(stderr, "[pb200] mg-pcg it %d rnorm %.3e tol %.3e\n", it, rnorm, tol);
             if (rnorm <= tol) { converged = 1; break; }
             if (!(rnorm == rnorm)) break;
-            if ((rc = mg_vcycle(H, 0, F.r, L0.e))) return rc;
-            kf_dot<<<wave_grid(s, kf_dot), FCH, 0, ctx->stream>>>(I, F.r, L0.e, ctx->d_partials, res + MG_RHON, ctx->d_counter); LAUNCH_CHECK(ctx);
-            kf_mg_p<<<wave_grid(s, kf_mg_p), FCH, 0, ctx->stream>>>(I, res, MG_RHON, MG_RHO, 0, L0.e, F.p); LAUNCH_CHECK(ctx);
-            CUDA_TRY(ctx, cudaMemcpyAsync(res + MG_RHO, res + MG_RHON, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
     *iters = it; *conv = converged; *rnorm_out = rnorm; *bnorm_out = bnorm;

@@ -37,8 +37,9 @@ def test_steady_poisson_multi_sphere_3d(pb, path):
     assert np.all(s.x[:nn][cap_o.V == 0] == 0.0)                     # removed DOFs are exact zeros
 
 
-def test_steady_poisson_multigrid_3d(pb):
+def test_steady_poisson_multigrid_3d(pb, monkeypatch):
     """the same problem through the multigrid-preconditioned CG (csrc/mg.cuh: levels 16^3, 8^3, 4^3 rebuilt from the level set): same solution, fewer iterations"""
+    monkeypatch.setenv("PB200_MG_RES", "0")          # coarsen all the way (by default a level whose cells outgrow the spheres is not built: 16^3 would stay alone)
     n, L, cen, rad = small_case()
     mesh_o, cap_o, so = oracle_solution(n, L, cen, rad)
     mesh = pb.Mesh(n, L)
