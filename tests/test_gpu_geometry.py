@@ -6,6 +6,8 @@ Bar (BASELINE.json north_star): cut/solid/fluid classification bit-exact; capaci
 "Relative" is taken against the natural magnitude of each array (h^N for V and W, the face measure for A and B,
 h^(N-1) for Gamma, h for centroids): a near-empty cut cell has no meaningful relative error of its own.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -24,8 +26,10 @@ def pb():
     return penguin_b200
 
 
-def _chk(errs, name, a, b, bound):
+def _chk(errs, name, a, b, bound, scale=None):
     d = np.abs(np.asarray(a) - np.asarray(b))
+    if os.environ.get("PB200_GEOM_REPORT") and d.size and scale:      # measured agreement in units of the array's natural magnitude (pytest -s)
+        print(f"GEOMREPORT {name.split('[')[0].split('(')[0].strip():10s} {'near-empty' if 'near-empty' in name or 'all' in name else 'regular':10s} {d.max() / scale:.3e} (bound {bound / scale:.1e})")
     if d.size and d.max() > bound:
         i = np.unravel_index(int(np.argmax(d)), d.shape)
         errs.append(f"{name}: max |dev - oracle| = {d.max():.3e} > {bound:.3e} at {i}: dev {np.asarray(a)[i]!r} oracle {np.asarray(b)[i]!r}")
@@ -40,25 +44,27 @@ def _compare(pb, n, L, body, x0=None, tol=TOL):
     vol = float(np.prod(h))
     assert np.array_equal(cg.cell_types, co.cell_types), "classification must be bit-exact"
     errs = []
-    _chk(errs, "V", cg.V, co.V, tol * vol)
+    _chk(errs, "V", cg.V, co.V, tol * vol, vol)
     gsc = vol / min(h)
-    _chk(errs, "Gamma", cg.Γ, co.Gamma, tol * gsc)
+    _chk(errs, "Gamma", cg.Γ, co.Gamma, tol * gsc, gsc)
     for d in range(N):
         face = vol / h[d]
-        _chk(errs, f"A[{d}]", cg.A[d], co.A[d], tol * face)
-        # B (section through the barycentre) and W (box between barycentres) inherit the conditioning of the barycentre, a
-        # quotient by V: 1e-12-level agreement where the cell carries fluid, looser in near-empty cut cells
+        _chk(errs, f"A[{d}]", cg.A[d], co.A[d], tol * face, face)
+        # B (section through the barycentre) and W (box between barycentres) inherit the conditioning of the barycentre, a quotient by V.
+        # Measured over every case of this file (PB200_GEOM_REPORT=1, profiles/r2_geom_agreement.log), in units of the array's magnitude:
+        # V 6e-15, A 4e-15, Gamma 2e-14, W 2.0e-13, B 3.4e-12 where the cell carries fluid and 1.2e-10 in near-empty cut cells (V < 1e-3 h^N),
+        # C_omega 1.3e-12 (near-empty: 1.2e-8), C_gamma 4.5e-13 -- the bounds below are those numbers with a margin of 5-10, W at the 1e-12 bar
         okc = (co.V > 1e-3 * vol) | (co.cell_types != -1.0)
-        _chk(errs, f"B[{d}]", cg.B[d][okc], co.B[d][okc], 50 * tol * face)
-        _chk(errs, f"B[{d}] (near-empty cells)", cg.B[d], co.B[d], 1e-8 * face)
-        _chk(errs, f"W[{d}]", cg.W[d], co.W[d], 1e-9 * vol)
+        _chk(errs, f"B[{d}]", cg.B[d][okc], co.B[d][okc], 20 * tol * face, face)
+        _chk(errs, f"B[{d}] (near-empty cells)", cg.B[d], co.B[d], 1e-9 * face, face)
+        _chk(errs, f"W[{d}]", cg.W[d], co.W[d], tol * vol, vol)
     # centroids: compare where the cell carries enough fluid / interface for the quotient to be conditioned
     big = co.V > 1e-3 * vol
-    _chk(errs, "C_omega(big cells)", cg.C_ω[big], co.C_omega[big], 1e3 * tol * max(h))
-    _chk(errs, "C_omega(all)", cg.C_ω, co.C_omega, 1e-7 * max(h))
+    _chk(errs, "C_omega(big cells)", cg.C_ω[big], co.C_omega[big], 10 * tol * max(h), max(h))
+    _chk(errs, "C_omega(all)", cg.C_ω, co.C_omega, 1e-7 * max(h), max(h))
     bigg = co.Gamma > 1e-2 * gsc
     if bigg.any():
-        _chk(errs, "C_gamma", cg.C_γ[bigg], co.C_gamma[bigg], 1e3 * tol * max(h))
+        _chk(errs, "C_gamma", cg.C_γ[bigg], co.C_gamma[bigg], 5 * tol * max(h), max(h))
     assert not errs, "\n".join(errs)
     # the reference's own structural pins (test/capacity_test.jl:256-257): cut <=> Gamma > 0
     assert np.array_equal(cg.cell_types == -1.0, cg.Γ > 0.0)
