@@ -75,10 +75,17 @@ def build(levels, m=2, alpha=8.0, pconst=True):
     return H
 
 
-def vcycle(H, q, rh, omega_c=1.0):
-    """in hat variables of level q: returns zh ~ Mh^-1 rh"""
+def vcycle(H, q, rh, omega_c=1.0, coarse_sweeps=None, alpha_c=40.0):
+    """in hat variables of level q: returns zh ~ Mh^-1 rh.  coarse_sweeps = None: exact coarsest solve (sparse LU); an integer: what csrc/mg.cuh does --
+    one degree-2 Chebyshev polynomial on [hi / alpha_c, hi] from a zero guess followed by that many residual-correction sweeps with the same polynomial"""
     L = H[q]
     if q == len(H) - 1:
+        if coarse_sweeps is not None:
+            sm = L.setdefault("smc", cheb(L["Mh"], L["hi"] / alpha_c, L["hi"], 2))
+            z = sm(rh)
+            for _ in range(coarse_sweeps):
+                z = z + sm(rh - L["Mh"] @ z)
+            return z
         import scipy.sparse.linalg as spla
         if "lu" not in L:
             L["lu"] = spla.splu(L["Mh"].tocsc())
@@ -87,7 +94,7 @@ def vcycle(H, q, rh, omega_c=1.0):
     res = rh - L["Mh"] @ z
     C = H[q + 1]
     rc = C["s"] * (L["P"].T @ (res / L["s"]))                 # r = S^-1 r^ (true residual); coarse r^_c = S_c r_c
-    ec = vcycle(H, q + 1, rc, omega_c)
+    ec = vcycle(H, q + 1, rc, omega_c, coarse_sweeps, alpha_c)
     z = z + omega_c * (L["P"] @ (C["s"] * ec)) / L["s"]         # x = S x^ ; x^ = x / S
     res = rh - L["Mh"] @ z
     return z + L["sm"](res)
