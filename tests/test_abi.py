@@ -95,3 +95,21 @@ def test_polynomial_preconditioner_coefficients():
     lam = np.linspace(0.01, hi, 200)
     assert np.all(c[0] + c[2] * lam > 0)
     assert _lib.lib().pb200_poly_coefs(1.0, 0.5, ctypes.cast(out, _lib.dp)) != 0
+
+
+def test_krylov_opts_mirror_maps_the_preconditioner():
+    # pb200_krylov_opts.precond (include/penguin_b200.h): the Python mirror's `precond="mg"` and the Julia shim's `precond=:mg` select PB200_PRECOND_MG
+    from penguin_b200 import api
+    hdr = open(os.path.join(ROOT, "include", "penguin_b200.h")).read()
+    assert re.search(r"#define\s+PB200_PRECOND_DEFAULT\s+0\b", hdr) and re.search(r"#define\s+PB200_PRECOND_MG\s+1\b", hdr)
+    o = api._krylov_opts("cg", dict(precond="mg", reltol=1e-9))
+    assert (o.precond, o.method, o.rtol) == (1, 1, 1e-9)
+    assert api._krylov_opts("cg", {}).precond == 0
+    with pytest.raises(KeyError):
+        api._krylov_opts("cg", dict(precond="ilu"))
+    jl = open(os.path.join(ROOT, "julia", "b200.jl")).read()
+    fields = re.search(r"struct pb200_krylov_opts\s*\n\s*(.*?)\nend", jl, flags=re.S).group(1)
+    names_jl = re.findall(r"(\w+)::C", fields)
+    block = re.search(r"typedef struct \{([^}]*)\}\s*pb200_krylov_opts;", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S), flags=re.S).group(1)
+    names_h = re.findall(r"\b(?:int|double)\s+(\w+)\s*;", block)
+    assert names_jl == names_h == [f[0] for f in api.L.KrylovOpts._fields_]
