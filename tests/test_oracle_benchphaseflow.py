@@ -68,3 +68,86 @@ def test_neumann_mass_conservation():
     assert len(masses) == po.n_solves(dt, 0.1)
     assert np.max(np.abs(masses - masses[0])) < 1e-10
     assert abs(masses[0] - np.pi * 0.25 ** 2) < 1e-12            # V . 1 = area of the disc
+
+
+def test_heat_2d_dirichlet_order():
+    # Scalar_2D_Diffusion_Heat_Dirichlet.jl:22-52,70-100,135-147,158-160: disc r = 1 centre (2.01, 2.01), interface Dirichlet 1, borders Dirichlet 0, u0 = 0,
+    # BE constructor then CN loop, dt = 0.5 h^2, T_end = 0.1, against the Bessel series at t = 0.1; meshes 4 .. 64; `@test orders.all > 1.0`
+    from scipy.special import j0, j1, jn_zeros
+    c, R, t_end = (2.01, 2.01), 1.0, 0.1
+    al = jn_zeros(0, 200)
+
+    def u_ana(x, y):
+        r = np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2)
+        s = np.sum(np.exp(-al[None, :] ** 2 * t_end) * j0(al[None, :] * (r[:, None] / R)) / (al[None, :] * j1(al[None, :])), axis=1)
+        return np.where(r >= R, 0.0, 1.0 - 2.0 * s)
+    hs, errs = [], []
+    for nx in (4, 8, 16, 32, 64):
+        mesh = po.Mesh((nx, nx), (4.0, 4.0))
+        cap = geom.capacity(mesh, geom.LevelSet.ball(c, R))
+        ph = po.Phase(cap, po.DiffusionOps(cap), (lambda x, y, z, t: 0.0 * x), 1.0)
+        bc_b = po.BorderConditions({k: po.Dirichlet(0.0) for k in ("left", "right", "top", "bottom")})
+        dt = 0.5 * (4.0 / nx) ** 2
+        s = po.DiffusionUnsteadyMono(ph, bc_b, po.Dirichlet(1.0), dt, np.zeros(2 * mesh.n), "BE")
+        po.solve_DiffusionUnsteadyMono(s, ph, dt, t_end, bc_b, po.Dirichlet(1.0), "CN")
+        hs.append(4.0 / nx)
+        errs.append(po.check_convergence(u_ana, s.x, cap, 2, False)[0])
+    assert fitted_order(hs, errs) > 1.0
+    assert min(errs) < max(errs)
+
+
+def heat2ph2d_exact(center, R, t_end, Dg=1.0, Dl=1.0, He=1.0, cg0=1.0, nq=3000):
+    """diphasic/Heat_2ph_2D.jl:39-93: the Bessel-integral solution of the circular two-phase heat problem at t_end (phase 1 inside, phase 2 outside), with the
+    script's cut-off Umax = 5 / sqrt(Dg t_end); Gauss-Legendre in u for all points at once instead of one adaptive quadgk per point"""
+    from scipy.special import j0, j1, y0, y1
+    umax = 5.0 / np.sqrt(Dg * t_end)
+    xg, wg = np.polynomial.legendre.leggauss(nq)
+    u, w = 0.5 * umax * (xg + 1.0), 0.5 * umax * wg
+    D = np.sqrt(Dg / Dl)
+    phi = Dg * np.sqrt(Dl) * j1(u * R) * y0(D * u * R) - He * Dl * np.sqrt(Dg) * j0(u * R) * y1(D * u * R)
+    psi = Dg * np.sqrt(Dl) * j1(u * R) * j0(D * u * R) - He * Dl * np.sqrt(Dg) * j0(u * R) * j1(D * u * R)
+    den = phi ** 2 + psi ** 2
+    e = np.exp(-Dg * u ** 2 * t_end) * j1(u * R)
+
+    def u1(x, y):
+        r = np.hypot(x - center[0], y - center[1])
+        val = (j0(u[None, :] * r[:, None]) * (e / (u ** 2 * den))[None, :]) @ w
+        return np.where(r >= R, 0.0, 4.0 * cg0 * Dg * Dl ** 2 * He / (np.pi ** 2 * R) * val)
+
+    def u2(x, y):
+        r = np.hypot(x - center[0], y - center[1])
+        rr = np.maximum(r, 1e-12)
+        contrib = j0(D * u[None, :] * rr[:, None]) * phi[None, :] - y0(D * u[None, :] * rr[:, None]) * psi[None, :]
+        val = (contrib * (e / (u * den))[None, :]) @ w
+        return np.where(r < R, 0.0, 2.0 * cg0 * Dg * np.sqrt(Dl) * He / np.pi * val)
+    return u1, u2
+
+
+def test_heat_2ph_2d_against_the_bessel_solution():
+    # diphasic/Heat_2ph_2D.jl:94-160,216-231 -- the problem BASELINE.json configs[1] is quoted on (benchmark/Heat_2ph_2D.jl): [0, 8]^2, circle r = 2 centre (4, 4),
+    # ScalarJump(1, He = 1, 0), FluxJump(1, 1, 0), u0 = [1, 1, 0, 0], no border conditions, BE constructor then CN, dt = 0.5 h^2, T_end = 0.1;
+    # error = max over the phases of the volume-weighted L2 norm (src/convergence.jl:114-237).  The script asserts a fit that is not NaN and errors that
+    # vary with the mesh; the oracle shows more: the errors FALL with h, at an order above 1 (meshes 8 .. 64 of the script's 4 .. 128)
+    c, R, t_end = (4.0, 4.0), 2.0, 0.1
+    u1, u2 = heat2ph2d_exact(c, R, t_end)
+    hs, errs = [], []
+    for nx in (8, 16, 32, 64):
+        mesh = po.Mesh((nx, nx), (8.0, 8.0))
+        ls = geom.LevelSet.ball(c, R)
+        c1, c2 = geom.capacity(mesh, ls), geom.capacity(mesh, ls.flipped())
+        f = lambda x, y, z, t: 0.0 * x
+        p1, p2 = po.Phase(c1, po.DiffusionOps(c1), f, 1.0), po.Phase(c2, po.DiffusionOps(c2), f, 1.0)
+        ic = po.InterfaceConditions(po.ScalarJump(1.0, 1.0, 0.0), po.FluxJump(1.0, 1.0, 0.0))
+        n = mesh.n
+        u0 = np.concatenate([np.ones(2 * n), np.zeros(2 * n)])
+        dt = 0.5 * (8.0 / nx) ** 2
+        s = po.DiffusionUnsteadyDiph(p1, p2, po.BorderConditions(), ic, dt, u0, "BE")
+        po.solve_DiffusionUnsteadyDiph(s, p1, p2, dt, t_end, po.BorderConditions(), ic, "CN")
+        x = s.states[-1]
+        e1 = po.check_convergence(u1, x[:n], c1, 2, False)[0]
+        e2 = po.check_convergence(u2, x[2 * n:3 * n], c2, 2, False)[0]
+        hs.append(8.0 / nx)
+        errs.append(max(e1, e2))
+    order = fitted_order(hs, errs)
+    assert not np.isnan(order) and min(errs) < max(errs)           # the script's asserts
+    assert all(b < a for a, b in zip(errs, errs[1:])) and order > 1.0, (errs, order)
