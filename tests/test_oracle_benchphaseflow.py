@@ -151,3 +151,21 @@ def test_heat_2ph_2d_against_the_bessel_solution():
     order = fitted_order(hs, errs)
     assert not np.isnan(order) and min(errs) < max(errs)           # the script's asserts
     assert all(b < a for a, b in zip(errs, errs[1:])) and order > 1.0, (errs, order)
+
+
+def test_poisson_1d_dirichlet_order():
+    # Scalar_1D_Diffusion_Poisson_Dirichlet.jl:37-49,96-110,116-118: interval |x - 0.5| < 0.11 of [0, 1], f = x, Dirichlet 0 on the interface points and on
+    # :top / :bottom, u = -(x-c)^3/6 - c (x-c)^2/2 + R^2 (x-c)/6 + c R^2/2; meshes 2 .. 256; `@test orders.all > 1.0`
+    c, R = 0.5, 0.11
+    u = lambda x: -(x - c) ** 3 / 6 - c * (x - c) ** 2 / 2 + R * R / 6 * (x - c) + c * R * R / 2
+    hs, errs = [], []
+    for nx in (2, 4, 8, 16, 32, 64, 128, 256):
+        mesh = po.Mesh((nx,), (1.0,))
+        cap = geom.capacity(mesh, geom.LevelSet.ball((c,), R))
+        ph = po.Phase(cap, po.DiffusionOps(cap), (lambda x, y, z: x), 1.0)
+        bc_b = po.BorderConditions({"top": po.Dirichlet(0.0), "bottom": po.Dirichlet(0.0)})
+        s = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(ph, bc_b, po.Dirichlet(0.0)))
+        hs.append(1.0 / nx)
+        errs.append(po.check_convergence(u, s.x, cap, 2, False)[0])
+    assert fitted_order(hs, errs) > 1.0
+    assert min(errs) < max(errs)
