@@ -169,3 +169,60 @@ def test_poisson_1d_dirichlet_order():
         errs.append(po.check_convergence(u, s.x, cap, 2, False)[0])
     assert fitted_order(hs, errs) > 1.0
     assert min(errs) < max(errs)
+
+
+def test_heat_3d_dirichlet_order():
+    # Scalar_3D_Diffusion_Heat_Dirichlet.jl:21-59,83-111,151-161,171-173: ball r = 1 centre (2, 2, 2) in [0, 4]^3, interface Dirichlet 1 (border keys: Dirichlet 1,
+    # :front / :back never match), u0 = 0, BE throughout, dt = 0.25 h^2, T_end = 0.1, against the spherical sine series; meshes 8, 12, 16, 20; `@test orders.all > 1.0`
+    c, R, t_end = (2.0, 2.0, 2.0), 1.0, 0.1
+    nn = np.arange(1, 201)
+    lam = nn * np.pi / R
+
+    def u_ana(x, y, z):
+        r = np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2)
+        rr = np.maximum(r, 1e-12)
+        s = np.sum(((-1.0) ** (nn + 1) / nn)[None, :] * np.sin(lam[None, :] * rr[:, None]) * np.exp(-lam ** 2 * t_end)[None, :], axis=1)
+        return np.where(r >= R, 1.0, 1.0 - (2.0 * R / (np.pi * rr)) * s)
+    hs, errs = [], []
+    for nx in (8, 12, 16, 20):
+        mesh = po.Mesh((nx,) * 3, (4.0,) * 3)
+        cap = geom.capacity(mesh, geom.LevelSet.ball(c, R))
+        ph = po.Phase(cap, po.DiffusionOps(cap), (lambda x, y, z, t: 0.0 * x), 1.0)
+        bc_b = po.BorderConditions({k: po.Dirichlet(1.0) for k in ("left", "right", "top", "bottom")})
+        dt = 0.25 * (4.0 / nx) ** 2
+        s = po.DiffusionUnsteadyMono(ph, bc_b, po.Dirichlet(1.0), dt, np.zeros(2 * mesh.n), "BE")
+        po.solve_DiffusionUnsteadyMono(s, ph, dt, t_end, bc_b, po.Dirichlet(1.0), "BE")
+        hs.append(4.0 / nx)
+        errs.append(po.check_convergence(u_ana, s.x, cap, 2, False)[0])
+    assert fitted_order(hs, errs) > 1.0, (hs, errs)
+    assert min(errs) < max(errs)
+
+
+def test_heat_2d_robin_order():
+    # Scalar_2D_Diffusion_Heat_Robin.jl:20-53,76-100,140-148,159-160: disc r = 1 centre (2.01, 2.01), interface Robin(1, 1, 1), borders Dirichlet 0, u0 = 0,
+    # BE constructor then CN, dt = 0.25 h^2, T_end = 0.1, against the Robin Bessel series (roots of a J1(a) - k R J0(a)); meshes 4 .. 128 (here .. 64); order > 1
+    from scipy.optimize import brentq
+    from scipy.special import j0, j1
+    c, R, t_end, k = (2.01, 2.01), 1.0, 0.1, 1.0
+    eq = lambda a: a * j1(a) - k * R * j0(a)
+    al = np.array([brentq(eq, max((m - 0.25 - 0.5) * np.pi, 1e-6), (m - 0.25 + 0.5) * np.pi) for m in range(1, 201)])
+    An = 2.0 * k * R / ((k * k * R * R + al ** 2) * j0(al))
+
+    def u_ana(x, y):
+        r = np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2)
+        s = np.sum(An[None, :] * np.exp(-al[None, :] ** 2 * t_end / R ** 2) * j0(al[None, :] * (r[:, None] / R)), axis=1)
+        return np.where(r >= R, 0.0, 1.0 - s)
+    hs, errs = [], []
+    for nx in (4, 8, 16, 32, 64):
+        mesh = po.Mesh((nx, nx), (4.0, 4.0))
+        cap = geom.capacity(mesh, geom.LevelSet.ball(c, R))
+        ph = po.Phase(cap, po.DiffusionOps(cap), (lambda x, y, z, t: 0.0 * x), 1.0)
+        bc_b = po.BorderConditions({kk: po.Dirichlet(0.0) for kk in ("left", "right", "top", "bottom")})
+        bci = po.Robin(1.0, 1.0, 1.0)
+        dt = 0.25 * (4.0 / nx) ** 2
+        s = po.DiffusionUnsteadyMono(ph, bc_b, bci, dt, np.zeros(2 * mesh.n), "BE")
+        po.solve_DiffusionUnsteadyMono(s, ph, dt, t_end, bc_b, bci, "CN")
+        hs.append(4.0 / nx)
+        errs.append(po.check_convergence(u_ana, s.x, cap, 2, False)[0])
+    assert fitted_order(hs, errs) > 1.0, (hs, errs)
+    assert min(errs) < max(errs)
