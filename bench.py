@@ -577,7 +577,7 @@ def run_gpu(args):
                     extra[key] = {"error": repr(e)[:300]}
                 gc.collect()
         else:
-            extra["poisson3d_steady_mgcg"] = {"skipped": "the multigrid preconditioner runs on one rank (the slab decomposition does not coarsen with the grid); tools/run_poisson3d.py --gpus N runs the plain CG on N ranks"}
+            extra["poisson3d_steady_mgcg"] = {"skipped": "the multigrid preconditioner runs on one rank (the slab decomposition does not coarsen with the grid); tools/run_poisson3d.py --gpus N (not yet measured) runs the plain CG on N ranks"}
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:

@@ -3,7 +3,7 @@ Dirichlet 0, borders Dirichlet 0 on the six recognised keys, Krylov solve to ||r
 BenchPhaseFlow/problems/scalar/Scalar_3D_Diffusion_Poisson_Dirichlet.jl:43-61 widened to many spheres).
 
     python tools/run_poisson3d.py --nx 256                                   # one GPU
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_poisson3d.py --gpus 8 --nx 1536   # z-slabs, 8 GPUs
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_poisson3d.py --gpus 8 --nx 1536   # z-slabs, 8 GPUs: plain CG only, NOT yet run (no steady solve has been measured on several ranks)
 
 A "step" of this workload is one Krylov iteration (the system has no V/dt shift: kappa = O(n^2), un-multigridded CG needs O(n) iterations), so the
 line reports iterations, time-to-tolerance, DOF*iterations/s and the HBM fraction of the iteration.  Prints one JSON line (not the bench line:
