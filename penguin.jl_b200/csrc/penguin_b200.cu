@@ -2142,6 +2142,9 @@ extern "C" int pb200_solver_step(pb200_solver *s, const pb200_step_in *in, const
     if (o.path == PB200_PATH_FOLDED && !fold_eligible(s))
         return set_err(ctx, PB200_EUNSUPPORTED, "the folded path needs jump / Robin coefficients of one sign (alpha2/alpha1, beta1, beta2 > 0; beta > 0, alpha >= 0)");
     const bool use_fold = o.path != PB200_PATH_GENERIC && fold_eligible(s);
+    if (o.precond != PB200_PRECOND_DEFAULT && o.precond != PB200_PRECOND_MG) return set_err(ctx, PB200_EINVAL, "unknown preconditioner (pb200_krylov_opts.precond)");
+    if (o.precond == PB200_PRECOND_MG && !use_fold)   // never a silent fall-back to the plain iteration
+        return set_err(ctx, PB200_EUNSUPPORTED, "the multigrid preconditioner belongs to the folded path (PB200_PATH_AUTO / PB200_PATH_FOLDED on an eligible system)");
     // AUTO: the folded system is symmetric positive definite for mono AND diphasic problems, so CG (one operator apply per
     // iteration) is the cheaper choice there; the reference's rows of the diphasic system are not symmetric => BiCGSTAB.
     const bool advect = s->p1.kd || s->p2.kd;   // ConvectionOps: non-symmetric rows (gmres in the reference, src/solver/advectiondiffusion.jl:61) -> BiCGSTAB

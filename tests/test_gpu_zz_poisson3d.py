@@ -84,6 +84,10 @@ def test_multigrid_refuses_what_it_cannot_do(pb):
     s = pb.DiffusionSteadyMono(ph, pb.BorderConditions(), pb.Dirichlet(0.0))
     with pytest.raises(Exception):
         pb.solve_DiffusionSteadyMono_(s, method="cg", path="folded", precond="mg")
+    with pytest.raises(Exception):                      # the generic path has no multigrid: refused, not ignored
+        pb.solve_DiffusionSteadyMono_(s, method="cg", path="generic", precond="mg")
+    pb.solve_DiffusionSteadyMono_(s, method="cg", path="generic", reltol=1e-12)      # the solver object survives both refusals
+    assert rel_l2(s.x, so.x) < 1e-9
 
 
 def test_diphasic_3d_on_device_built_capacities(pb):
