@@ -287,3 +287,22 @@ def test_heat_2ph_1d_henry_100():
     order = fitted_order(hs, errs)
     assert not np.isnan(order) and min(errs) < max(errs), (errs, order)
     assert errs[-1] < 0.05 * errs[0], errs                 # (beyond the script's asserts: the oracle does converge to the similarity solution)
+
+
+def test_johansen_colella_problem4():
+    # johansenColella/Problem4_SchwartzColella_Poisson3D.jl:20-31,49-72,113-131: -lap(phi) = 14 sin x sin 2y sin 3z inside the sphere r = 0.392 centre (1/2, 1/2, 1/2) of
+    # the unit cube, phi = sin x sin 2y sin 3z imposed at the interface CENTROIDS (a function-valued Dirichlet: build_g_g, src/solver.jl:309-323); meshes 8 .. 64 (here
+    # .. 32); asserts: the fit is not NaN, errors vary with the mesh.  The oracle also shows second-order behaviour.
+    fe = lambda x, y, z: np.sin(x) * np.sin(2 * y) * np.sin(3 * z)
+    hs, errs = [], []
+    for nx in (8, 16, 32):
+        mesh = po.Mesh((nx,) * 3, (1.0,) * 3)
+        cap = geom.capacity(mesh, geom.LevelSet.ball((0.5, 0.5, 0.5), 0.392))
+        ph = po.Phase(cap, po.DiffusionOps(cap), (lambda x, y, z: 14.0 * fe(x, y, z)), 1.0)
+        bc_b = po.BorderConditions({k: po.Dirichlet(0.0) for k in ("left", "right", "top", "bottom")})
+        s = po.solve_DiffusionSteadyMono(po.DiffusionSteadyMono(ph, bc_b, po.Dirichlet(fe)))
+        hs.append(1.0 / nx)
+        errs.append(po.check_convergence(fe, s.x, cap, 2, False)[0])
+    order = fitted_order(hs, errs)
+    assert not np.isnan(order) and min(errs) < max(errs)
+    assert order > 1.5, (errs, order)
